@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py — EM iterations/s of the EMSAR quantification hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference arm: CPU EM (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): synthetic human-scale SE rsh index — 200K transcripts, ~2M rsh classes,
+30M reads, -k 100 — one sample per GPU (samples are independent: -M sharding, no collective, weak scaling).
+A step = `--em-iters` EM iterations over the resident packed sample. `value` = EM iterations/s summed over
+ranks; `e2e` = the same metric through the C ABI with HOST buffers (pinned read lists H2D, counting, model
+build, the same number of EM iterations, results D2H) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (index kwargs, reads)
+    "config2_human_se": (dict(T=200000, n_multi=2100000, alpha=2.4, kmax=99, module_cap=5000), 30_000_000),
+    "small": (dict(T=20000, n_multi=200000, alpha=2.4, kmax=99, module_cap=500), 3_000_000),
+    "tiny": (dict(T=2000, n_multi=20000, alpha=2.4, kmax=40, module_cap=200), 200_000),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.rows = gpu, threading.Event(), []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_workload(name, seed):
+    from emsar_b200 import synth
+    kw, n_reads = WORKLOADS[name]
+    t0 = time.time()
+    idx = synth.make_index(seed=2, **kw)                 # one index shared by every sample / rank
+    reads = synth.make_reads(idx, n_reads, seed=seed)    # this rank's sample
+    return idx, reads, time.time() - t0
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path: no EM exists in parklab/emsar, so the
+    metric 'EM iterations/s' is timed on the oracle port (same update as the CUDA kernel) with all host threads;
+    oracle/_ref/emsar (the real binary) is timed on a scaled twin for the samples/min context figure."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    idx, reads, gen_s = make_workload(args.workload, seed=1000)
+    cores = os.cpu_count() or 1
+    R, F, N = oracle.count(idx, reads)
+    Wf, adj, ps, iE = oracle.prepare(idx, F, N)
+    one = oracle.em_time(idx, R, ps, 2, cores) / 2
+    iters = max(2, min(args.em_iters, int(4.0 / max(one, 1e-6))))       # bounded sample: ~4 s of CPU work per step
+    for _ in range(args.warmup):
+        oracle.em_time(idx, R, ps, 1, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += oracle.em_time(idx, R, ps, iters, cores)
+    v = args.steps * iters / t
+    line = {"impl": "reference", "metric": "em_iterations_per_sec", "value": v, "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "T": idx.T, "C": idx.C, "reads": int(N), "em_iters_per_step": iters},
+            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
+                             "sample": f"{iters} EM iterations per step of the full {args.workload} model, pthread team of {cores}"},
+            "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2_human_se", choices=list(WORKLOADS))
+    ap.add_argument("--em-iters", type=int, default=2000, help="EM iterations per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-converge", action="store_true", help="skip the one-off run to convergence (samples/min)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from emsar_b200.api import Context, Index
+
+    idx, reads, gen_s = make_workload(args.workload, seed=1000 + rank)
+    ctx = Context(local)
+    ix = Index(ctx, idx)
+    # pinned host copies of this rank's read lists (the e2e leg copies them every step)
+    h_ptr = torch.from_numpy(reads.read_ptr).pin_memory()
+    h_tid = torch.from_numpy(reads.read_tid).pin_memory()
+    h_fl = torch.from_numpy(reads.read_fraglen).pin_memory()
+    h2d_bytes = h_ptr.numel() * 8 + h_tid.numel() * 4 + h_fl.numel() * 4
+    # resident sample for the device-timed leg
+    smp = ix.sample()
+    smp.count(h_ptr, h_tid, h_fl)
+    smp.prepare()
+    st = smp.model_stats()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def step_resident():
+        flush.zero_()                      # L2 flush between steps (torch stream), then the EM loop (library stream)
+        torch.cuda.synchronize()
+        it, fd, ms = smp.em_run(max_iter=args.em_iters, stop_on_conv=False, reset_theta=True)
+        return it, ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = ctx.launches()
+    t0 = time.perf_counter()
+    iters_done, em_ms = 0, 0.0
+    for _ in range(args.steps):
+        it, ms = step_resident()
+        iters_done += it
+        em_ms += ms
+    barrier()
+    t1 = time.perf_counter()
+    launches = ctx.launches() - l0
+    wall = t1 - t0
+    # device time of the EM kernel alone (CUDA events on the library's stream) -> roofline
+    t_em = em_ms / 1e3
+
+    # ---- e2e leg: host buffers through the C ABI ----
+    def step_e2e():
+        s = ix.sample()
+        s.count(h_ptr, h_tid, h_fl)
+        s.prepare()
+        it, fd, ms = s.em_run(max_iter=args.em_iters, stop_on_conv=False)
+        r = s.finalize()
+        s.close()
+        return it, r
+
+    step_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    e_iters = 0
+    for _ in range(args.steps):
+        it, r = step_e2e()
+        e_iters += it
+    barrier()
+    e1 = time.perf_counter()
+    e_wall = e1 - e0
+    d2h_bytes = idx.T * (8 * 4 + 4)
+
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    # ---- one sample to convergence (samples/min context) ----
+    conv = None
+    if not args.no_converge:
+        barrier()
+        c0 = time.perf_counter()
+        s = ix.sample()
+        s.count(h_ptr, h_tid, h_fl)
+        r = s.solve()
+        s.close()
+        c1 = time.perf_counter()
+        conv = {"seconds": c1 - c0, "n_iter": int(r["n_iter"]), "final_delta": float(r["final_delta"]), "em_ms": float(r["em_ms"]),
+                "prep_ms": float(r["prep_ms"])}
+
+    # ---- reduce over ranks: max time, summed work ----
+    if world > 1:
+        tt = torch.tensor([wall, e_wall, t_em], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall, e_wall, t_em = tt.tolist()
+        ww = torch.tensor([iters_done, e_iters, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        iters_tot, e_iters_tot, launches_tot = ww.tolist()
+    else:
+        iters_tot, e_iters_tot, launches_tot = iters_done, e_iters, launches
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = st["bytes_per_iter"] * iters_done / t_em / 1e9 if t_em > 0 else 0.0
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle
+            cores = os.cpu_count() or 1
+            R, F, N = smp.counts()
+            Wf, adj, ps, iE = oracle.prepare(idx, F, N)
+            one = oracle.em_time(idx, R, ps, 2, cores) / 2
+            n_it = max(2, int(10.0 / max(one, 1e-6)))
+            n_it = min(n_it, 2000)
+            sec = oracle.em_time(idx, R, ps, n_it, cores)
+            cpu = {"value": n_it / sec, "unit": "iterations/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_it} EM iterations of the same packed sample ({sec:.1f} s), pthread team of {cores}"}
+        line = {
+            "metric": "em_iterations_per_sec", "value": iters_tot / wall, "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "T": idx.T, "C": idx.C, "reads_per_sample": int(len(reads.read_fraglen)),
+                       "C_a": st["C_a"], "nnz_a": st["nnz_a"], "em_iters_per_step": args.em_iters, "samples": world,
+                       "parallelism": f"sample-sharded x{world} (-M), no collective",
+                       "l2": "flushed between steps (256 MiB memset); iterations inside a step reuse L2 as the production loop does"},
+            "e2e": {"value": e_iters_tot / e_wall, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": 1e3 * e_wall / args.steps},
+            "gpu_launches": int(launches_tot),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "k_em_persistent", "bytes_per_iter": st["bytes_per_iter"],
+                         "us_per_iter": 1e6 * t_em / max(iters_done, 1)},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+            "to_convergence": conv,
+            "model": st, "gen_seconds": gen_s,
+        }
+        print(json.dumps(line), flush=True)
+    smp.close()
+    ix.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+// Internal declarations shared by the translation units of libemsar_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "emsar_cuda.h"
+
+void emsar_set_err(const char *fmt, ...);
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            emsar_set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            return EMSAR_ERR_CUDA;                                                                  \
+        }                                                                                           \
+    } while (0)
+
+#define CHECK_ARG(cond, ...)                                                                        \
+    do {                                                                                            \
+        if (!(cond)) { emsar_set_err(__VA_ARGS__); return EMSAR_ERR_BAD_ARG; }                      \
+    } while (0)
+
+#define TRY(call)                                                                                   \
+    do { int rc_ = (call); if (rc_ != EMSAR_OK) return rc_; } while (0)
+
+// ---- tunables of the EM kernels ---------------------------------------------------------------------
+#ifndef EM_BLOCK
+#define EM_BLOCK 512          // threads per CTA of the persistent EM kernel
+#endif
+#ifndef EM_MIN_BLOCKS
+#define EM_MIN_BLOCKS 3       // launch-bounds hint: resident CTAs per SM (caps registers)
+#endif
+constexpr int EM_WARPS = EM_BLOCK / 32;
+constexpr int KT = 8;             // classes with cardinality <= KT: thread-per-class, tile-transposed tids
+constexpr int KSUB = 32;          // KT < k <= KSUB: 8 lanes per class; k > KSUB: warp per class
+constexpr int E_TILE_TARGET = 256; // target gathers per warp tile for the long-class modes
+constexpr int M_SHORT_MAX = 128;  // transposed rows with <= this many active entries are "short" (smem-staged)
+constexpr int M_WINDOW = 128;     // cost window of a short-row tile (cost = entries + M_ROW_COST per row)
+constexpr int M_ROW_COST = 2;
+constexpr int M_TILE_SMEM = M_WINDOW + M_SHORT_MAX + M_ROW_COST; // doubles of staging per warp (upper bound)
+constexpr int M_HUB_MIN = 4096;   // rows with more active entries are reduced by a whole CTA
+
+struct KSeg {          // multi-tid classes of one cardinality, contiguous in cid order
+    int32_t k;
+    int64_t cid0, cid1;
+};
+
+struct emsar_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaDeviceProp prop;
+    int64_t launches;
+    int em_blocks_per_sm;
+    unsigned *d_barrier;      // [0] arrival count, [1] generation   (persistent-kernel grid barrier)
+    void *d_scratch;          // CUB temp storage (grow-only)
+    size_t scratch_bytes;
+    cudaEvent_t ev0, ev1;
+    size_t l2_persist_bytes;
+};
+
+struct emsar_index {
+    emsar_ctx *ctx;
+    int32_t T;
+    int64_t C, nnz, n_multi, nnz_multi;
+    int32_t nF, min_fl, max_fl, readlength, max_t_size, frag_min, frag_max, max_card;
+    // device
+    uint32_t *d_cls_off;   // [C+1]
+    int32_t *d_cls_tid;    // [nnz]
+    int32_t *d_euma;       // [C*nF]
+    uint8_t *d_has_node;   // [C]
+    uint32_t *d_txm_off;   // [T+1]   transpose of the multi-tid classes, ascending cid, multiplicity kept
+    int32_t *d_txm_cid;    // [nnz_multi]
+    unsigned long long *d_hash; // open addressing: (fingerprint << 32) | (cid + 1), 0 = empty
+    uint64_t hash_mask;
+    int64_t hash_inserted;
+    int64_t *d_kseg_cid0;  // [n_kseg+1] first cid of each cardinality segment (last = C)
+    int32_t *d_kseg_k;     // [n_kseg]
+    std::vector<KSeg> kseg;
+    // host copies kept for the set decomposition (emsar_main.c:411-425)
+    std::vector<uint32_t> h_cls_off;
+    std::vector<int32_t> h_cls_tid;
+    int32_t n_sets_nocut, max_set_tids;
+    int64_t device_bytes;
+};
+
+// per-sample packed model the EM kernel streams (all device pointers)
+struct EmModel {
+    int32_t T;
+    int64_t C_a, nnz_a;
+    // E side
+    int32_t *e_tid;        // packed member tids (tile-transposed for k<=KT, row-major otherwise)
+    int32_t *e_R;          // [C_a] read counts of the active classes
+    int4 *e_tiles;         // {j0, cnt, tid_off, k | mode<<16}
+    int32_t n_etiles;
+    // M side
+    int32_t *m_cls;        // [nnz_a] compact class id per transposed entry (rows in permuted order)
+    uint32_t *row_off;     // [P+1]
+    int32_t *row_t;        // [P]   transcript of permuted row p
+    double2 *row_RsA;      // [P]   {Rs, A} of permuted row p
+    int2 *m_tiles;         // short-row tiles {p0, p1}
+    int32_t n_mtiles;
+    int32_t n_short, n_long, n_hub; // permuted rows: [0,n_short) short, then long, then hub
+    // state
+    double *theta;         // [T]
+    double *q;             // [C_a]
+};
+
+struct emsar_sample {
+    emsar_index *index;
+    emsar_ctx *ctx;
+    // counts
+    int32_t *d_R;          // [C]
+    int32_t *d_hist;       // [max_fl+1]
+    int32_t *d_flags;      // [0] error flags raised by kernels
+    bool have_counts;
+    // staging for host read batches (grow-only)
+    void *d_rd_ptr, *d_rd_tid, *d_rd_fl;
+    size_t cap_rd_ptr, cap_rd_tid, cap_rd_fl;
+    // model
+    bool prepared;
+    int64_t N;
+    double eumacut, delta;
+    int32_t max_sid;
+    double *d_Wf;          // [nF]
+    double *d_adj;         // [C]
+    double *d_amodel;      // [C]  EUMAps if the class is modelled else 0
+    uint8_t *d_in_model;   // [C]
+    std::vector<int32_t> h_CS; // set ids (filled when computed)
+    bool have_CS;
+    double *d_A, *d_Rs, *d_iE; // [T]
+    uint8_t *d_lone;       // [T] 1 = no in-model multi-tid class contains t (the lone-singleton set of MLE())
+    int32_t *d_pos;        // [T] permuted row of transcript t, -1 when A_t == 0
+    double *d_state;       // theta | q (one allocation: one L2 access-policy window)
+    size_t state_bytes;
+    void *d_pack;          // packed model arena
+    size_t pack_bytes;
+    EmModel m;
+    emsar_model_stats stats;
+    // solve bookkeeping
+    int32_t n_iter;
+    double final_delta;
+    double em_ms, prep_ms;
+    emsar_solve_opts opts;
+};
+
+// ---- helpers implemented across the .cu files ---------------------------------------------------
+int ctx_scratch(emsar_ctx *ctx, size_t bytes, void **p);
+template <class T> static inline int dev_alloc(T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) { emsar_set_err("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); return EMSAR_ERR_NOMEM; }
+    *p = (T *)q;
+    return EMSAR_OK;
+}
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+int index_build_hash(emsar_index *ix, const std::vector<uint8_t> &insertable);
+int sample_build_model(emsar_sample *s);
+int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms);
+int em_query_occupancy(emsar_ctx *ctx);
+int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+// order-sensitive, but summable in any order: h(key) = mix(sum_i elem(i, tid_i) + k*phi)
+__device__ __forceinline__ uint64_t key_elem(int i, int tid) { return mix64(((uint64_t)(uint32_t)tid << 32) | (uint32_t)i); }
+__device__ __forceinline__ uint64_t key_finish(uint64_t sum, int k) { return mix64(sum + (uint64_t)k * 0x9E3779B97F4A7C15ULL); }
+#endif

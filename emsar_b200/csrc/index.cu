@@ -1,0 +1,216 @@
+// rsh index on the device: class-major CSR, transpose of the multi-tid classes, cardinality segments,
+// and the open-addressing hash (class key -> cid) that replaces the rshbucket chains
+// (reference emsar.h:76-83,139-145; emsar_functions.c:1334-1347, 1432-1510, 1542-1625).
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+// One thread per multi-tid class: hash the sorted multiset and claim a slot by linear probing.
+// Only "reachable" classes are inserted: a chain node that an earlier node of the same (cardinality,
+// first tid) chain shadows can never be hit by update_rshbucket's walk (:1603-1622).
+__global__ void k_hash_build(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off,
+                             const int32_t *__restrict__ cls_tid, const uint8_t *__restrict__ insertable,
+                             unsigned long long *table, uint64_t mask, unsigned long long *n_inserted)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi) return;
+    if (!insertable[i]) return;
+    int64_t cid = T + i;
+    uint32_t o = cls_off[cid];
+    int k = (int)(cls_off[cid + 1] - o);
+    uint64_t sum = 0;
+    for (int j = 0; j < k; j++) sum += key_elem(j, cls_tid[o + j]);
+    uint64_t h = key_finish(sum, k);
+    unsigned long long entry = ((h >> 32) << 32) | (unsigned long long)(uint32_t)(cid + 1);
+    uint64_t s = h & mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS(&table[s], 0ULL, entry);
+        if (prev == 0ULL) break;
+        s = (s + 1) & mask;
+    }
+    atomicAdd(n_inserted, 1ULL);
+}
+
+int index_build_hash(emsar_index *ix, const std::vector<uint8_t> &insertable)
+{
+    emsar_ctx *ctx = ix->ctx;
+    uint64_t slots = 1024;
+    while (slots < (uint64_t)ix->n_multi * 2) slots <<= 1;
+    ix->hash_mask = slots - 1;
+    TRY(dev_alloc(&ix->d_hash, slots));
+    ix->device_bytes += slots * 8;
+    CU(cudaMemsetAsync(ix->d_hash, 0, slots * 8, ctx->stream));
+    ix->hash_inserted = 0;
+    if (ix->n_multi == 0) return EMSAR_OK;
+    uint8_t *d_ins = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    TRY(dev_alloc(&d_ins, (size_t)ix->n_multi));
+    TRY(dev_alloc(&d_cnt, 1));
+    CU(cudaMemcpyAsync(d_ins, insertable.data(), (size_t)ix->n_multi, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_cnt, 0, 8, ctx->stream));
+    int bs = 256;
+    k_hash_build<<<(unsigned)((ix->n_multi + bs - 1) / bs), bs, 0, ctx->stream>>>(ix->n_multi, ix->T, ix->d_cls_off, ix->d_cls_tid, d_ins,
+                                                                                  ix->d_hash, ix->hash_mask, d_cnt);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ix->hash_inserted = (int64_t)cnt;
+    cudaFree(d_ins);
+    cudaFree(d_cnt);
+    return EMSAR_OK;
+}
+
+static int uf_find(std::vector<int32_t> &p, int x)
+{
+    while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+    return x;
+}
+
+extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, emsar_index **out)
+{
+    CHECK_ARG(ctx && d && out, "emsar_index_create: NULL argument");
+    *out = nullptr;
+    CHECK_ARG(d->T > 0 && d->C >= d->T && d->class_ptr && d->class_tid && d->euma && d->nF >= 1,
+              "emsar_index_create: empty or incomplete descriptor");
+    CHECK_ARG(d->T < (1 << 21), "emsar_index_create: T = %d exceeds the supported 2^21 - 1 transcripts", d->T);
+    const int32_t T = d->T;
+    const int64_t C = d->C;
+    const int64_t nnz = d->class_ptr[C];
+    if (nnz >= ((int64_t)1 << 31) || C >= ((int64_t)1 << 31)) { emsar_set_err("index too large: nnz=%lld C=%lld", (long long)nnz, (long long)C); return EMSAR_ERR_UNSUPPORTED; }
+    // ---- validate the scan order (scan_rshbucket :2149-2191) ----
+    for (int32_t t = 0; t < T; t++)
+        if (d->class_ptr[t] != t || d->class_tid[t] != t) { emsar_set_err("class %d is not the singleton of tid %d", t, t); return EMSAR_ERR_BAD_INDEX; }
+    if (d->class_ptr[T] != T) { emsar_set_err("class_ptr[T] != T"); return EMSAR_ERR_BAD_INDEX; }
+    std::vector<KSeg> kseg;
+    std::vector<uint8_t> insertable((size_t)(C - T), 1);
+    int32_t max_card = 1;
+    {
+        int prev_k = 1, prev_t0 = -1;
+        int64_t chain_max = -1; // cid holding the running maximum key of the current chain
+        for (int64_t c = T; c < C; c++) {
+            int64_t o = d->class_ptr[c];
+            int64_t k64 = d->class_ptr[c + 1] - o;
+            if (k64 < 2) { emsar_set_err("class %lld has cardinality %lld (multi-tid classes need >= 2)", (long long)c, (long long)k64); return EMSAR_ERR_BAD_INDEX; }
+            int k = (int)k64;
+            if (k > d->max_t_size) { emsar_set_err("class %lld has %d tids > header max_t_size %d", (long long)c, k, d->max_t_size); return EMSAR_ERR_BAD_INDEX; }
+            const int32_t *t = d->class_tid + o;
+            for (int j = 0; j < k; j++) {
+                if (t[j] < 0 || t[j] >= T) { emsar_set_err("class %lld: tid %d out of range", (long long)c, t[j]); return EMSAR_ERR_BAD_INDEX; }
+                if (j && t[j] < t[j - 1]) { emsar_set_err("class %lld: tids not sorted", (long long)c); return EMSAR_ERR_BAD_INDEX; }
+            }
+            if (k < prev_k || (k == prev_k && t[0] < prev_t0)) {
+                emsar_set_err("class %lld out of scan order (cardinality, first tid)", (long long)c);
+                return EMSAR_ERR_BAD_INDEX;
+            }
+            if (k != prev_k) { kseg.push_back(KSeg{k, c, c}); }
+            kseg.back().cid1 = c + 1;
+            if (k != prev_k || t[0] != prev_t0) chain_max = c; // new chain: head is always reachable
+            else {
+                const int32_t *m = d->class_tid + d->class_ptr[chain_max];
+                int cmp = 0;
+                for (int j = 1; j < k && !cmp; j++) cmp = (t[j] < m[j]) ? -1 : (t[j] > m[j] ? 1 : 0);
+                if (cmp > 0) chain_max = c; else insertable[(size_t)(c - T)] = 0; // shadowed: unreachable by the chain walk
+            }
+            prev_k = k; prev_t0 = t[0];
+            if (k > max_card) max_card = k;
+        }
+    }
+    emsar_index *ix = new emsar_index();
+    ix->ctx = ctx; ix->T = T; ix->C = C; ix->nnz = nnz; ix->n_multi = C - T; ix->nnz_multi = nnz - T;
+    ix->nF = d->nF; ix->min_fl = d->min_fraglength; ix->max_fl = d->max_fraglength; ix->readlength = d->readlength;
+    ix->max_t_size = d->max_t_size; ix->max_card = max_card;
+    ix->frag_min = d->min_fraglength > d->readlength ? d->min_fraglength : d->readlength;   // determine_fraglength_range :2471-2475
+    ix->frag_max = d->max_fraglength >= ix->frag_min ? d->max_fraglength : ix->frag_min;
+    if (ix->frag_max - ix->frag_min + 1 != d->nF) {
+        emsar_set_err("nF = %d does not match the fragment length range %d..%d", d->nF, ix->frag_min, ix->frag_max);
+        delete ix; return EMSAR_ERR_BAD_INDEX;
+    }
+    if (ix->frag_max > ix->max_fl) { // the reference would index FraglengthCounts out of bounds (:2511)
+        emsar_set_err("read length %d exceeds Max_Fraglength %d", d->readlength, d->max_fraglength);
+        delete ix; return EMSAR_ERR_BAD_INDEX;
+    }
+    ix->kseg = kseg;
+    ix->device_bytes = 0;
+    CU(cudaSetDevice(ctx->device));
+    // ---- host copies (32-bit) ----
+    ix->h_cls_off.resize((size_t)C + 1);
+    for (int64_t c = 0; c <= C; c++) ix->h_cls_off[(size_t)c] = (uint32_t)d->class_ptr[c];
+    ix->h_cls_tid.assign(d->class_tid, d->class_tid + nnz);
+    // ---- transpose of the multi-tid classes (build_TC_from_CT_2 :2201-2227 without the singleton entries) ----
+    std::vector<uint32_t> txm_off((size_t)T + 1, 0);
+    for (int64_t j = T; j < nnz; j++) txm_off[(size_t)d->class_tid[j] + 1]++;
+    for (int32_t t = 0; t < T; t++) txm_off[(size_t)t + 1] += txm_off[(size_t)t];
+    std::vector<int32_t> txm_cid((size_t)(nnz - T));
+    {
+        std::vector<uint32_t> cur(txm_off.begin(), txm_off.end() - 1);
+        for (int64_t c = T; c < C; c++)
+            for (int64_t j = d->class_ptr[c]; j < d->class_ptr[c + 1]; j++) txm_cid[cur[(size_t)d->class_tid[j]]++] = (int32_t)c;
+    }
+    // ---- sets without EUMAcut (union-find over transcripts); decides whether the cut loop can ever trigger ----
+    {
+        std::vector<int32_t> par((size_t)T);
+        std::iota(par.begin(), par.end(), 0);
+        for (int64_t c = T; c < C; c++) {
+            int r0 = uf_find(par, d->class_tid[d->class_ptr[c]]);
+            for (int64_t j = d->class_ptr[c] + 1; j < d->class_ptr[c + 1]; j++) {
+                int r = uf_find(par, d->class_tid[j]);
+                if (r != r0) par[(size_t)r] = r0;
+            }
+        }
+        std::vector<int32_t> sz((size_t)T, 0);
+        int32_t ns = 0, mx = 0;
+        for (int32_t t = 0; t < T; t++) { int r = uf_find(par, t); if (sz[(size_t)r]++ == 0) ns++; if (sz[(size_t)r] > mx) mx = sz[(size_t)r]; }
+        ix->n_sets_nocut = ns; ix->max_set_tids = mx;
+    }
+    // ---- upload ----
+    int rc;
+#define UP(dst, src, n, type)                                                                         \
+    if ((rc = dev_alloc(&dst, (size_t)(n))) != EMSAR_OK) { emsar_index_destroy(ix); return rc; }      \
+    ix->device_bytes += (int64_t)(n) * sizeof(type);                                                  \
+    CU(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(type), cudaMemcpyHostToDevice, ctx->stream));
+    UP(ix->d_cls_off, ix->h_cls_off.data(), C + 1, uint32_t);
+    UP(ix->d_cls_tid, ix->h_cls_tid.data(), nnz, int32_t);
+    UP(ix->d_euma, d->euma, C * (int64_t)d->nF, int32_t);
+    std::vector<uint8_t> hn((size_t)C, 1);
+    if (d->has_node) memcpy(hn.data(), d->has_node, (size_t)C);
+    UP(ix->d_has_node, hn.data(), C, uint8_t);
+    UP(ix->d_txm_off, txm_off.data(), T + 1, uint32_t);
+    UP(ix->d_txm_cid, txm_cid.data(), nnz - T, int32_t);
+    std::vector<int64_t> kc0; std::vector<int32_t> kk;
+    for (auto &s : kseg) { kc0.push_back(s.cid0); kk.push_back(s.k); }
+    kc0.push_back(C);
+    UP(ix->d_kseg_cid0, kc0.data(), kc0.size(), int64_t);
+    UP(ix->d_kseg_k, kk.data(), kk.size() ? kk.size() : 1, int32_t);
+#undef UP
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = index_build_hash(ix, insertable);
+    if (rc != EMSAR_OK) { emsar_index_destroy(ix); return rc; }
+    *out = ix;
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_index_info_get(const emsar_index *ix, emsar_index_info *info)
+{
+    CHECK_ARG(ix && info, "emsar_index_info_get: NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->T = ix->T; info->C = ix->C; info->nnz = ix->nnz; info->n_multi = ix->n_multi; info->nnz_multi = ix->nnz_multi;
+    info->n_kseg = (int32_t)ix->kseg.size(); info->max_card = ix->max_card;
+    info->hash_slots = (int64_t)ix->hash_mask + 1; info->hash_inserted = ix->hash_inserted;
+    info->n_sets_nocut = ix->n_sets_nocut; info->max_set_tids = ix->max_set_tids;
+    info->device_bytes = ix->device_bytes; info->frag_min = ix->frag_min; info->frag_max = ix->frag_max;
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_index_destroy(emsar_index *ix)
+{
+    if (!ix) return EMSAR_OK;
+    cudaSetDevice(ix->ctx->device);
+    cudaStreamSynchronize(ix->ctx->stream);
+    cudaFree(ix->d_cls_off); cudaFree(ix->d_cls_tid); cudaFree(ix->d_euma); cudaFree(ix->d_has_node);
+    cudaFree(ix->d_txm_off); cudaFree(ix->d_txm_cid); cudaFree(ix->d_hash); cudaFree(ix->d_kseg_cid0); cudaFree(ix->d_kseg_k);
+    delete ix;
+    return EMSAR_OK;
+}

@@ -1,0 +1,311 @@
+"""Seeded synthetic rsh indices and read sets (SURVEY.md §8(d) "Concrete synthetic inputs").
+
+One generator serves the parity tests (small, also written as `.rsh` + bowtie/SAM text so the real
+reference binary can be run on them) and bench.py (human-scale, packed arrays only).
+
+Index conventions follow the reference's `.rsh` semantics (reference src/emsar_functions.c:2071-2130
+writer, :1351-1510 reader): class ids are positional; cid 0..T-1 are the singleton classes in tid
+order (cid == tid); multi-tid classes follow ordered by (cardinality, first tid, lexicographic rest);
+a class is a sorted multiset of tids (duplicates allowed, :1792).
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Optional
+
+import numpy as np
+
+
+@dataclasses.dataclass
+class SynthIndex:
+    T: int                      # transcripts (max_tid + 1)
+    names: list                 # transcript names (len T); may be lazily generated
+    class_ptr: np.ndarray       # int64[C+1]  CSR offsets over ALL classes (singletons first)
+    class_tid: np.ndarray       # int32[nnz]
+    euma: np.ndarray            # int32[C, nF]
+    has_node: np.ndarray        # uint8[C]    0 = singleton line without EUMA ("\t\t\t": no node)
+    min_fraglength: int         # header field 3 (overwrites -f, :1419)
+    max_fraglength: int         # header field 4 (overwrites -F, :1420)
+    readlength: int             # header field 5 (-1 for SE)
+    max_t_size: int             # header field 2 (rshbucket_max_t_size)
+
+    @property
+    def C(self) -> int:
+        return len(self.class_ptr) - 1
+
+    @property
+    def frag_min(self) -> int:   # Fraglengths.min (determine_fraglength_range :2471-2475)
+        return max(self.min_fraglength, self.readlength)
+
+    @property
+    def frag_max(self) -> int:
+        return max(self.max_fraglength, self.frag_min)
+
+    @property
+    def nF(self) -> int:
+        return self.frag_max - self.frag_min + 1
+
+
+@dataclasses.dataclass
+class SynthReads:
+    read_ptr: np.ndarray        # int64[n+1]
+    read_tid: np.ndarray        # int32[sum k]  (unsorted within a read)
+    read_fraglen: np.ndarray    # int32[n]
+    true_class: Optional[np.ndarray] = None  # int64[n]  (-1 = matches no class); generator's own truth
+
+
+def _powerlaw_k(rng, n, alpha, kmin, kmax):
+    ks = np.arange(kmin, kmax + 1)
+    p = ks.astype(np.float64) ** (-alpha)
+    p /= p.sum()
+    return rng.choice(ks, size=n, p=p)
+
+
+def make_index(T=2000, n_multi=10000, alpha=2.4, kmax=99, nF=1, seed=0, module_cap=500,
+               p_dup_tid=0.01, p_no_node=0.0, frag_min=None, readlength=-1,
+               hubs=0, hub_classes=0) -> SynthIndex:
+    """Gene-family structured index. Modules (connected components) stay <= module_cap transcripts
+    because class members are always drawn inside one family block of consecutive tids."""
+    rng = np.random.default_rng(seed)
+    # families: consecutive blocks of transcripts, heavy-tailed sizes capped by module_cap
+    fam_sizes = []
+    left = T
+    while left > 0:
+        s = int(min(left, module_cap, max(1, round(rng.pareto(1.2) * 8 + 1 + rng.geometric(0.2)))))
+        fam_sizes.append(s)
+        left -= s
+    fam_sizes = np.array(fam_sizes, dtype=np.int64)
+    fam_start = np.concatenate([[0], np.cumsum(fam_sizes)[:-1]])
+    # classes by cardinality
+    ks = _powerlaw_k(rng, n_multi, alpha, 2, kmax)
+    blocks = {}
+    order_sizes = np.argsort(fam_sizes)
+    sizes_sorted = fam_sizes[order_sizes]
+    for k in np.unique(ks):
+        n_want = int((ks == k).sum())
+        n_k = n_want + n_want // 3 + 8      # oversample: duplicate keys are dropped below, then trimmed back
+        # a class with repeated tid may need only k-1 distinct members; keep it simple: need k distinct
+        lo = np.searchsorted(sizes_sorted, k, side="left")
+        if lo >= len(sizes_sorted):
+            continue  # no family large enough for this cardinality
+        elig = order_sizes[lo:]
+        w_f = fam_sizes[elig].astype(np.float64)
+        fam = elig[rng.choice(len(elig), size=n_k, p=w_f / w_f.sum())]
+        fsz = fam_sizes[fam]
+        # window inside the family: mostly gene-sized neighbourhoods, sometimes a wider paralog neighbourhood
+        wide = rng.random(n_k) < 0.1
+        w = np.where(wide, k + 16 + rng.geometric(0.05, size=n_k), k + rng.geometric(0.25, size=n_k))
+        w = np.maximum(np.minimum(w, fsz), k)
+        start = fam_start[fam] + (rng.random(n_k) * (fsz - w + 1)).astype(np.int64)
+        rows = np.empty((n_k, k), dtype=np.int64)
+        step = max(1, (1 << 24) // max(int(w.max()), 1))        # bound the scratch to ~16M keys per chunk
+        for c0 in range(0, n_k, step):
+            wc = w[c0:c0 + step]
+            wmax = int(wc.max())
+            keys = rng.random((len(wc), wmax))
+            keys[np.arange(wmax)[None, :] >= wc[:, None]] = 2.0  # outside the window: never chosen
+            offs = np.argpartition(keys, k - 1, axis=1)[:, :k] if k < wmax else np.tile(np.arange(wmax), (len(wc), 1))[:, :k]
+            rows[c0:c0 + step] = start[c0:c0 + step, None] + offs
+        if p_dup_tid > 0:
+            dup = rng.random(n_k) < p_dup_tid
+            if dup.any():
+                src = rng.integers(0, k, size=n_k)
+                dst = (src + 1 + rng.integers(0, k - 1, size=n_k)) % k if k > 1 else src
+                idx = np.nonzero(dup)[0]
+                rows[idx, dst[idx]] = rows[idx, src[idx]]
+        rows.sort(axis=1)
+        rows = np.unique(rows, axis=0)          # drop duplicate keys; also gives canonical order
+        if len(rows) > n_want:
+            rows = rows[np.sort(rng.choice(len(rows), size=n_want, replace=False))]
+        blocks[int(k)] = rows.astype(np.int32)
+    # hub transcripts: `hubs` tids that each sit in `hub_classes` extra pair classes inside their family
+    if hubs > 0 and hub_classes > 0:
+        big = np.nonzero(fam_sizes >= min(200, int(fam_sizes.max())))[0]   # hubs need room for many distinct classes
+        hub_f = big[rng.choice(len(big), size=hubs)]
+        extra = []
+        for f in hub_f:
+            h = fam_start[f] + rng.integers(0, fam_sizes[f])
+            other = fam_start[f] + rng.integers(0, fam_sizes[f], size=hub_classes)
+            third = fam_start[f] + rng.integers(0, fam_sizes[f], size=hub_classes)
+            r = np.stack([np.full(hub_classes, h), other, third], axis=1)
+            extra.append(r)
+        r = np.concatenate(extra)
+        r.sort(axis=1)
+        r = np.concatenate([blocks.get(3, np.zeros((0, 3), np.int32)), r.astype(np.int32)])
+        blocks[3] = np.unique(r, axis=0)
+    k_sorted = sorted(blocks)
+    card = np.concatenate([np.full(len(blocks[k]), k, dtype=np.int64) for k in k_sorted]) if k_sorted else np.zeros(0, np.int64)
+    multi_tid = np.concatenate([blocks[k].ravel() for k in k_sorted]) if k_sorted else np.zeros(0, np.int32)
+    n_multi = len(card)
+    C = T + n_multi
+    class_ptr = np.zeros(C + 1, dtype=np.int64)
+    class_ptr[1:T + 1] = np.arange(1, T + 1)
+    class_ptr[T + 1:] = T + np.cumsum(card)
+    class_tid = np.concatenate([np.arange(T, dtype=np.int32), multi_tid.astype(np.int32)])
+    # EUMA (number of distinct k-mers / fragments per class and fragment length)
+    a_single = np.floor(rng.lognormal(6.0, 0.8, size=T)).astype(np.int64) + 1
+    # shared stretches get shorter as more transcripts share them
+    a_multi = rng.geometric(np.minimum(0.9, 0.01 * card), size=n_multi).astype(np.int64)
+    a = np.concatenate([a_single, a_multi])
+    if nF == 1:
+        euma = a[:, None].astype(np.int32)
+    else:
+        slope = a / (nF * rng.uniform(0.8, 3.0, size=C))
+        f = np.arange(nF)[None, :]
+        euma = np.maximum(0, np.floor(a[:, None] - slope[:, None] * f)).astype(np.int32)
+    has_node = np.ones(C, dtype=np.uint8)
+    if p_no_node > 0:
+        nn = rng.random(T) < p_no_node
+        has_node[:T][nn] = 0
+        euma[:T][nn] = 0
+    if frag_min is None:
+        frag_min = 1 if readlength < 0 else readlength
+    minf = frag_min
+    maxf = frag_min + nF - 1
+    max_t_size = int(card.max()) if n_multi else 1
+    names = [f"T{t:07d}" for t in range(T)] if T <= 200000 else None
+    return SynthIndex(T=T, names=names, class_ptr=class_ptr, class_tid=class_tid, euma=np.ascontiguousarray(euma),
+                      has_node=has_node, min_fraglength=minf, max_fraglength=maxf, readlength=readlength,
+                      max_t_size=max(max_t_size, 2))
+
+
+def true_theta(idx: SynthIndex, seed=0, p_zero=0.3):
+    rng = np.random.default_rng(seed + 7919)
+    th = rng.lognormal(0.0, 2.0, size=idx.T)
+    th[rng.random(idx.T) < p_zero] = 0.0
+    return th
+
+
+def frag_weights(idx: SynthIndex):
+    nF = idx.nF
+    if nF == 1:
+        return np.ones(1)
+    f = np.arange(nF) + idx.frag_min
+    mu = idx.frag_min + 0.5 * nF
+    w = np.exp(-0.5 * ((f - mu) / (0.1 * nF + 1.0)) ** 2)
+    return w / w.sum()
+
+
+def class_rates(idx: SynthIndex, theta):
+    """p_c ∝ (Σ_f w_f·EUMA[c][f]) · Σ_{t∈c} θ_t   (reference model: lambdap :2966-2975)."""
+    w = frag_weights(idx)
+    a = idx.euma.astype(np.float64) @ w
+    a = a * idx.has_node
+    seg = np.add.reduceat(theta[idx.class_tid], idx.class_ptr[:-1].astype(np.int64))
+    return a * seg
+
+
+def sample_class_counts(idx: SynthIndex, N, seed=0, p_zero=0.3):
+    rng = np.random.default_rng(seed + 104729)
+    p = class_rates(idx, true_theta(idx, seed, p_zero))
+    p = p / p.sum()
+    return rng.multinomial(N, p).astype(np.int64)
+
+
+def make_reads(idx: SynthIndex, N, seed=0, p_zero=0.3, p_unmatched=0.005, shuffle_tids=True) -> SynthReads:
+    """Read tid-lists as the host reader would hand them to update_ReadCounts (:838): one list per read
+    group, unsorted, plus the group's fragment length. `p_unmatched` of the reads carry a tid multiset that
+    is (almost surely) not a class: they count toward N and the fragment histogram only (:940-941)."""
+    rng = np.random.default_rng(seed + 15485863)
+    n_un = int(round(N * p_unmatched))
+    counts = sample_class_counts(idx, N - n_un, seed, p_zero)
+    cls = np.repeat(np.arange(idx.C, dtype=np.int64), counts)
+    cls = np.concatenate([cls, np.full(n_un, -1, dtype=np.int64)])
+    rng.shuffle(cls)
+    n = len(cls)
+    k = np.where(cls >= 0, idx.class_ptr[np.maximum(cls, 0) + 1] - idx.class_ptr[np.maximum(cls, 0)], 2)
+    read_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(k, out=read_ptr[1:])
+    tot = int(read_ptr[-1])
+    # ragged gather
+    rid = np.repeat(np.arange(n, dtype=np.int64), k)
+    pos = np.arange(tot, dtype=np.int64) - read_ptr[rid]
+    kk = k[rid]
+    if shuffle_tids:
+        rot = rng.integers(0, 1 << 30, size=n)[rid]
+        rev = (rng.random(n) < 0.5)[rid]
+        pos = (pos + rot) % kk
+        pos = np.where(rev, kk - 1 - pos, pos)
+    src = idx.class_ptr[np.maximum(cls, 0)][rid] + pos
+    read_tid = idx.class_tid[src].astype(np.int32)
+    un = np.nonzero(cls < 0)[0]
+    if len(un):
+        # two far-apart random tids: virtually never a class (classes live inside one family block)
+        a = rng.integers(0, idx.T, size=len(un))
+        b = (a + idx.T // 2 + rng.integers(0, max(1, idx.T // 4), size=len(un))) % idx.T
+        read_tid[read_ptr[un]] = a
+        read_tid[read_ptr[un] + 1] = b
+    if idx.nF == 1:
+        fl = np.full(n, idx.frag_min, dtype=np.int32)
+    else:
+        fl = (idx.frag_min + rng.choice(idx.nF, size=n, p=frag_weights(idx))).astype(np.int32)
+    return SynthReads(read_ptr=read_ptr, read_tid=read_tid, read_fraglen=fl, true_class=cls)
+
+
+# ----------------------------------------------------------------------------------------------
+# Text writers (small fixtures only): `.rsh` and bowtie / SAM alignments for the reference binary.
+# ----------------------------------------------------------------------------------------------
+
+def write_rsh(idx: SynthIndex, path: str):
+    """`.rsh` text exactly as print_rsh (:2071-2130) lays it out (trailing commas included)."""
+    with open(path, "w") as f:
+        f.write(f"#{idx.T - 1},{idx.max_t_size},{idx.min_fraglength},{idx.max_fraglength},{idx.readlength}\n")
+        for t in range(idx.T):
+            f.write(f"@{t}\t{idx.names[t]}\n")
+        f.write("cid\tno.tids\tfirst.tid\tother.tids\tsegment.length\n")
+        cp, ct = idx.class_ptr, idx.class_tid
+        for c in range(idx.C):
+            tids = ct[cp[c]:cp[c + 1]]
+            k = len(tids)
+            if k == 1 and not idx.has_node[c]:
+                f.write(f"{c}\t1\t{tids[0]}\t\t\t\n")
+                continue
+            e = "".join(f"{v}," for v in idx.euma[c])
+            if k == 1:
+                f.write(f"{c}\t1\t{tids[0]}\t\t{e}\n")
+            else:
+                o = "".join(f"{v}," for v in tids[1:])
+                f.write(f"{c}\t{k}\t{tids[0]}\t{o}\t{e}\n")
+
+
+def write_bowtie_se(idx: SynthIndex, reads: SynthReads, path: str):
+    """Default bowtie output, SE: id, strand, tname, pos, seq, qual, other, mismatches (parse_bowtieline
+    :552-587). The fragment length is strlen(seq) (:572), so `A`*fraglen keeps lines short."""
+    rp, rt, fl = reads.read_ptr, reads.read_tid, reads.read_fraglen
+    with open(path, "w") as f:
+        for r in range(len(fl)):
+            seq = "A" * int(fl[r])
+            for j, t in enumerate(rt[rp[r]:rp[r + 1]]):
+                # distinct pos per alignment so that the duplicate filter (alignment.c:36-40) keeps repeats
+                f.write(f"r{r}\t+\t{idx.names[t]}\t{j}\t{seq}\t{seq}\t0\t\n")
+
+
+def write_sam_pe(idx: SynthIndex, reads: SynthReads, path: str, tlen=100000):
+    """SAM, PE: mates adjacent, flags 0x40/0x80 (+0x10 on the reverse mate), MD:Z tags, l_qseq = readlength,
+    fraglen = pos2 - pos1 + readlength (convert_bam_alignment_2_alignment_PE :426-469)."""
+    L = idx.readlength
+    rp, rt, fl = reads.read_ptr, reads.read_tid, reads.read_fraglen
+    seq = "A" * L
+    with open(path, "w") as f:
+        f.write("@HD\tVN:1.0\tSO:unsorted\n")
+        for t in range(idx.T):
+            f.write(f"@SQ\tSN:{idx.names[t]}\tLN:{tlen}\n")
+        for r in range(len(fl)):
+            d = int(fl[r]) - L
+            for j, t in enumerate(rt[rp[r]:rp[r + 1]]):
+                p1 = 1 + 1000 * j      # SAM is 1-based; distinct pos per alignment
+                p2 = p1 + d
+                n = idx.names[t]
+                if d > 0:
+                    f.write(f"r{r}\t{0x1 | 0x2 | 0x20 | 0x40}\t{n}\t{p1}\t255\t{L}M\t=\t{p2}\t{d + L}\t{seq}\t{seq}\tMD:Z:{L}\n")
+                    f.write(f"r{r}\t{0x1 | 0x2 | 0x10 | 0x80}\t{n}\t{p2}\t255\t{L}M\t=\t{p1}\t{-(d + L)}\t{seq}\t{seq}\tMD:Z:{L}\n")
+                else:
+                    # pos2 == pos1 is treated as "mate2(f)...mate1(r)" (:461-465)
+                    f.write(f"r{r}\t{0x1 | 0x2 | 0x10 | 0x40}\t{n}\t{p1}\t255\t{L}M\t=\t{p2}\t{L}\t{seq}\t{seq}\tMD:Z:{L}\n")
+                    f.write(f"r{r}\t{0x1 | 0x2 | 0x20 | 0x80}\t{n}\t{p2}\t255\t{L}M\t=\t{p1}\t{-L}\t{seq}\t{seq}\tMD:Z:{L}\n")
+
+
+def ensure_dir(p):
+    os.makedirs(p, exist_ok=True)
+    return p

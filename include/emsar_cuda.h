@@ -1,0 +1,182 @@
+/*
+ * emsar_cuda.h — C ABI of libemsar_cuda.so: the B200 (sm_100a) replacement for EMSAR's per-sample
+ * quantification hot path.  Plain C, plain pointers and sizes; no CUDA or torch types in any signature.
+ *
+ * The reference (parklab/emsar v2.0.1, paths relative to its src/) has no plugin API; its only designed
+ * seams are three global function pointers (emsar.h:219-221) and the global arrays the estimator reads and
+ * writes (emsar.h:90-195).  Each entry point below names the reference code it replaces, so that the
+ * reference's own main loop (emsar_main.c:380-488) can call this library instead.
+ *
+ * Conventions
+ *   - every function returns an int status: EMSAR_OK (0) or an EMSAR_ERR_* code; emsar_cuda_strerror()
+ *     names the code and emsar_cuda_last_error() gives the detail of the calling thread's last failure.
+ *     (The reference prints to stderr and exit(1)s; the host program turns a non-zero status into that.)
+ *   - host buffers stay owned by the caller; device memory lives behind the opaque handles.
+ *   - a context is bound to ONE device and ONE CUDA stream; handles are not thread-safe: use one host
+ *     thread (or one process) per device.  There is no CPU fallback: without a usable sm_100 device
+ *     emsar_cuda_open() fails with EMSAR_ERR_NO_DEVICE.
+ *   - class ids follow the reference's scan order (scan_rshbucket, emsar_functions.c:2149-2191): cid
+ *     0..T-1 are the singleton classes (cid == tid), multi-tid classes follow ordered by cardinality,
+ *     then first tid, then chain (file) order.  A class is a sorted multiset of tids.
+ */
+#ifndef EMSAR_CUDA_H
+#define EMSAR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMSAR_OK 0
+#define EMSAR_ERR_NO_DEVICE 1   /* no CUDA device / not compute capability 10.x */
+#define EMSAR_ERR_CUDA 2        /* a CUDA runtime call failed (see emsar_cuda_last_error) */
+#define EMSAR_ERR_BAD_ARG 3     /* NULL / out-of-range argument */
+#define EMSAR_ERR_BAD_INDEX 4   /* class table not in the reference's scan order / malformed */
+#define EMSAR_ERR_UNSUPPORTED 5 /* a documented limit was exceeded (e.g. a read with > 1024 alignments) */
+#define EMSAR_ERR_STATE 6       /* call order violated (e.g. solve before any counts) */
+#define EMSAR_ERR_NOMEM 7       /* host or device allocation failed */
+#define EMSAR_ERR_COMM 8        /* NCCL / multi-GPU failure */
+
+#define EMSAR_MAX_READ_TIDS 1024 /* longest tid list one read may carry (reference: MAX_REPEAT, default 100) */
+
+typedef struct emsar_ctx emsar_ctx;       /* one device + stream */
+typedef struct emsar_index emsar_index;   /* packed rsh index resident on the device */
+typedef struct emsar_sample emsar_sample; /* per-alignment-file state: counts, model, estimates */
+
+/* -------- context ------------------------------------------------------------------------------- */
+int emsar_cuda_open(int device, emsar_ctx **ctx);
+int emsar_cuda_close(emsar_ctx *ctx);
+const char *emsar_cuda_strerror(int status);
+const char *emsar_cuda_last_error(void);
+/* number of kernels this library has launched on the context so far (bench.py's gpu_launches) */
+int emsar_cuda_launch_count(emsar_ctx *ctx, int64_t *launches);
+int emsar_cuda_synchronize(emsar_ctx *ctx);
+
+typedef struct {
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    int64_t l2_bytes;
+    int64_t hbm_bytes;
+    int32_t em_blocks_per_sm; /* resident CTAs/SM of the persistent EM kernel */
+    int32_t em_block_threads;
+    char name[64];
+} emsar_device_info;
+int emsar_cuda_device_info(emsar_ctx *ctx, emsar_device_info *info);
+
+/* -------- index ---------------------------------------------------------------------------------
+ * Replaces the product of construct_rsh_from_rshfile (emsar_functions.c:1351-1378): rshbucket,
+ * rshbucket_single (emsar.h:139-145), initialize_rshbucket (:1334-1347), delete_rshbucket (:1687-1723). */
+typedef struct {
+    int32_t T;                 /* max_tid + 1 */
+    int64_t C;                 /* max_cid + 1 (T singleton classes first) */
+    const int64_t *class_ptr;  /* [C+1] CSR offsets, class_ptr[c] == c for c <= T */
+    const int32_t *class_tid;  /* [class_ptr[C]] sorted within a class, duplicates kept */
+    int32_t nF;                /* nFraglen = Fraglengths.max - Fraglengths.min + 1 (:2471-2475) */
+    const int32_t *euma;       /* [C * nF] row-major EUMA counts (node1.EUMA, emsar.h:79) */
+    const uint8_t *has_node;   /* [C] 0 = singleton line without EUMA: no node exists (:1486), NULL = all 1 */
+    int32_t min_fraglength;    /* rsh header field 3 -> Min_Fraglength (:1419) */
+    int32_t max_fraglength;    /* rsh header field 4 -> Max_Fraglength (:1420) */
+    int32_t readlength;        /* rsh header field 5, -1 for SE (:1421) */
+    int32_t max_t_size;        /* rsh header field 2 -> rshbucket_max_t_size (:1418) */
+} emsar_index_desc;
+
+typedef struct {
+    int32_t T;
+    int64_t C, nnz;            /* all classes */
+    int64_t n_multi, nnz_multi;
+    int32_t n_kseg;            /* distinct cardinalities among multi-tid classes */
+    int32_t max_card;
+    int64_t hash_slots, hash_inserted;
+    int32_t n_sets_nocut;      /* sequence-sharing sets with EUMAcut = 0 */
+    int32_t max_set_tids;      /* largest set (transcripts) with EUMAcut = 0 */
+    int64_t device_bytes;
+    int32_t frag_min, frag_max; /* Fraglengths.min / .max */
+} emsar_index_info;
+
+int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *desc, emsar_index **index);
+int emsar_index_info_get(const emsar_index *index, emsar_index_info *info);
+int emsar_index_destroy(emsar_index *index);
+
+/* -------- per-sample ----------------------------------------------------------------------------
+ * emsar_sample_begin   : clear_readcounts_in_rshbucket_PTR + calloc FraglengthCounts (emsar_main.c:383-384)
+ * emsar_sample_count   : update_ReadCounts -> update_rshbucket[_single]_PTR(...,'r',...)
+ *                        (emsar_functions.c:838-943, 1514-1537, 1597-1624) for a batch of read groups that
+ *                        already passed the reader-side filters (alignment.c:29-60, 85-95; size <= MAX_REPEAT).
+ *                        tids may arrive unsorted; asynchronous with respect to the host.
+ * emsar_sample_counts_get : ReadCount[] / FraglengthCounts[] / TotalReadCount as scan_rshbucket (:2135-2192)
+ *                        would flatten them (bit-exact integers).
+ * emsar_sample_solve   : transfer_fraglendist_to_Wf ... compute_iEUMA (emsar_main.c:396-454) and the numeric
+ *                        part of print_FPKMfinal (:3163-3212).
+ * emsar_sample_segments_get : numeric columns of print_aEUMA_3 (:2262-2300).
+ * emsar_sample_end     : the frees at emsar_main.c:478-486. */
+int emsar_sample_begin(emsar_index *index, emsar_sample **sample);
+int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_t *read_ptr, const int32_t *read_tid,
+                       const int32_t *read_fraglen);
+/* same, but the three arrays already live in device memory of the context's device (bench: resident inputs) */
+int emsar_sample_count_device(emsar_sample *s, int64_t n_reads, const void *d_read_ptr, const void *d_read_tid,
+                              const void *d_read_fraglen);
+/* install counts computed elsewhere (class-sharded mode, tests of the estimator alone) */
+int emsar_sample_counts_set(emsar_sample *s, const int32_t *ReadCount, const int32_t *FraglengthCounts);
+int emsar_sample_counts_get(emsar_sample *s, int32_t *ReadCount, int32_t *FraglengthCounts, int64_t *TotalReadCount);
+
+typedef struct {
+    double eps_abs;        /* reads; <= 0 selects the default 1e-7 */
+    double eps_rel;        /* relative; <= 0 selects the default 1e-10 */
+    int32_t max_iter;      /* <= 0 selects the default 200000 (reference -i, MAX_NITER_MLE) */
+    double delta;          /* reference -d (DELTA): lambda scaled by 10^delta */
+    double eumacut;        /* in: EUMAcut carried over from the previous sample (emsar.h:94 is never reset) */
+    int32_t max_ntid_per_sid; /* <= 0 selects MAX_NTID_PER_SID = 5000 (emsar.h:17) */
+    const uint8_t *in_model;  /* optional [C]: caller-supplied set membership (CS[c] != -1); NULL = computed here */
+} emsar_solve_opts;
+
+typedef struct {
+    /* caller-provided output buffers, each [T] (any may be NULL) */
+    double *fpkm;            /* FPKM[tid] (one deterministic round; reference averages NUM_ROUND random rounds) */
+    double *efflen;          /* iEUMA[tid]  (.fpkm column eff.length) */
+    double *ireadcount;      /* iEUMA/1e3 * FPKM * N/1e6 */
+    int32_t *ireadcount_int; /* Round_off() */
+    double *tpm;             /* FPKM * 1e6 / sum FPKM */
+    /* scalars filled by the call */
+    int32_t n_iter;
+    double final_delta;      /* max_t |dtheta_t| A_t / (eps_abs + eps_rel n_t) of the last iteration; converged iff <= 1 */
+    double loglik;           /* sum_c R_c log(lambda_c) - lambda_c over modelled classes (Fp, :2946-2964) */
+    int64_t total_ireadcount;
+    int64_t total_readcount; /* TotalReadCount */
+    double eumacut;          /* EUMAcut after the set-size loop (emsar_main.c:411-425) */
+    int32_t max_sid;
+    double em_ms;            /* device time of the EM loop (CUDA events) */
+    double prep_ms;          /* device+host time of the per-sample model build */
+} emsar_solve_out;
+
+int emsar_sample_solve(emsar_sample *s, const emsar_solve_opts *opts, emsar_solve_out *out);
+/* [C] each, any may be NULL: adjEUMA (eff.length), expected_Readcount, set id (CS, -1 = cut by EUMAcut) */
+int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, double *expected, int32_t *set_id);
+/* [nF]: Wf (normalized.Fragment.length.sampling.prob of .fraglength_effect) */
+int emsar_sample_wf_get(emsar_sample *s, double *Wf);
+int emsar_sample_end(emsar_sample *s);
+
+/* -------- finer-grained steps of emsar_sample_solve (tests, bench.py, profiling) ----------------- */
+typedef struct {
+    int32_t T;
+    int64_t C_a, nnz_a;       /* active multi-tid classes (modelled, R > 0) and their members */
+    int64_t rows_short, rows_long, rows_hub, rows_fixed; /* transcripts by transposed-row length; fixed: A_t == 0 */
+    int64_t e_tiles, m_tiles;
+    int64_t bytes_per_iter;   /* algorithmic bytes of one EM iteration: 8 nnz_a + 24 C_a + 44 T */
+    int64_t stream_bytes_per_iter; /* bytes the kernels actually stream per iteration (index + state) */
+} emsar_model_stats;
+/* Wf, adjEUMA, EUMAps, sets/EUMAcut, A_t, iEUMA and the packed active model; theta := start point */
+int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opts);
+int emsar_sample_model_stats(emsar_sample *s, emsar_model_stats *st);
+/* run up to max_iter EM iterations from the current theta; stop_on_conv != 0 stops once delta <= 1.
+   elapsed_ms is measured with CUDA events on the context's stream. */
+int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
+                        int32_t *iters_done, double *final_delta, double *elapsed_ms);
+int emsar_sample_theta_get(emsar_sample *s, double *theta);
+int emsar_sample_finalize(emsar_sample *s, emsar_solve_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMSAR_CUDA_H */
