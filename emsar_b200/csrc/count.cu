@@ -212,7 +212,7 @@ extern "C" int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_
                                   const int32_t *read_fraglen)
 {
     CHECK_ARG(s && n_reads >= 0, "emsar_sample_count: bad argument");
-    if (n_reads == 0) return EMSAR_OK;
+    if (n_reads == 0) { s->have_counts = true; return EMSAR_OK; }   // an empty alignment file is still a sample
     CHECK_ARG(read_ptr && read_tid && read_fraglen, "emsar_sample_count: NULL read arrays");
     emsar_ctx *ctx = s->ctx;
     CU(cudaSetDevice(ctx->device));
@@ -233,7 +233,7 @@ extern "C" int emsar_sample_count_device(emsar_sample *s, int64_t n_reads, const
                                          const void *d_read_fraglen)
 {
     CHECK_ARG(s && n_reads >= 0, "emsar_sample_count_device: bad argument");
-    if (n_reads == 0) return EMSAR_OK;
+    if (n_reads == 0) { s->have_counts = true; return EMSAR_OK; }
     CHECK_ARG(d_read_ptr && d_read_tid && d_read_fraglen, "emsar_sample_count_device: NULL read arrays");
     CU(cudaSetDevice(s->ctx->device));
     return launch_count(s, n_reads, (const int64_t *)d_read_ptr, (const int32_t *)d_read_tid, (const int32_t *)d_read_fraglen);
