@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--em-iters", type=int, default=2000, help="EM iterations per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converge", action="store_true", help="skip the one-off run to convergence (samples/min)")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg (e2e is then null)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -195,16 +196,17 @@ def main():
         s.close()
         return it, r
 
-    step_e2e()
-    barrier()
-    e0 = time.perf_counter()
-    e_iters = 0
-    for _ in range(args.steps):
-        it, r = step_e2e()
-        e_iters += it
-    barrier()
-    e1 = time.perf_counter()
-    e_wall = e1 - e0
+    e_iters, e_wall = 0, 1.0
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(args.steps):
+            it, r = step_e2e()
+            e_iters += it
+        barrier()
+        e1 = time.perf_counter()
+        e_wall = e1 - e0
     d2h_bytes = idx.T * (8 * 4 + 4)
 
     if rank == 0:
@@ -258,7 +260,7 @@ def main():
                        "C_a": st["C_a"], "nnz_a": st["nnz_a"], "em_iters_per_step": args.em_iters, "samples": world,
                        "parallelism": f"sample-sharded x{world} (-M), no collective",
                        "l2": "flushed between steps (256 MiB memset); iterations inside a step reuse L2 as the production loop does"},
-            "e2e": {"value": e_iters_tot / e_wall, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+            "e2e": None if args.no_e2e else {"value": e_iters_tot / e_wall, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * e_wall / args.steps},
             "gpu_launches": int(launches_tot),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

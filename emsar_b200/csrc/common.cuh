@@ -40,9 +40,8 @@ constexpr int KT = 8;             // classes with cardinality <= KT: thread-per-
 constexpr int KSUB = 32;          // KT < k <= KSUB: 8 lanes per class; k > KSUB: warp per class
 constexpr int E_TILE_TARGET = 256; // target gathers per warp tile for the long-class modes
 constexpr int M_SHORT_MAX = 128;  // transposed rows with <= this many active entries are "short" (smem-staged)
-constexpr int M_WINDOW = 128;     // cost window of a short-row tile (cost = entries + M_ROW_COST per row)
-constexpr int M_ROW_COST = 2;
-constexpr int M_TILE_SMEM = M_WINDOW + M_SHORT_MAX + M_ROW_COST; // doubles of staging per warp (upper bound)
+constexpr int M_WINDOW = 512;     // cost window of a short-row tile (cost = entries + M_ROW_COST per row)
+constexpr int M_ROW_COST = 16;    // => at most M_WINDOW / M_ROW_COST = 32 rows per tile (one per lane)
 constexpr int M_HUB_MIN = 4096;   // rows with more active entries are reduced by a whole CTA
 
 struct KSeg {          // multi-tid classes of one cardinality, contiguous in cid order
@@ -56,6 +55,7 @@ struct emsar_ctx {
     cudaDeviceProp prop;
     int64_t launches;
     int em_blocks_per_sm;
+    int em_minb;              // launch-bounds variant of the EM kernel in use
     unsigned *d_barrier;      // [0] arrival count, [1] generation   (persistent-kernel grid barrier)
     void *d_scratch;          // CUB temp storage (grow-only)
     size_t scratch_bytes;

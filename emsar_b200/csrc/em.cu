@@ -124,7 +124,7 @@ __device__ __forceinline__ double m_update(const EmParams &p, int row, double Q)
     return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
 }
 
-__device__ __forceinline__ double m_phase(const EmParams &p, double *sm_warp, double *sm_block, int gwarp, int nwarps, int lane)
+__device__ __forceinline__ double m_phase(const EmParams &p, double *sm_block, int gwarp, int nwarps, int lane)
 {
     double dmax = 0;
     const double *q = p.m.q;
@@ -158,29 +158,36 @@ __device__ __forceinline__ double m_phase(const EmParams &p, double *sm_warp, do
         for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
         if (lane == 0) dmax = fmax(dmax, m_update(p, row, s));
     }
-    // (3) short rows: a warp stages one tile of gathered q values in shared memory, then each lane sums whole
-    //     rows sequentially (ascending class id: the same order as the CPU oracle)
+    // (3) short rows: a warp takes one tile of <= 32 consecutive rows; 8 lanes reduce one row at a time (4 rows per
+    //     pass, fixed shuffle tree), then all 32 lanes update their row together (coalesced Rs/A/theta traffic)
     for (int g = nwarps - 1 - gwarp; g < p.m.n_mtiles; g += nwarps) {
         const int2 tile = __ldg(p.m.m_tiles + g);
-        if (tile.x >= tile.y) continue;
-        const uint32_t e0 = row_off[tile.x], e1 = row_off[tile.y];
-        const int n = (int)(e1 - e0);
-        for (int i = lane; i < n; i += 32) sm_warp[i] = q[__ldg(p.m.m_cls + e0 + i)];
-        __syncwarp();
-        for (int row = tile.x + lane; row < tile.y; row += 32) {
-            const int a = (int)(row_off[row] - e0), b = (int)(row_off[row + 1] - e0);
-            double Q = 0;
-            for (int i = a; i < b; i++) Q += sm_warp[i];
-            dmax = fmax(dmax, m_update(p, row, Q));
+        const int nrows = tile.y - tile.x;
+        if (nrows <= 0) continue;
+        const int sub = lane >> 3, l = lane & 7;
+        double Qmine = 0;
+        for (int pass = 0; pass * 4 < nrows; pass++) {
+            const int r = pass * 4 + sub;
+            double s = 0;
+            if (r < nrows) {
+                const uint32_t a = row_off[tile.x + r], b = row_off[tile.x + r + 1];
+#pragma unroll 4
+                for (uint32_t e = a + l; e < b; e += 8) s += q[__ldg(p.m.m_cls + e)];
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            const double got = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);
+            if ((lane >> 2) == pass) Qmine = got;
         }
-        __syncwarp();
+        if (lane < nrows) dmax = fmax(dmax, m_update(p, tile.x + lane, Qmine));
     }
     return dmax;
 }
 
-__global__ void __launch_bounds__(EM_BLOCK, EM_MIN_BLOCKS) k_em_persistent(EmParams p)
+template <int MINB>
+__global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
 {
-    __shared__ double sm_tiles[EM_WARPS][M_TILE_SMEM];
     __shared__ double sm_block[EM_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = gridDim.x * EM_WARPS;
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(EM_BLOCK, EM_MIN_BLOCKS) k_em_persistent(EmPar
     while (it < p.max_iter) {
         e_phase(p, gwarp, nwarps, lane);
         grid_barrier(p.bar, gridDim.x);
-        double dm = m_phase(p, sm_tiles[warp], sm_block, gwarp, nwarps, lane);
+        double dm = m_phase(p, sm_block, gwarp, nwarps, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         __syncthreads();
@@ -213,7 +220,14 @@ __global__ void __launch_bounds__(EM_BLOCK, EM_MIN_BLOCKS) k_em_persistent(EmPar
 int em_query_occupancy(emsar_ctx *ctx)
 {
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent, EM_BLOCK, 0));
+    // register budget variant: 2, 3 or 4 resident CTAs per SM (EMSAR_EM_MINB overrides the default for tuning)
+    int minb = EM_MIN_BLOCKS;
+    const char *e = getenv("EMSAR_EM_MINB");
+    if (e && atoi(e) >= 2 && atoi(e) <= 4) minb = atoi(e);
+    ctx->em_minb = minb;
+    if (minb == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<2>, EM_BLOCK, 0));
+    else if (minb == 3) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<3>, EM_BLOCK, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<4>, EM_BLOCK, 0));
     if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM"); return EMSAR_ERR_CUDA; }
     ctx->em_blocks_per_sm = nb;
     return EMSAR_OK;
@@ -259,7 +273,9 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
-    CU(cudaLaunchKernelEx(&cfg, k_em_persistent, p));
+    if (ctx->em_minb == 2) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<2>, p));
+    else if (ctx->em_minb == 3) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<3>, p));
+    else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<4>, p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     int it = 0; double fd = 0;
