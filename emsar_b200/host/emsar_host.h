@@ -1,0 +1,81 @@
+/*
+ * emsar_host.h — host side of the B200 EMSAR hot path, in C like the reference: the `.rsh` text loader that packs
+ * the class store into CSR, the alignment readers (bowtie / SAM / BAM) with the reference's read-group semantics,
+ * and the output writers. No CUDA here; the numeric work is behind include/emsar_cuda.h.
+ * Reference citations are relative to parklab/emsar v2.0.1 src/.
+ */
+#ifndef EMSAR_HOST_H
+#define EMSAR_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMSAR_HOST_ERRLEN 512
+
+/* ---- rsh index in host memory (product of construct_rsh_from_rshfile, emsar_functions.c:1351-1510),
+ *      flattened in the reference's scan order (scan_rshbucket :2149-2191) ---- */
+typedef struct {
+    int32_t T;              /* max_tid + 1 */
+    int64_t C;              /* max_cid + 1 */
+    int64_t *class_ptr;     /* [C+1] */
+    int32_t *class_tid;     /* [class_ptr[C]] */
+    int32_t nF;             /* nFraglen */
+    int32_t *euma;          /* [C * nF] */
+    uint8_t *has_node;      /* [C] */
+    int32_t min_fraglength, max_fraglength, readlength, max_t_size; /* header fields 3,4,5,2 */
+    int32_t frag_min, frag_max; /* Fraglengths.min/.max (determine_fraglength_range :2471-2475) */
+    char **names;           /* IndexTable[tid] */
+    /* tname -> tid (replaces the reference's character trie, stringhash.c) */
+    uint32_t *name_slots;
+    uint32_t name_mask;
+} emsar_rsh;
+
+int emsar_rsh_load(const char *path, emsar_rsh **out, char *err);
+void emsar_rsh_free(emsar_rsh *r);
+int emsar_rsh_tid(const emsar_rsh *r, const char *name);           /* -1 when absent (search_treehash) */
+int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err); /* print_rsh :2071-2130 */
+
+/* ---- alignment readers ------------------------------------------------------------------------ */
+typedef struct {
+    int pe;            /* -P */
+    char strand;       /* library_strand_type: 0, '+', '-' (set_library_strand_type :16-22) */
+    int max_repeat;    /* -k MAX_REPEAT */
+    char format;       /* 0 = default bowtie output, 's' = SAM, 'b' = BAM (bamflag) */
+    int64_t batch_reads; /* read groups per batch handed to the callback (0 = 1<<20) */
+} emsar_reader_opts;
+
+/* A batch of read groups that passed the reader-side filters (add_alignment_to_list alignment.c:29-60, size <=
+ * MAX_REPEAT, PE: check_fraglen_discrepancy alignment.c:85-95): per group the tids of the kept alignments in file
+ * order and the fragment length of the first one — exactly the argument of update_ReadCounts (:838). */
+typedef int (*emsar_batch_fn)(void *user, int64_t n_reads, const int64_t *read_ptr, const int32_t *read_tid,
+                              const int32_t *read_fraglen);
+
+/* `readlength` is the PE read length (in: rsh header field 5 or -1; out: the value seen). Empty path = stdin.
+ * Returns 0, or non-zero with `err` filled (the reference prints the same text to stderr and exits). */
+int emsar_read_alignments(const emsar_rsh *r, const char *path, const emsar_reader_opts *o, int *readlength,
+                          emsar_batch_fn fn, void *user, char *err);
+
+/* one read group through the reference's list logic; exposed for tests. alignments: arrays of n; keep: out indices.
+ * returns the kept count or -1 when the group is dropped */
+int emsar_filter_group(int n, const int *tid, const int *mm, const int *fraglen, const int *pos, int max_repeat, int pe,
+                       int *keep);
+int emsar_parse_mmstr(const char *s);       /* alignment.c:101-108 */
+int emsar_parse_sam_mmstr(const char *s);   /* emsar_functions.c:418-424 */
+int emsar_check_mate_readid_matching(const char *id1, const char *id2); /* alignment.c:113-126 */
+
+/* ---- writers (print_FPKMfinal :3163-3212, print_FraglengthDist :2477-2493, print_aEUMA_3 :2262-2300) ---- */
+int emsar_write_fpkm(const char *path, const emsar_rsh *r, const double *fpkm, const double *sd, const double *efflen,
+                     const double *ireadcount, const int32_t *ireadcount_int, const double *tpm, char *err);
+int emsar_write_fraglength(const char *path, const emsar_rsh *r, const int32_t *FraglengthCounts, const double *Wf, char *err);
+int emsar_write_segments(const char *path, const emsar_rsh *r, const int32_t *set_id, const double *adjEUMA,
+                         const int32_t *ReadCount, const double *expected, char *err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

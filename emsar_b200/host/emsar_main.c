@@ -1,0 +1,289 @@
+/* emsar — command-line driver of the B200 quantification path. Same flags, positional arguments and output files
+ * as the reference driver (parklab/emsar v2.0.1 src/emsar_main.c:4-511); the per-file loop (:380-488) calls
+ * libemsar_cuda (include/emsar_cuda.h) where the reference calls update_ReadCounts / scan_rshbucket / run_MLE_threads.
+ *
+ * Differences that are visible and deliberate:
+ *   - the estimator is one deterministic EM run, not NUM_ROUND random restarts: `sd.of.FPKM` prints 0.000000, -n is
+ *     accepted and ignored; -e / -r / -i map to eps_abs / eps_rel / max EM iterations when given;
+ *   - -x (build the index from a fasta inside emsar) is not part of the hot path: it fails with a message that
+ *     points to emsar-build + -I;  -T (print suffix array) likewise;  -m/-W/-w (positional bias, undocumented and
+ *     half-implemented in the reference) are rejected;
+ *   - -k above 1024 is rejected (device sort limit, EMSAR_MAX_READ_TIDS);
+ *   - EMSAR_DEVICES=0,1,.. spreads the files of a -M list over several GPUs (one host thread per GPU, no
+ *     communication); EUMAcut then persists per GPU instead of per run.
+ */
+#define _GNU_SOURCE
+#include <getopt.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "emsar_cuda.h"
+#include "emsar_host.h"
+
+#define FILENAMEMAX 1000
+#define MAX_nALNFILES 1000
+
+typedef struct {
+    char rshfile[FILENAMEMAX], fasta[FILENAMEMAX], strand_str[8];
+    int pe, multisample, print_segments, print_rsh, verbose, max_repeat, nthread, max_iter;
+    int min_fl, max_fl, num_round;
+    char bamflag, strand;
+    double eps_abs, eps_rel, delta;
+    const char *outdir, *outprefix;
+    char **aln; int naln;
+} options;
+
+static void die(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+    exit(1);
+}
+
+static void stamp(const options *o, const char *what)
+{
+    if (o->verbose <= 0) return;
+    time_t t = time(NULL);
+    struct tm tm;
+    localtime_r(&t, &tm);
+    char b[32];
+    strftime(b, sizeof b, "%m/%d,%T", &tm);
+    fprintf(stdout, "%s :%s\n", what, b);
+    fflush(stdout);
+}
+
+static void usage(const char *p)
+{
+    fprintf(stdout,
+            "usage: %s <options> -I rshfile outdir outprefix [alignmentfile | listfile (with -M)]\n"
+            "  -I rshfile   rsh index built by emsar-build          -M  third argument is a list of alignment files\n"
+            "  -P           paired-end                              -s  ns|ssf|ssr (SE)  ns|ssfr|ssrf (PE)\n"
+            "  -S / -B      SAM / BAM input (default: bowtie out)   -k  max alignments per read (default 100)\n"
+            "  -g           also write prefix.i.segments            -R  write the rsh index to outdir/prefix.rsh\n"
+            "  -i n         max EM iterations (default 200000)      -e/-r  absolute (reads) / relative EM tolerance\n"
+            "  -d n         delta (lambda scaled by 10^n)           -q / -v  quiet / verbose\n"
+            "  -p -n -b -t -h -F -f are accepted for compatibility; -F/-f are overwritten by the rsh header.\n",
+            p);
+}
+
+typedef struct { emsar_sample *s; int rc; } count_ctx;
+static int on_batch(void *user, int64_t n, const int64_t *ptr, const int32_t *tid, const int32_t *fl)
+{
+    count_ctx *c = (count_ctx *)user;
+    c->rc = emsar_sample_count(c->s, n, ptr, tid, fl);
+    return c->rc;
+}
+
+typedef struct {
+    const options *o; const emsar_rsh *rsh; int device, worker, nworker; int rc;
+} worker_arg;
+
+static int run_file(const options *o, const emsar_rsh *rsh, emsar_index *ix, int i, double *eumacut)
+{
+    char err[EMSAR_HOST_ERRLEN] = "";
+    emsar_sample *s = NULL;
+    int rc = emsar_sample_begin(ix, &s);
+    if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    fprintf(stdout, "alnfile[%d]=%s\n", i, o->aln[i]);
+    emsar_reader_opts ro;
+    memset(&ro, 0, sizeof ro);
+    ro.pe = o->pe; ro.strand = o->strand; ro.max_repeat = o->max_repeat; ro.format = o->bamflag; ro.batch_reads = 1 << 21;
+    int readlength = rsh->readlength;
+    count_ctx cc = {s, 0};
+    if (emsar_read_alignments(rsh, o->aln[i], &ro, &readlength, on_batch, &cc, err)) {
+        if (cc.rc) die("%s: %s", emsar_cuda_strerror(cc.rc), emsar_cuda_last_error());
+        die("%s", err);
+    }
+    stamp(o, "\nscanning rsh array and constructing EUMA, ReadCount and CT array...");
+    emsar_solve_opts so;
+    memset(&so, 0, sizeof so);
+    so.eps_abs = o->eps_abs; so.eps_rel = o->eps_rel; so.max_iter = o->max_iter; so.delta = o->delta; so.eumacut = *eumacut;
+    emsar_solve_out out;
+    memset(&out, 0, sizeof out);
+    const int32_t T = rsh->T;
+    out.fpkm = (double *)malloc(sizeof(double) * T);
+    out.efflen = (double *)malloc(sizeof(double) * T);
+    out.ireadcount = (double *)malloc(sizeof(double) * T);
+    out.ireadcount_int = (int32_t *)malloc(sizeof(int32_t) * T);
+    out.tpm = (double *)malloc(sizeof(double) * T);
+    rc = emsar_sample_solve(s, &so, &out);
+    if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    if (out.eumacut != *eumacut && o->verbose > 0) fprintf(stdout, "module size too big. EUMAcut is readjusted to %.0f\n", out.eumacut);
+    *eumacut = out.eumacut;   /* EUMAcut is a global that is never reset between files (emsar.h:94) */
+    if (o->verbose > 0)
+        fprintf(stdout, "EM finished: %d iterations, delta %.3g, %.1f ms on the device (model build %.1f ms), logL %.10g\n",
+                out.n_iter, out.final_delta, out.em_ms, out.prep_ms, out.loglik);
+    int32_t *F = (int32_t *)malloc(sizeof(int32_t) * ((size_t)rsh->max_fraglength + 1));
+    int32_t *R = (int32_t *)malloc(sizeof(int32_t) * (size_t)rsh->C);
+    double *Wf = (double *)malloc(sizeof(double) * rsh->nF);
+    int64_t N = 0;
+    if ((rc = emsar_sample_counts_get(s, R, F, &N)) || (rc = emsar_sample_wf_get(s, Wf))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    char p1[FILENAMEMAX * 2 + 64], p2[FILENAMEMAX * 2 + 64], p3[FILENAMEMAX * 2 + 64];
+    snprintf(p1, sizeof p1, "%s/%s.%d.fpkm", o->outdir, o->outprefix, i);
+    snprintf(p2, sizeof p2, "%s/%s.%d.fraglength_effect", o->outdir, o->outprefix, i);
+    snprintf(p3, sizeof p3, "%s/%s.%d.segments", o->outdir, o->outprefix, i);
+    if (emsar_write_fpkm(p1, rsh, out.fpkm, NULL, out.efflen, out.ireadcount, out.ireadcount_int, out.tpm, err)) die("%s", err);
+    if (o->verbose > 0) fprintf(stdout, "Total inferred readcount=%lld\n", (long long)out.total_ireadcount);
+    if (emsar_write_fraglength(p2, rsh, F, Wf, err)) die("%s", err);
+    if (o->print_segments) {
+        double *adj = (double *)malloc(sizeof(double) * (size_t)rsh->C), *ex = (double *)malloc(sizeof(double) * (size_t)rsh->C);
+        int32_t *cs = (int32_t *)malloc(sizeof(int32_t) * (size_t)rsh->C);
+        if ((rc = emsar_sample_segments_get(s, adj, ex, cs))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+        if (emsar_write_segments(p3, rsh, cs, adj, R, ex, err)) die("%s", err);
+        free(adj); free(ex); free(cs);
+    }
+    fprintf(stdout, "Complete: Output file :\n  %s\n  %s\n", p1, p2);
+    if (o->print_segments) fprintf(stdout, "  %s\n", p3);
+    fflush(stdout);
+    free(F); free(R); free(Wf);
+    free(out.fpkm); free(out.efflen); free(out.ireadcount); free(out.ireadcount_int); free(out.tpm);
+    emsar_sample_end(s);
+    return 0;
+}
+
+static void *worker(void *p)
+{
+    worker_arg *w = (worker_arg *)p;
+    const options *o = w->o;
+    emsar_ctx *ctx = NULL;
+    int rc = emsar_cuda_open(w->device, &ctx);
+    if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    emsar_index_desc d;
+    memset(&d, 0, sizeof d);
+    const emsar_rsh *r = w->rsh;
+    d.T = r->T; d.C = r->C; d.class_ptr = r->class_ptr; d.class_tid = r->class_tid; d.nF = r->nF; d.euma = r->euma; d.has_node = r->has_node;
+    d.min_fraglength = r->min_fraglength; d.max_fraglength = r->max_fraglength; d.readlength = r->readlength; d.max_t_size = r->max_t_size;
+    emsar_index *ix = NULL;
+    rc = emsar_index_create(ctx, &d, &ix);
+    if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    double eumacut = 0;
+    for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ix, i, &eumacut);
+    emsar_index_destroy(ix);
+    emsar_cuda_close(ctx);
+    return NULL;
+}
+
+int main(int argc, char *argv[])
+{
+    options o;
+    memset(&o, 0, sizeof o);
+    if (argc < 3) { usage(argv[0]); return 0; }
+    static struct option long_options[] = {
+        {"rsh", required_argument, 0, 'I'}, {"fasta", required_argument, 0, 'x'}, {"print_segments", no_argument, 0, 'g'},
+        {"print_sfa", no_argument, 0, 'T'}, {"print_rsh", no_argument, 0, 'R'}, {"BAM", no_argument, 0, 'B'}, {"SAM", no_argument, 0, 'S'},
+        {"PE", no_argument, 0, 'P'}, {"strand_type", required_argument, 0, 's'}, {"multisample", no_argument, 0, 'M'},
+        {"bias_model", required_argument, 0, 'm'}, {"posbias_training_len", required_argument, 0, 'W'},
+        {"posbias_impute_len", required_argument, 0, 'w'}, {"binsize", required_argument, 0, 'b'}, {"maxthread", required_argument, 0, 'p'},
+        {"header", required_argument, 0, 'h'}, {"taglen", required_argument, 0, 't'}, {"maxfraglen", required_argument, 0, 'F'},
+        {"minfraglen", required_argument, 0, 'f'}, {"max_repeat", required_argument, 0, 'k'}, {"nround", required_argument, 0, 'n'},
+        {"epsilon", required_argument, 0, 'e'}, {"precision", required_argument, 0, 'r'}, {"delta", required_argument, 0, 'd'},
+        {"max_niter_mle", required_argument, 0, 'i'}, {"max_nloop_mle", required_argument, 0, 'l'}, {"verbose", no_argument, 0, 'v'},
+        {"no_verbose", no_argument, 0, 'q'}, {0, 0, 0, 0}};
+    /* defaults (emsar_main.c:64-91) */
+    strcpy(o.strand_str, "ns");
+    o.max_fl = 400; o.min_fl = 1; o.max_repeat = 100; o.verbose = 1; o.nthread = 1; o.num_round = 4;
+    int c, oi;
+    while ((c = getopt_long(argc, argv, "vqPs:b:p:h:t:F:f:n:e:r:p:d:gm:MHBSW:w:k:i:l:TRI:x:", long_options, &oi)) != -1) {
+        switch (c) {
+        case 'I': strncpy(o.rshfile, optarg, FILENAMEMAX - 1); break;
+        case 'x': strncpy(o.fasta, optarg, FILENAMEMAX - 1); break;
+        case 'P': o.pe = 1; break;
+        case 's': strncpy(o.strand_str, optarg, sizeof(o.strand_str) - 1); break;
+        case 'b': case 'h': case 't': case 'l': case 'H': break;                 /* index-build / MLE-loop knobs: accepted, unused */
+        case 'p': o.nthread = atoi(optarg); if (o.nthread < 1) die("error: number of threads must be at least 1 (option -p)."); break;
+        case 'F': o.max_fl = atoi(optarg); break;
+        case 'f': o.min_fl = atoi(optarg); break;
+        case 'k': o.max_repeat = atoi(optarg); break;
+        case 'n': o.num_round = atoi(optarg); if (o.num_round <= 0) { fprintf(stderr, "option -n must be a natural number.\n"); return 0; } break;
+        case 'e': o.eps_abs = atof(optarg); if (o.eps_abs <= 0) { fprintf(stderr, "option -e must be positive.\n"); return 0; } break;
+        case 'r': o.eps_rel = atof(optarg); if (o.eps_rel <= 0) { fprintf(stderr, "option -p must be positive.\n"); return 0; } break;
+        case 'i': o.max_iter = atoi(optarg); if (o.max_iter <= 0) { fprintf(stderr, "option -i must be positive.\n"); return 0; } break;
+        case 'd': o.delta = atoi(optarg); break;
+        case 'g': o.print_segments = 1; break;
+        case 'm': if (optarg[0] != '0') die("positional bias model (-m 1) is not supported by this build."); break;
+        case 'W': case 'w': break;
+        case 'M': o.multisample = 1; break;
+        case 'B': if (o.bamflag == 's') { fprintf(stderr, "error: Options -B(--BAM) and -S(--SAM) cannot be used simultaneously.\n"); return 0; } o.bamflag = 'b'; break;
+        case 'S': if (o.bamflag == 'b') { fprintf(stderr, "error: Options -B(--BAM) and -S(--SAM) cannot be used simultaneously.\n"); return 0; } o.bamflag = 's'; break;
+        case 'T': die("-T (print suffix array) belongs to index construction: use emsar-build.");
+        case 'R': o.print_rsh = 1; break;
+        case 'v': o.verbose = 2; break;
+        case 'q': o.verbose = 0; break;
+        case '?': fprintf(stderr, "error: unknown option?\n"); /* fallthrough */
+        default: return 0;
+        }
+    }
+    if (strlen(o.rshfile) == 0 && strlen(o.fasta) == 0) die("error: either fasta file or an rsh file must be used as an input.");
+    if (strlen(o.rshfile) == 0)
+        die("error: -x builds the rsh index from a fasta, which is outside the GPU hot path: run emsar-build once and pass its output with -I.");
+    if (o.min_fl > o.max_fl || o.min_fl < 1 || o.max_fl < 1) die("error: invalid fragment length range.");
+    /* set_library_strand_type (:16-22); unlike the reference an unknown type IS an error here */
+    if (!strcmp(o.strand_str, "ns")) o.strand = 0;
+    else if (!strcmp(o.strand_str, "ssf") && !o.pe) o.strand = '+';
+    else if (!strcmp(o.strand_str, "ssr") && !o.pe) o.strand = '-';
+    else if (!strcmp(o.strand_str, "ssfr") && o.pe) o.strand = '+';
+    else if (!strcmp(o.strand_str, "ssrf") && o.pe) o.strand = '-';
+    else die("error: invalid strand type.");
+    if (o.max_repeat > EMSAR_MAX_READ_TIDS) die("error: -k %d exceeds the supported maximum of %d alignments per read.", o.max_repeat, EMSAR_MAX_READ_TIDS);
+    if (optind + 1 >= argc) { usage(argv[0]); return 0; }
+    o.outdir = argv[optind]; o.outprefix = argv[optind + 1];
+    const char *third = optind + 2 < argc ? argv[optind + 2] : "";
+    o.aln = (char **)malloc(sizeof(char *) * MAX_nALNFILES);
+    if (!o.multisample) { o.aln[0] = strdup(third); o.naln = 1; }
+    else {
+        FILE *lf = fopen(third, "r");
+        if (!lf) { fprintf(stderr, "Can't open alignment list file.\n"); return 1; }
+        char line[FILENAMEMAX];
+        while (fgets(line, sizeof line, lf) && o.naln < MAX_nALNFILES) {
+            size_t n = strlen(line);
+            if (n && line[n - 1] == '\n') line[n - 1] = 0;
+            o.aln[o.naln++] = strdup(line);
+        }
+        fclose(lf);
+    }
+    if (o.naln == 0) { fprintf(stderr, "No alignment files in the alignment list\n"); return 1; }
+    if (o.verbose > 0) {
+        fprintf(stdout, "input rshfile name= %s\nInput type= %s\nPaired-end= %c\nstrand type= %s\nMultisample= %c\nMAX_REPEAT= %d\n", o.rshfile,
+                o.bamflag == 0 ? "default bowtie output" : (o.bamflag == 's' ? "SAM" : "BAM"), o.pe ? 'y' : 'n', o.strand_str, o.multisample ? 'y' : 'n', o.max_repeat);
+        fprintf(stdout, "print segments = %c\nprint rsh structure = %c\nfinished reading options and arguments..\n", o.print_segments ? 'y' : 'n', o.print_rsh ? 'y' : 'n');
+    }
+    char cmd[FILENAMEMAX + 16];
+    snprintf(cmd, sizeof cmd, "mkdir -p %s", o.outdir);
+    fflush(stdout);
+    if (system(cmd) != 0) die("can't create output directory %s", o.outdir);
+    stamp(&o, "reading rsh array...");
+    char err[EMSAR_HOST_ERRLEN] = "";
+    emsar_rsh *rsh = NULL;
+    if (emsar_rsh_load(o.rshfile, &rsh, err)) { printf("%s\n", err); exit(1); }
+    fprintf(stderr, "done reading rsh. rshsize=%lld\n", (long long)(rsh->C - rsh->T));
+    if (o.verbose > 0) fprintf(stdout, "max_tid=%d, rshsize=%lld, max_cid=%lld\n", rsh->T - 1, (long long)(rsh->C - rsh->T), (long long)rsh->C - 1);
+    if (o.print_rsh) {
+        char p[FILENAMEMAX * 2 + 16];
+        snprintf(p, sizeof p, "%s/%s.rsh", o.outdir, o.outprefix);
+        if (emsar_rsh_write(rsh, o.pe, p, err)) die("%s", err);
+    }
+    stamp(&o, "reading alignment file(s)...");
+    /* devices: EMSAR_DEVICES="0,1,2" (default "0") — files of a -M list are spread over them, no communication */
+    int devs[64], ndev = 0;
+    const char *env = getenv("EMSAR_DEVICES");
+    if (env && *env) { char *dup = strdup(env), *sv = NULL; for (char *t = strtok_r(dup, ",", &sv); t && ndev < 64; t = strtok_r(NULL, ",", &sv)) devs[ndev++] = atoi(t); free(dup); }
+    if (ndev == 0) devs[ndev++] = 0;
+    if (ndev > o.naln) ndev = o.naln;
+    pthread_t th[64];
+    worker_arg wa[64];
+    for (int w = 0; w < ndev; w++) { wa[w].o = &o; wa[w].rsh = rsh; wa[w].device = devs[w]; wa[w].worker = w; wa[w].nworker = ndev; wa[w].rc = 0; }
+    for (int w = 1; w < ndev; w++) pthread_create(&th[w], NULL, worker, &wa[w]);
+    worker(&wa[0]);
+    for (int w = 1; w < ndev; w++) pthread_join(th[w], NULL);
+    stamp(&o, "freeing rsh array ...");
+    emsar_rsh_free(rsh);
+    return 0;
+}

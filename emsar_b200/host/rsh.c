@@ -1,0 +1,232 @@
+/* `.rsh` text index: loader (reference construct_rsh_from_rshfile, emsar_functions.c:1351-1510), writer (print_rsh
+ * :2071-2130) and the tname -> tid map (the reference uses a character trie, stringhash.c; any map will do).
+ * The loader flattens the class store directly into the reference's scan order (scan_rshbucket :2149-2191):
+ * all singletons in tid order, then multi-tid classes by cardinality, first tid and chain (file) order. */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "emsar_host.h"
+
+static int fail(char *err, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    if (err) vsnprintf(err, EMSAR_HOST_ERRLEN, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+static uint32_t fnv1a(const char *s)
+{
+    uint32_t h = 2166136261u;
+    for (; *s; s++) { h ^= (unsigned char)*s; h *= 16777619u; }
+    return h;
+}
+
+int emsar_rsh_tid(const emsar_rsh *r, const char *name)
+{
+    uint32_t s = fnv1a(name) & r->name_mask;
+    for (;;) {
+        uint32_t v = r->name_slots[s];
+        if (v == 0) return -1;
+        if (r->names[v - 1] && strcmp(r->names[v - 1], name) == 0) return (int)(v - 1);
+        s = (s + 1) & r->name_mask;
+    }
+}
+
+static void name_insert(emsar_rsh *r, int tid)
+{
+    /* insert_key (stringhash.c): a later identical name overwrites the value, so lookups return the LAST tid */
+    uint32_t s = fnv1a(r->names[tid]) & r->name_mask;
+    for (;;) {
+        uint32_t v = r->name_slots[s];
+        if (v == 0) { r->name_slots[s] = (uint32_t)tid + 1; return; }
+        if (strcmp(r->names[v - 1], r->names[tid]) == 0) { r->name_slots[s] = (uint32_t)tid + 1; return; }
+        s = (s + 1) & r->name_mask;
+    }
+}
+
+void emsar_rsh_free(emsar_rsh *r)
+{
+    if (!r) return;
+    if (r->names) { for (int32_t t = 0; t < r->T; t++) free(r->names[t]); free(r->names); }
+    free(r->class_ptr); free(r->class_tid); free(r->euma); free(r->has_node); free(r->name_slots);
+    free(r);
+}
+
+/* split `line` in place at `sep`; returns the number of fields (pointers into line) */
+static int split(char *line, char sep, char **f, int maxf)
+{
+    int n = 0;
+    char *p = line;
+    f[n++] = p;
+    for (; *p; p++)
+        if (*p == sep) { *p = 0; if (n < maxf) f[n++] = p + 1; else return n; }
+    return n;
+}
+
+typedef struct { int32_t k, tid0; int64_t seq, tid_off, euma_off; } mrec;
+static int mrec_cmp(const void *a, const void *b)
+{
+    const mrec *x = (const mrec *)a, *y = (const mrec *)b;
+    if (x->k != y->k) return x->k < y->k ? -1 : 1;
+    if (x->tid0 != y->tid0) return x->tid0 < y->tid0 ? -1 : 1;
+    return x->seq < y->seq ? -1 : (x->seq > y->seq ? 1 : 0);
+}
+
+/* values are terminated by ',' like the reference's loops (:1459-1467, :1475-1483): a last value without a
+ * trailing comma is never stored */
+static int parse_commas(const char *s, int32_t *out, int maxn)
+{
+    int n = 0;
+    const char *start = s;
+    for (const char *p = s; *p; p++)
+        if (*p == ',') { if (n < maxn) out[n] = atoi(start); n++; start = p + 1; }
+    return n;
+}
+
+int emsar_rsh_load(const char *path, emsar_rsh **out, char *err)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return fail(err, "can't open input rsh file.");
+    emsar_rsh *r = (emsar_rsh *)calloc(1, sizeof(emsar_rsh));
+    char *line = NULL;
+    size_t cap = 0;
+    ssize_t len;
+    int have_header = 0;
+    mrec *m = NULL; int64_t nm = 0, capm = 0;
+    int32_t *tpool = NULL; int64_t ntp = 0, captp = 0;
+    int32_t *epool = NULL; int64_t nep = 0, capep = 0;
+    int32_t *s_euma = NULL; /* singleton EUMA rows [T*nF] */
+    int rc = 0;
+    int64_t lineno = 0;
+    while ((len = getline(&line, &cap, f)) >= 0) {
+        lineno++;
+        if (len > 0 && line[len - 1] == '\n') line[--len] = 0;
+        if (line[0] == '#') {                                   /* parse_rsh_headerline :1406-1430 */
+            char *fld[8];
+            int n = split(line, ',', fld, 8);
+            if (n < 5) { rc = fail(err, "rsh header line has %d fields, need 5", n); break; }
+            r->T = atoi(fld[0] + 1) + 1;
+            r->max_t_size = atoi(fld[1]);
+            r->min_fraglength = atoi(fld[2]);
+            r->max_fraglength = atoi(fld[3]);
+            r->readlength = atoi(fld[4]);
+            if (r->T <= 0) { rc = fail(err, "rsh header: bad max_tid"); break; }
+            r->frag_min = r->min_fraglength > r->readlength ? r->min_fraglength : r->readlength;
+            r->frag_max = r->max_fraglength >= r->frag_min ? r->max_fraglength : r->frag_min;
+            r->nF = r->frag_max - r->frag_min + 1;
+            r->names = (char **)calloc((size_t)r->T, sizeof(char *));
+            r->has_node = NULL;
+            s_euma = (int32_t *)calloc((size_t)r->T * r->nF, sizeof(int32_t));
+            r->has_node = (uint8_t *)calloc((size_t)r->T, 1);
+            have_header = 1;
+        } else if (line[0] == '@') {                            /* parse_rsh_indexline :1381-1403 */
+            if (!have_header) { rc = fail(err, "rsh: index line before the header"); break; }
+            char *fld[3];
+            int n = split(line, '\t', fld, 3);
+            int tid = atoi(fld[0] + 1);
+            if (n < 2 || tid < 0 || tid >= r->T) { rc = fail(err, "rsh line %lld: bad index line", (long long)lineno); break; }
+            free(r->names[tid]);
+            r->names[tid] = strdup(fld[1]);
+        } else if (line[0] != 'c') {                            /* parse_rsh_mainline :1432-1510 */
+            if (!have_header) { rc = fail(err, "rsh: class line before the header"); break; }
+            if (line[0] == 0) continue;
+            char *fld[6];
+            int n = split(line, '\t', fld, 6);
+            if (n < 3) { rc = fail(err, "rsh line %lld: too few fields", (long long)lineno); break; }
+            int k = atoi(fld[1]), tid0 = atoi(fld[2]);
+            const char *others = n > 3 ? fld[3] : "", *eu = n > 4 ? fld[4] : "";
+            if (k < 1 || tid0 < 0 || tid0 >= r->T) { rc = fail(err, "rsh line %lld: bad cardinality or tid", (long long)lineno); break; }
+            if (strlen(eu) == 0) continue;                      /* no EUMA: no node is created (:1486) */
+            if (k == 1) {
+                int32_t *row = s_euma + (size_t)tid0 * r->nF;
+                memset(row, 0, sizeof(int32_t) * r->nF);
+                parse_commas(eu, row, r->nF);
+                r->has_node[tid0] = 1;                          /* a later line replaces an earlier one (:1488) */
+                continue;
+            }
+            if (k > r->max_t_size) { rc = fail(err, "rsh line %lld: %d tids exceed header max_t_size %d", (long long)lineno, k, r->max_t_size); break; }
+            if (nm == capm) { capm = capm ? capm * 2 : 1 << 16; m = (mrec *)realloc(m, sizeof(mrec) * capm); }
+            if (ntp + k > captp) { captp = captp ? captp * 2 : 1 << 18; while (ntp + k > captp) captp *= 2; tpool = (int32_t *)realloc(tpool, sizeof(int32_t) * captp); }
+            if (nep + r->nF > capep) { capep = capep ? capep * 2 : 1 << 18; while (nep + r->nF > capep) capep *= 2; epool = (int32_t *)realloc(epool, sizeof(int32_t) * capep); }
+            tpool[ntp] = tid0;
+            int got = parse_commas(others, tpool + ntp + 1, k - 1);
+            if (got != k - 1) { rc = fail(err, "rsh line %lld: %d other tids, expected %d", (long long)lineno, got, k - 1); break; }
+            for (int j = 0; j < k; j++) {
+                if (tpool[ntp + j] < 0 || tpool[ntp + j] >= r->T) { rc = fail(err, "rsh line %lld: tid out of range", (long long)lineno); break; }
+                if (j && tpool[ntp + j] < tpool[ntp + j - 1]) { rc = fail(err, "rsh line %lld: tids not sorted", (long long)lineno); break; }
+            }
+            if (rc) break;
+            memset(epool + nep, 0, sizeof(int32_t) * r->nF);
+            parse_commas(eu, epool + nep, r->nF);
+            m[nm].k = k; m[nm].tid0 = tid0; m[nm].seq = nm; m[nm].tid_off = ntp; m[nm].euma_off = nep;
+            nm++; ntp += k; nep += r->nF;
+        }
+    }
+    free(line);
+    fclose(f);
+    if (!rc && !have_header) rc = fail(err, "rsh file has no header line");
+    if (!rc) {
+        /* chains are appended behind the LAST node read (lastp, :1495-1502): a (cardinality, first tid) chain that is
+         * revisited after another chain was started cannot be represented by the reference; reject such files */
+        qsort(m, (size_t)nm, sizeof(mrec), mrec_cmp);
+        for (int64_t i = 1; i < nm && !rc; i++)
+            if (m[i].k == m[i - 1].k && m[i].tid0 == m[i - 1].tid0 && m[i].seq != m[i - 1].seq + 1)
+                rc = fail(err, "rsh: classes with %d tids starting at tid %d are not contiguous in the file", m[i].k, m[i].tid0);
+    }
+    if (!rc) {
+        for (int32_t t = 0; t < r->T; t++)
+            if (!r->names[t]) { char b[32]; snprintf(b, sizeof b, "tid%d", t); r->names[t] = strdup(b); }
+        r->C = (int64_t)r->T + nm;
+        r->class_ptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(r->C + 1));
+        r->class_tid = (int32_t *)malloc(sizeof(int32_t) * (size_t)(r->T + ntp > 0 ? r->T + ntp : 1));
+        r->euma = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->C * r->nF);
+        r->has_node = (uint8_t *)realloc(r->has_node, (size_t)r->C);
+        for (int32_t t = 0; t < r->T; t++) { r->class_ptr[t] = t; r->class_tid[t] = t; }
+        memcpy(r->euma, s_euma, sizeof(int32_t) * (size_t)r->T * r->nF);
+        int64_t o = r->T;
+        for (int64_t i = 0; i < nm; i++) {
+            int64_t c = r->T + i;
+            r->class_ptr[c] = o;
+            memcpy(r->class_tid + o, tpool + m[i].tid_off, sizeof(int32_t) * m[i].k);
+            memcpy(r->euma + (size_t)c * r->nF, epool + m[i].euma_off, sizeof(int32_t) * r->nF);
+            r->has_node[c] = 1;
+            o += m[i].k;
+        }
+        r->class_ptr[r->C] = o;
+        uint32_t slots = 16;
+        while (slots < (uint32_t)r->T * 2u) slots <<= 1;
+        r->name_mask = slots - 1;
+        r->name_slots = (uint32_t *)calloc(slots, sizeof(uint32_t));
+        for (int32_t t = 0; t < r->T; t++) name_insert(r, t);
+    }
+    free(m); free(tpool); free(epool); free(s_euma);
+    if (rc) { emsar_rsh_free(r); return rc; }
+    *out = r;
+    return 0;
+}
+
+int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return fail(err, "Can't write to output rsh file %s", path);
+    fprintf(f, "#%d,%d,%d,%d,%d\n", r->T - 1, r->max_t_size, r->frag_min, r->frag_max, pe ? r->readlength : -1);
+    for (int32_t t = 0; t < r->T; t++) fprintf(f, "@%d\t%s\n", t, r->names[t]);
+    fprintf(f, "cid\tno.tids\tfirst.tid\tother.tids\tsegment.length\n");
+    for (int64_t c = 0; c < r->C; c++) {
+        int64_t o = r->class_ptr[c];
+        int k = (int)(r->class_ptr[c + 1] - o);
+        if (k == 1 && !r->has_node[c]) { fprintf(f, "%lld\t%d\t%d\t\t\t\n", (long long)c, 1, r->class_tid[o]); continue; }
+        fprintf(f, "%lld\t%d\t%d\t", (long long)c, k, r->class_tid[o]);
+        for (int j = 1; j < k; j++) fprintf(f, "%d,", r->class_tid[o + j]);
+        fprintf(f, "\t");
+        for (int i = 0; i < r->nF; i++) fprintf(f, "%d,", r->euma[(size_t)c * r->nF + i]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return 0;
+}

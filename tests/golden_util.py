@@ -1,0 +1,76 @@
+"""Helpers for the golden fixtures under tests/golden/ (made by tests/golden/make_golden.py from the unmodified
+reference binaries)."""
+import gzip
+import os
+import shutil
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# name -> (alignment file, format, pe, strand, -k)
+FIXTURES = {
+    "se": dict(aln="se.in.bowtie", rsh="se.in.rsh", fmt="bowtie", pe=False, strand="ns", k=100, out="se", rounds=8),
+    "pe": dict(aln="pe.in.sam", rsh="pe.in.rsh", fmt="sam", pe=True, strand="ns", k=100, out="pe", rounds=8),
+    "pe_bam_ssfr": dict(aln="pe.in.bam", rsh="pe.in.rsh", fmt="bam", pe=True, strand="ssfr", k=100, out="pe_bam_ssfr", rounds=2),
+    "crafted": dict(aln="crafted.in.bowtie", rsh="crafted.in.rsh", fmt="bowtie", pe=False, strand="ssf", k=3, out="crafted", rounds=2),
+    "built": dict(aln="built.in.sam", rsh="built.in.rsh", fmt="sam", pe=False, strand="ssf", k=100, out="built", rounds=8),
+    "bowtie_pe_ns": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ns", k=100, out="bowtie_pe_ns", rounds=2),
+    "bowtie_pe_ssfr": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ssfr", k=100, out="bowtie_pe_ssfr", rounds=2),
+    "bowtie_pe_ssrf": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ssrf", k=100, out="bowtie_pe_ssrf", rounds=2),
+}
+
+
+def materialize(name, tmpdir):
+    """Gunzip a fixture file into tmpdir and return its path (the .bam is stored as is)."""
+    src = os.path.join(GOLD, name)
+    dst = os.path.join(str(tmpdir), name)
+    if os.path.exists(src):
+        shutil.copy(src, dst)
+    else:
+        with gzip.open(src + ".gz", "rb") as f, open(dst, "wb") as g:
+            shutil.copyfileobj(f, g)
+    return dst
+
+
+def _rows(name):
+    with gzip.open(os.path.join(GOLD, name + ".gz"), "rt") as f:
+        return [l.rstrip("\n").split("\t") for l in f][1:]
+
+
+def read_segments(prefix):
+    rows = _rows(prefix + ".p.0.segments")
+    return dict(set_id=np.array([int(r[1][1:]) for r in rows], dtype=np.int32), adjEUMA=np.array([float(r[4]) for r in rows]),
+                ReadCount=np.array([int(r[5]) for r in rows], dtype=np.int32), expected=np.array([float(r[6]) for r in rows]),
+                text=rows)
+
+
+def read_fraglength(prefix):
+    rows = _rows(prefix + ".p.0.fraglength_effect")
+    return dict(length=np.array([int(r[0]) for r in rows]), counts=np.array([int(r[1]) for r in rows], dtype=np.int64),
+                Wf=np.array([float(r[2]) for r in rows]), text=rows)
+
+
+def has_fpkm(prefix):
+    return os.path.exists(os.path.join(GOLD, prefix + ".p.0.fpkm.gz"))
+
+
+def read_fpkm(prefix):
+    rows = _rows(prefix + ".p.0.fpkm")
+    f = lambda i: np.array([float(r[i]) for r in rows])
+    return dict(names=[r[0] for r in rows], fpkm=f(1), sd=f(2), efflen=f(3), ireadcount=f(4),
+                ireadcount_int=np.array([int(r[5]) for r in rows]), tpm=f(6))
+
+
+def parse_out_file(path):
+    with open(path) as f:
+        return [l.rstrip("\n").split("\t") for l in f][1:]
+
+
+def fpkm_tolerance(gold_fpkm, efflen, N, rounds):
+    """|x - m| <= max(1e-6 |m|, 1e-3 reads-equivalent, 6 s_t) (+ the file's print precision)."""
+    m = gold_fpkm["fpkm"]
+    s_t = gold_fpkm["sd"] * rounds            # the file stores sd / NUM_ROUND (:3200)
+    s_t = np.where(np.isfinite(s_t), s_t, 0.0)
+    per_read = np.where(efflen > 0, 1e-3 / np.maximum(efflen / 1e3 * N / 1e6, 1e-300), np.inf)
+    return np.maximum(np.maximum(1e-6 * np.abs(m), 6 * s_t), per_read) + 2e-6
