@@ -1,4 +1,7 @@
-// The EM loop: one persistent cooperative kernel (one wave of CTAs resident on all 148 SMs) that runs
+// The EM loop: one persistent cooperative kernel, one CTA per SM. Each CTA owns a contiguous range of transcripts
+// (rows) and the classes whose first member lies in it, and keeps theta / q of what it owns in SHARED MEMORY: the
+// gathers of both phases hit 32 independent banks instead of one L1 line per wavefront; only references that leave
+// the range (halo) go through the L2-resident global copies. Per iteration:
 //   E-phase  q_c = R_c / sum_{t in c} theta_t        class-major, binned by cardinality
 //   -- grid barrier --
 //   M-phase  theta_t' = (Rs_t + theta_t * sum_{c∋t} q_c) / A_t   transposed CSR, deterministic segmented reduction,
@@ -45,134 +48,200 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
     __syncthreads();
 }
 
-// ---- E-phase ---------------------------------------------------------------------------------------
+// ---- shared-memory resident slices ---------------------------------------------------------------------
+struct BlockView {
+    double *sm_theta;          // theta of the rows this CTA owns
+    double *sm_q;              // q of the resident classes this CTA owns
+    const int4 *sm_etiles;     // this CTA's E tile descriptors
+    const int2 *sm_mtiles;     // this CTA's row tiles
+    const uint32_t *sm_rowoff; // row_off[row0 .. row0+nrows]
+    int row0, nrows, cls0, nres;
+};
+
+__device__ __forceinline__ double load_theta(const EmParams &p, const BlockView &v, int enc)
+{
+    return enc >= 0 ? v.sm_theta[enc] : p.m.theta[~enc];
+}
+__device__ __forceinline__ double load_q(const EmParams &p, const BlockView &v, int enc)
+{
+    return enc >= 0 ? v.sm_q[enc] : p.m.q[~enc];
+}
+__device__ __forceinline__ void store_q(const EmParams &p, const BlockView &v, int j, uint32_t rflag, double s)
+{
+    const double r = (double)(rflag & 0x7fffffffu);
+    const double val = s > 0 ? r / s : 0.0;
+    const int loc = j - v.cls0;
+    if (loc < v.nres) v.sm_q[loc] = val;
+    if (rflag & 0x80000000u) p.m.q[j] = val;        // a row of another CTA reads it, or it does not fit in shared memory
+}
+
+// ---- index staging: a tile's chunk of the int32 index stream -> this warp's shared buffer via cp.async ------------
+// The chunk [g, g+n) is fetched from its 16-byte-aligned floor; entry i then sits at buf[shift + i].
+__device__ __forceinline__ int stage_issue(int *buf, const int32_t *g, int n, int lane)
+{
+    const uintptr_t ga = (uintptr_t)g & ~(uintptr_t)15;
+    const int shift = (int)(((uintptr_t)g - ga) >> 2);
+    const int chunks = (n + shift + 3) >> 2;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    for (int c = lane; c < chunks; c += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + c * 16), "l"(ga + (uintptr_t)c * 16));
+    return shift;
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct Idx {                   // a tile's index chunk: staged in shared memory, or (oversized tiles) straight from global
+    const int *sm;
+    const int32_t *g;
+    bool staged;
+    __device__ __forceinline__ int operator[](int i) const { return staged ? sm[i] : __ldg(g + i); }
+};
+
+__device__ __forceinline__ int etile_ints(int4 t)
+{
+    const int k = t.w & 0xffff, mode = t.w >> 16;
+    return mode == 0 ? 32 * k : t.y * k;
+}
+
+// ---- E-phase: q_c = R_c / sum of theta over the class members --------------------------------------------------
 template <int K>
-__device__ __forceinline__ double esum_tp(const int32_t *__restrict__ tids, const double *theta, int lane)
+__device__ __forceinline__ double esum_tp(const EmParams &p, const BlockView &v, const Idx &ix, int lane)
 {
     int t[K];
 #pragma unroll
-    for (int j = 0; j < K; j++) t[j] = __ldg(tids + j * 32 + lane);
-    double v[K];
+    for (int j = 0; j < K; j++) t[j] = ix[j * 32 + lane];
+    double x[K];
 #pragma unroll
-    for (int j = 0; j < K; j++) v[j] = theta[t[j]];
+    for (int j = 0; j < K; j++) x[j] = load_theta(p, v, t[j]);
     double s = 0;
 #pragma unroll
-    for (int j = 0; j < K; j++) s += v[j];      // sequential member order
+    for (int j = 0; j < K; j++) s += x[j];      // sequential member order
     return s;
 }
 
 template <int G>
-__device__ __forceinline__ void etile_group(const EmParams &p, int4 tile, int k, int lane)
+__device__ __forceinline__ void etile_group(const EmParams &p, const BlockView &v, int4 tile, int k, const Idx &ix, int lane)
 {
     constexpr int CPP = 32 / G;          // classes per pass
     const int sub = lane / G, l = lane % G;
-    const double *theta = p.m.theta;
     for (int c0 = 0; c0 < tile.y; c0 += CPP) {
         const int cl = c0 + sub;
         const bool valid = cl < tile.y;
         double s = 0;
         if (valid) {
-            const int32_t *tids = p.m.e_tid + (uint32_t)tile.z + (uint32_t)cl * (uint32_t)k;
+            const int base = cl * k;
 #pragma unroll 4
-            for (int i = l; i < k; i += G) s += theta[__ldg(tids + i)];
+            for (int i = l; i < k; i += G) s += load_theta(p, v, ix[base + i]);
         }
 #pragma unroll
         for (int d = G / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (valid && l == 0) {
-            const int j = tile.x + cl;
-            const double r = (double)__ldg(p.m.e_R + j);
-            p.m.q[j] = s > 0 ? r / s : 0.0;
-        }
+        if (valid && l == 0) store_q(p, v, tile.x + cl, __ldg(p.m.e_R + tile.x + cl), s);
     }
 }
 
-__device__ __forceinline__ void e_phase(const EmParams &p, int gwarp, int nwarps, int lane)
+__device__ __forceinline__ void e_phase(const EmParams &p, const BlockView &v, int n_tiles, int *stg, int warp, int lane)
 {
-    for (int g = gwarp; g < p.m.n_etiles; g += nwarps) {
-        const int4 tile = __ldg(p.m.e_tiles + g);
+    int g = warp, buf = 0;
+    int4 tile = make_int4(0, 0, 0, 0);
+    int shift = 0; bool staged = false;
+    if (g < n_tiles) {
+        tile = v.sm_etiles[g];
+        const int n = etile_ints(tile);
+        staged = n <= STG_INTS - 4;
+        if (staged) shift = stage_issue(stg, p.m.e_tid + (uint32_t)tile.z, n, lane);
+    }
+    stage_commit();
+    for (; g < n_tiles; g += EM_WARPS) {
+        // prefetch the next tile's members into the other buffer
+        const int gn = g + EM_WARPS;
+        int4 tile_n = make_int4(0, 0, 0, 0);
+        int shift_n = 0; bool staged_n = false;
+        if (gn < n_tiles) {
+            tile_n = v.sm_etiles[gn];
+            const int n = etile_ints(tile_n);
+            staged_n = n <= STG_INTS - 4;
+            if (staged_n) shift_n = stage_issue(stg + (buf ^ 1) * STG_INTS, p.m.e_tid + (uint32_t)tile_n.z, n, lane);
+        }
+        stage_commit();
         const int k = tile.w & 0xffff, mode = tile.w >> 16;
+        uint32_t rf = 0;
+        if (mode == 0 && lane < tile.y) rf = __ldg(p.m.e_R + tile.x + lane);      // in flight while the staging lands
+        stage_wait<1>();
+        __syncwarp();
+        Idx ix;
+        ix.sm = stg + buf * STG_INTS + shift; ix.g = p.m.e_tid + (uint32_t)tile.z; ix.staged = staged;
         if (mode == 0) {
-            const int32_t *tids = p.m.e_tid + (uint32_t)tile.z;
             double s;
             switch (k) {
-            case 2: s = esum_tp<2>(tids, p.m.theta, lane); break;
-            case 3: s = esum_tp<3>(tids, p.m.theta, lane); break;
-            case 4: s = esum_tp<4>(tids, p.m.theta, lane); break;
-            case 5: s = esum_tp<5>(tids, p.m.theta, lane); break;
-            case 6: s = esum_tp<6>(tids, p.m.theta, lane); break;
-            case 7: s = esum_tp<7>(tids, p.m.theta, lane); break;
-            default: s = esum_tp<8>(tids, p.m.theta, lane); break;
+            case 2: s = esum_tp<2>(p, v, ix, lane); break;
+            case 3: s = esum_tp<3>(p, v, ix, lane); break;
+            case 4: s = esum_tp<4>(p, v, ix, lane); break;
+            case 5: s = esum_tp<5>(p, v, ix, lane); break;
+            case 6: s = esum_tp<6>(p, v, ix, lane); break;
+            case 7: s = esum_tp<7>(p, v, ix, lane); break;
+            default: s = esum_tp<8>(p, v, ix, lane); break;
             }
-            if (lane < tile.y) {
-                const int j = tile.x + lane;
-                const double r = (double)__ldg(p.m.e_R + j);
-                p.m.q[j] = s > 0 ? r / s : 0.0;
-            }
-        } else if (mode == 1) etile_group<8>(p, tile, k, lane);
-        else etile_group<32>(p, tile, k, lane);
+            if (lane < tile.y) store_q(p, v, tile.x + lane, rf, s);
+        } else if (mode == 1) etile_group<8>(p, v, tile, k, ix, lane);
+        else etile_group<32>(p, v, tile, k, ix, lane);
+        __syncwarp();
+        tile = tile_n; shift = shift_n; staged = staged_n; buf ^= 1;
     }
+    stage_wait<0>();
 }
 
-// ---- M-phase ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double m_update(const EmParams &p, int row, double Q)
-{
-    const double2 ra = p.m.row_RsA[row];
-    const double th = p.m.theta[row];
-    const double n = ra.x + th * Q;
-    const double thn = n / ra.y;
-    p.m.theta[row] = thn;
-    return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
-}
-
-__device__ __forceinline__ double m_phase(const EmParams &p, double *sm_block, int gwarp, int nwarps, int lane)
+// ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
+__device__ __forceinline__ double m_phase(const EmParams &p, const BlockView &v, int n_tiles, int *stg, int warp, int lane)
 {
     double dmax = 0;
-    const double *q = p.m.q;
-    const uint32_t *row_off = p.m.row_off;
-    // (1) hub rows: one CTA per row
-    const int hub0 = p.m.n_short + p.m.n_long;
-    for (int h = blockIdx.x; h < p.m.n_hub; h += gridDim.x) {
-        const int row = hub0 + h;
-        const uint32_t e0 = row_off[row], e1 = row_off[row + 1];
-        double s = 0;
-        for (uint32_t e = e0 + threadIdx.x; e < e1; e += EM_BLOCK) s += q[__ldg(p.m.m_cls + e)];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) sm_block[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double Q = 0;
-            for (int w = 0; w < EM_WARPS; w++) Q += sm_block[w];
-            dmax = fmax(dmax, m_update(p, row, Q));
+    const int sub = lane >> 3, l = lane & 7;
+    int g = warp, buf = 0;
+    int2 tile = make_int2(0, 0);
+    int shift = 0; bool staged = false; uint32_t e0 = 0;
+    if (g < n_tiles) {
+        tile = v.sm_mtiles[g];
+        e0 = v.sm_rowoff[tile.x - v.row0];
+        const int n = (int)(v.sm_rowoff[tile.y - v.row0] - e0);
+        staged = n <= STG_INTS - 4;
+        if (staged && n > 0) shift = stage_issue(stg, p.m.m_cls + e0, n, lane);
+    }
+    stage_commit();
+    for (; g < n_tiles; g += EM_WARPS) {
+        const int gn = g + EM_WARPS;
+        int2 tile_n = make_int2(0, 0);
+        int shift_n = 0; bool staged_n = false; uint32_t e0_n = 0;
+        if (gn < n_tiles) {
+            tile_n = v.sm_mtiles[gn];
+            e0_n = v.sm_rowoff[tile_n.x - v.row0];
+            const int n = (int)(v.sm_rowoff[tile_n.y - v.row0] - e0_n);
+            staged_n = n <= STG_INTS - 4;
+            if (staged_n && n > 0) shift_n = stage_issue(stg + (buf ^ 1) * STG_INTS, p.m.m_cls + e0_n, n, lane);
         }
-        __syncthreads();
-    }
-    // (2) long rows: one warp per row
-    for (int r = gwarp; r < p.m.n_long; r += nwarps) {
-        const int row = p.m.n_short + r;
-        const uint32_t e0 = row_off[row], e1 = row_off[row + 1];
-        double s = 0;
-#pragma unroll 4
-        for (uint32_t e = e0 + lane; e < e1; e += 32) s += q[__ldg(p.m.m_cls + e)];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) dmax = fmax(dmax, m_update(p, row, s));
-    }
-    // (3) short rows: a warp takes one tile of <= 32 consecutive rows; 8 lanes reduce one row at a time (4 rows per
-    //     pass, fixed shuffle tree), then all 32 lanes update their row together (coalesced Rs/A/theta traffic)
-    for (int g = nwarps - 1 - gwarp; g < p.m.n_mtiles; g += nwarps) {
-        const int2 tile = __ldg(p.m.m_tiles + g);
+        stage_commit();
         const int nrows = tile.y - tile.x;
-        if (nrows <= 0) continue;
-        const int sub = lane >> 3, l = lane & 7;
+        // each lane owns one row of the tile; its {Rs, A} load overlaps the staging
+        uint32_t a_mine = 0, b_mine = 0;
+        double2 ra = make_double2(0.0, 1.0);
+        if (lane < nrows) {
+            a_mine = v.sm_rowoff[tile.x - v.row0 + lane] - e0;
+            b_mine = v.sm_rowoff[tile.x - v.row0 + lane + 1] - e0;
+            ra = p.m.row_RsA[tile.x + lane];
+        }
+        const bool is_long = (b_mine - a_mine) > (uint32_t)M_SHORT_MAX;
+        stage_wait<1>();
+        __syncwarp();
+        Idx ix;
+        ix.sm = stg + buf * STG_INTS + shift; ix.g = p.m.m_cls + e0; ix.staged = staged;
         double Qmine = 0;
+        // short rows: 8 lanes per row, 4 rows per pass, fixed shuffle tree
         for (int pass = 0; pass * 4 < nrows; pass++) {
             const int r = pass * 4 + sub;
+            const uint32_t a = __shfl_sync(0xffffffffu, a_mine, r & 31), b = __shfl_sync(0xffffffffu, b_mine, r & 31);
+            const bool lng = __shfl_sync(0xffffffffu, (int)is_long, r & 31) != 0;
             double s = 0;
-            if (r < nrows) {
-                const uint32_t a = row_off[tile.x + r], b = row_off[tile.x + r + 1];
+            if (r < nrows && !lng) {
 #pragma unroll 4
-                for (uint32_t e = a + l; e < b; e += 8) s += q[__ldg(p.m.m_cls + e)];
+                for (uint32_t e = a + l; e < b; e += 8) s += load_q(p, v, ix[(int)e]);
             }
             s += __shfl_xor_sync(0xffffffffu, s, 4);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -180,33 +249,75 @@ __device__ __forceinline__ double m_phase(const EmParams &p, double *sm_block, i
             const double got = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);
             if ((lane >> 2) == pass) Qmine = got;
         }
-        if (lane < nrows) dmax = fmax(dmax, m_update(p, tile.x + lane, Qmine));
+        // long rows of the tile: the whole warp reduces one row at a time
+        unsigned longm = __ballot_sync(0xffffffffu, is_long);
+        while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const uint32_t a = __shfl_sync(0xffffffffu, a_mine, src), b = __shfl_sync(0xffffffffu, b_mine, src);
+            double s = 0;
+#pragma unroll 4
+            for (uint32_t e = a + lane; e < b; e += 32) s += load_q(p, v, ix[(int)e]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == src) Qmine = s;
+        }
+        if (lane < nrows) {
+            const int row = tile.x + lane;
+            const double th = v.sm_theta[row - v.row0];
+            const double n = ra.x + th * Qmine;
+            const double thn = n / ra.y;
+            v.sm_theta[row - v.row0] = thn;
+            p.m.theta[row] = thn;                       // write-through: halo readers and the final result
+            dmax = fmax(dmax, fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n));
+        }
+        __syncwarp();
+        tile = tile_n; shift = shift_n; staged = staged_n; e0 = e0_n; buf ^= 1;
     }
+    stage_wait<0>();
     return dmax;
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
 {
-    __shared__ double sm_block[EM_WARPS];
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    __shared__ double sm_red[EM_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = gridDim.x * EM_WARPS;
-    const int gwarp = blockIdx.x * EM_WARPS + warp;
+    const int b = blockIdx.x;
+    const int et0 = p.m.blk_etile0[b], n_et = p.m.blk_etile0[b + 1] - et0;
+    const int mt0 = p.m.blk_mtile0[b], n_mt = p.m.blk_mtile0[b + 1] - mt0;
+    BlockView v;
+    v.row0 = p.m.blk_row0[b]; v.nrows = p.m.blk_row0[b + 1] - v.row0;
+    v.cls0 = p.m.blk_cls0[b]; v.nres = p.m.blk_nres[b];
+    const SmemPlan pl = em_smem_plan(n_et, n_mt, v.nrows);
+    int *stg = (int *)sm_dyn + warp * (2 * STG_INTS);
+    int4 *s_et = (int4 *)(sm_dyn + pl.off_etiles);
+    int2 *s_mt = (int2 *)(sm_dyn + pl.off_mtiles);
+    uint32_t *s_ro = (uint32_t *)(sm_dyn + pl.off_rowoff);
+    v.sm_theta = (double *)(sm_dyn + pl.off_theta);
+    v.sm_q = (double *)(sm_dyn + pl.off_q);
+    v.sm_etiles = s_et; v.sm_mtiles = s_mt; v.sm_rowoff = s_ro;
+    // per-CTA constants and the CTA's slice of theta -> shared memory, once
+    for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_et[i] = p.m.e_tiles[et0 + i];
+    for (int i = threadIdx.x; i < n_mt; i += EM_BLOCK) s_mt[i] = p.m.m_tiles[mt0 + i];
+    for (int i = threadIdx.x; i <= v.nrows; i += EM_BLOCK) s_ro[i] = p.m.row_off[v.row0 + i];
+    for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = p.m.theta[v.row0 + i];
+    __syncthreads();
     int it = 0;
     double d = INFINITY;
     while (it < p.max_iter) {
-        e_phase(p, gwarp, nwarps, lane);
+        e_phase(p, v, n_et, stg, warp, lane);
         grid_barrier(p.bar, gridDim.x);
-        double dm = m_phase(p, sm_block, gwarp, nwarps, lane);
+        double dm = m_phase(p, v, n_mt, stg, warp, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-        __syncthreads();
-        if (lane == 0) sm_block[warp] = dm;
+        if (lane == 0) sm_red[warp] = dm;
         __syncthreads();
         if (threadIdx.x == 0) {
-            double b = 0;
-            for (int w = 0; w < EM_WARPS; w++) b = fmax(b, sm_block[w]);
-            atomicMax(p.dmax + (it & 1), (unsigned long long)__double_as_longlong(b));
+            double bm = 0;
+            for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
+            atomicMax(p.dmax + (it & 1), (unsigned long long)__double_as_longlong(bm));
         }
         grid_barrier(p.bar, gridDim.x);
         d = __longlong_as_double((long long)*((volatile unsigned long long *)(p.dmax + (it & 1))));
@@ -219,17 +330,18 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
 
 int em_query_occupancy(emsar_ctx *ctx)
 {
+    // one CTA per SM owns a row range; all the shared memory an SM can give goes to the theta | q slices
+    ctx->em_minb = 1;
+    int smem = (int)ctx->prop.sharedMemPerBlockOptin - 2048;      // static (sm_red) + reserve
+    const char *e = getenv("EMSAR_EM_SMEM_KB");
+    if (e && atoi(e) > 0 && atoi(e) * 1024 < smem) smem = atoi(e) * 1024;
+    smem &= ~255;
+    CU(cudaFuncSetAttribute(k_em_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int nb = 0;
-    // register budget variant: 2, 3 or 4 resident CTAs per SM (EMSAR_EM_MINB overrides the default for tuning)
-    int minb = EM_MIN_BLOCKS;
-    const char *e = getenv("EMSAR_EM_MINB");
-    if (e && atoi(e) >= 2 && atoi(e) <= 4) minb = atoi(e);
-    ctx->em_minb = minb;
-    if (minb == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<2>, EM_BLOCK, 0));
-    else if (minb == 3) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<3>, EM_BLOCK, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<4>, EM_BLOCK, 0));
-    if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM"); return EMSAR_ERR_CUDA; }
-    ctx->em_blocks_per_sm = nb;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<1>, EM_BLOCK, smem));
+    if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM (%d bytes of shared memory)", smem); return EMSAR_ERR_CUDA; }
+    ctx->em_blocks_per_sm = 1;
+    ctx->em_smem_bytes = smem;
     return EMSAR_OK;
 }
 
@@ -246,12 +358,12 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     p.iters_done = (int *)(ctx->d_barrier + 8);
     p.final_delta = (double *)(ctx->d_barrier + 10);
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 64, st));
-    const int grid = ctx->prop.multiProcessorCount * ctx->em_blocks_per_sm;
+    const int grid = s->m.B;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(EM_BLOCK);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)ctx->em_smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
     int na = 0;
@@ -259,7 +371,7 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     attrs[na].val.cooperative = 1;
     na++;
     if (ctx->l2_persist_bytes > 0 && s->state_bytes > 0) {
-        // keep theta | q resident in L2 while the index streams through (access-policy window)
+        // the global copies of theta | q (halo traffic) stay resident in L2 while the index streams through
         size_t win = s->state_bytes;
         if (win > (size_t)ctx->prop.accessPolicyMaxWindowSize) win = (size_t)ctx->prop.accessPolicyMaxWindowSize;
         attrs[na].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -273,9 +385,7 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
-    if (ctx->em_minb == 2) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<2>, p));
-    else if (ctx->em_minb == 3) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<3>, p));
-    else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<4>, p));
+    CU(cudaLaunchKernelEx(&cfg, k_em_persistent<1>, p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     int it = 0; double fd = 0;
@@ -302,7 +412,7 @@ extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t st
     CHECK_ARG(s, "emsar_sample_em_run: NULL sample");
     if (!s->prepared) { emsar_set_err("emsar_sample_em_run: call emsar_sample_prepare first"); return EMSAR_ERR_STATE; }
     CU(cudaSetDevice(s->ctx->device));
-    const int P = s->m.n_short + s->m.n_long + s->m.n_hub;
+    const int P = s->m.P;
     if (reset_theta) {
         if (P > 0) { k_fill_double2<<<(unsigned)((P + 255) / 256), 256, 0, s->ctx->stream>>>(s->m.theta, P, 1.0); LAUNCHED(s->ctx); }
         s->n_iter = 0;

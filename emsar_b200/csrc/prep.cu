@@ -71,12 +71,12 @@ __global__ void k_class_model(int64_t C, int32_t T, const double *__restrict__ a
 }
 
 // One warp per transcript over its row of the static multi-class transpose: iEUMA (all classes, ascending cid,
-// multiplicity, sequential order), A_t (modelled classes), Rs_t, active degree, lone-singleton flag, row class.
+// multiplicity, sequential order), A_t (modelled classes), Rs_t, active degree, lone-singleton flag, participation flag.
 __global__ void k_row_stats(int32_t T, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
                             const double *__restrict__ adj, const double *__restrict__ amodel, const int32_t *__restrict__ act,
                             const uint8_t *__restrict__ in_model, const int32_t *__restrict__ R,
                             double *__restrict__ iE, double *__restrict__ A, double *__restrict__ Rs, int32_t *__restrict__ deg,
-                            uint8_t *__restrict__ lone, unsigned long long *__restrict__ rkey)
+                            uint8_t *__restrict__ lone, uint32_t *__restrict__ rflag)
 {
     const int lane = threadIdx.x & 31;
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -105,80 +105,55 @@ __global__ void k_row_stats(int32_t T, const uint32_t *__restrict__ txm_off, con
         Rs[t] = amodel[t] > 0 ? (double)R[t] : 0.0;
         deg[t] = d;
         lone[t] = any_model ? 0 : 1;
-        int rc = !(acc_a > 0) ? 3 : (d <= M_SHORT_MAX ? 0 : (d < M_HUB_MIN ? 1 : 2));
-        rkey[t] = rc < 3 ? (1ULL << (21 * rc)) : 0ULL;
-        if (t == T - 1) rkey[T] = 0ULL;
+        rflag[t] = acc_a > 0 ? 1u : 0u;
+        if (t == T - 1) rflag[T] = 0u;
     }
 }
 
-__global__ void k_row_perm(int32_t T, const unsigned long long *__restrict__ rpre, const unsigned long long *__restrict__ rkey,
-                           const int32_t *__restrict__ deg, const double *__restrict__ Rs, const double *__restrict__ A,
-                           int32_t *__restrict__ pos, int32_t *__restrict__ row_t, uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA)
+// rows in natural order: pos[t] = rank among the participating transcripts (in place over the scan output), -1 otherwise
+__global__ void k_row_fill(int32_t T, const uint32_t *__restrict__ rflag, int32_t *__restrict__ pos, const int32_t *__restrict__ deg,
+                           const double *__restrict__ Rs, const double *__restrict__ A, uint32_t *__restrict__ degp,
+                           double2 *__restrict__ row_RsA, int32_t *__restrict__ ecost, int32_t P)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { degp[P] = 0; ecost[P] = 0; }
     if (t >= T) return;
-    const unsigned long long tot = rpre[T];
-    const int n0 = (int)(tot & 0x1FFFFF), n1 = (int)((tot >> 21) & 0x1FFFFF), n2 = (int)((tot >> 42) & 0x1FFFFF);
-    unsigned long long key = rkey[t], pre = rpre[t];
-    int p = -1;
-    if (key == 1ULL) p = (int)(pre & 0x1FFFFF);
-    else if (key == (1ULL << 21)) p = n0 + (int)((pre >> 21) & 0x1FFFFF);
-    else if (key == (1ULL << 42)) p = n0 + n1 + (int)((pre >> 42) & 0x1FFFFF);
-    pos[t] = p;
-    if (p >= 0) { row_t[p] = t; degp[p] = (uint32_t)deg[t]; row_RsA[p] = make_double2(Rs[t], A[t]); }
-    if (t == 0) degp[n0 + n1 + n2] = 0;
+    if (rflag[t]) {
+        const int p = pos[t];
+        degp[p] = (uint32_t)deg[t];
+        row_RsA[p] = make_double2(Rs[t], A[t]);
+        ecost[p] = 0;
+    } else pos[t] = -1;
 }
 
-// One warp per transcript: copy the ACTIVE entries of its transposed row, in order, as compact class ids.
-__global__ void k_scatter_rows(int32_t T, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
-                               const int32_t *__restrict__ act, const int32_t *__restrict__ newid, const int32_t *__restrict__ pos,
-                               const uint32_t *__restrict__ row_off, int32_t *__restrict__ m_cls)
+// E-phase cost lands on the row that owns the class (its first member)
+__global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
+                             const int32_t *__restrict__ act, const int32_t *__restrict__ pos, int32_t *__restrict__ ecost)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= T) return;
-    const int p = pos[t];
-    if (p < 0) return;
-    uint32_t out = row_off[p];
-    const uint32_t e0 = txm_off[t], e1 = txm_off[t + 1];
-    for (uint32_t e = e0; e < e1; e += 32) {
-        int a = 0, id = 0;
-        if (e + lane < e1) { int i = txm_cid[e + lane] - T; a = act[i]; id = newid[i]; }
-        unsigned m = __ballot_sync(0xffffffffu, a != 0);
-        if (a) m_cls[out + __popc(m & ((1u << lane) - 1))] = id;
-        out += __popc(m);
-    }
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi || !act[i]) return;
+    const uint32_t o = cls_off[T + i];
+    atomicAdd(&ecost[pos[cls_tid[o]]], (int)(cls_off[T + i + 1] - o));
 }
 
-// Cardinality segments of the active classes: counts, tid-layout offsets and tile ranges. <= ~1000 segments.
-struct SegTab {          // device arrays of n_kseg (+1) entries
-    int32_t *j0;         // first compact id
-    int32_t *cnt;
-    uint32_t *tid_off;   // offset (ints) of the segment's tid block
-    int32_t *tile0;      // [n_kseg+1] first tile
-    int32_t *cpt;        // classes per tile
-    long long *totals;   // [0] n_etiles, [1] e_tid ints, [2] C_a
-};
-__global__ void k_seg_tables(int n_kseg, int32_t T, const int64_t *__restrict__ kseg_cid0, const int32_t *__restrict__ kseg_k,
-                             const int32_t *__restrict__ newid, SegTab st)
+__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degp, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    long long tiles = 0, ints = 0;
-    for (int s = 0; s < n_kseg; s++) {
-        int j0 = newid[kseg_cid0[s] - T], j1 = newid[kseg_cid0[s + 1] - T];
-        int cnt = j1 - j0, k = kseg_k[s];
-        int cpt;
-        long long sz;
-        if (k <= KT) { cpt = 32; sz = (long long)((cnt + 31) / 32) * 32 * k; }
-        else if (k <= KSUB) { cpt = max(4, (E_TILE_TARGET / k) & ~3); cpt = min(cpt, 32); sz = (long long)cnt * k; }
-        else { cpt = max(1, E_TILE_TARGET / k); sz = (long long)cnt * k; }
-        st.j0[s] = j0; st.cnt[s] = cnt; st.tid_off[s] = (uint32_t)ints; st.tile0[s] = (int32_t)tiles; st.cpt[s] = cpt;
-        tiles += (cnt + cpt - 1) / cpt;
-        ints += sz;
-    }
-    st.tile0[n_kseg] = (int32_t)tiles;
-    st.totals[0] = tiles; st.totals[1] = ints;
-    st.totals[2] = n_kseg ? newid[kseg_cid0[n_kseg] - T] : 0;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    cost[p] = p < P ? degp[p] + (uint32_t)ecost[p] + 2u : 0u;
+}
+
+// cut the rows into B ranges of equal cost
+__global__ void k_block_bounds(int B, int32_t P, const uint32_t *__restrict__ costp, int32_t *__restrict__ row0)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    if (b == 0) { row0[0] = 0; return; }
+    if (b == B) { row0[B] = P; return; }
+    const unsigned long long target = (unsigned long long)costp[P] * (unsigned long long)b / (unsigned long long)B;
+    int lo = 0, hi = P;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((unsigned long long)costp[mid] >= target) hi = mid; else lo = mid + 1; }
+    row0[b] = lo;
 }
 
 __device__ __forceinline__ int seg_of_cid(const int64_t *kseg_cid0, int n_kseg, int64_t cid)
@@ -187,73 +162,191 @@ __device__ __forceinline__ int seg_of_cid(const int64_t *kseg_cid0, int n_kseg, 
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (kseg_cid0[mid] <= cid) lo = mid; else hi = mid - 1; }
     return lo;
 }
+__device__ __forceinline__ int block_of_row(const int32_t *row0, int B, int p)
+{
+    int lo = 0, hi = B - 1;       // largest b with row0[b] <= p (that CTA is non-empty because p < row0[b+1])
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (row0[mid] <= p) lo = mid; else hi = mid - 1; }
+    return lo;
+}
 
-// One warp per multi-tid class: write the member list of an active class into the packed E layout
-// (as PERMUTED ROW indices, so that theta is stored in row order) and its read count.
-__global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int64_t *__restrict__ kseg_cid0,
-                               const int32_t *__restrict__ kseg_k, const uint32_t *__restrict__ cls_off,
-                               const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
-                               const int32_t *__restrict__ newid, const int32_t *__restrict__ R, const int32_t *__restrict__ pos,
-                               SegTab st, int32_t *__restrict__ e_tid, int32_t *__restrict__ e_R)
+// cell = (owner CTA, cardinality segment). Classes of one cell are contiguous in cid order (first tids ascend inside a
+// cardinality segment), so a class's rank inside its cell is (old compact id - smallest old compact id of the cell).
+__global__ void k_class_cells(int64_t n_multi, int32_t T, int n_kseg, int B, const int64_t *__restrict__ kseg_cid0,
+                              const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
+                              const int32_t *__restrict__ newid, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
+                              int32_t *__restrict__ cellof, int32_t *__restrict__ cell_cnt, int32_t *__restrict__ cell_first)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi || !act[i]) return;
+    const int ob = block_of_row(row0, B, pos[cls_tid[cls_off[T + i]]]);
+    const int cell = ob * n_kseg + seg_of_cid(kseg_cid0, n_kseg, T + i);
+    const int j = newid[i];
+    cellof[j] = cell;
+    atomicAdd(&cell_cnt[cell], 1);
+    atomicMin(&cell_first[cell], j);
+}
+
+__device__ __forceinline__ int cls_per_tile(int k)
+{
+    if (k <= KT) return 32;
+    if (k <= KSUB) return min(32, max(4, (E_TILE_TARGET / k) & ~3));
+    return max(1, E_TILE_TARGET / k);
+}
+
+__global__ void k_cell_sizes(int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ cell_cnt,
+                             uint32_t *__restrict__ cell_ints, int32_t *__restrict__ cell_tiles)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    if (c == n_cells) { cell_ints[c] = 0; cell_tiles[c] = 0; return; }
+    const int k = kseg_k[c % n_kseg], cnt = cell_cnt[c], cpt = cls_per_tile(k);
+    cell_ints[c] = k <= KT ? (uint32_t)((cnt + 31) / 32) * 32u * (uint32_t)k : (uint32_t)cnt * (uint32_t)k;
+    cell_tiles[c] = (cnt + cpt - 1) / cpt;
+}
+
+__global__ void k_block_tables(int B, int n_kseg, const int32_t *__restrict__ clsbase, const int32_t *__restrict__ tilebase,
+                               int32_t *__restrict__ cls0, int32_t *__restrict__ etile0)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    cls0[b] = clsbase[b * n_kseg];
+    etile0[b] = tilebase[b * n_kseg];
+}
+
+__global__ void k_block_nres(int B, int smem_bytes, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
+                             const int32_t *__restrict__ etile0, const int32_t *__restrict__ mtile0, int32_t *__restrict__ nres)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int left = smem_bytes - em_fixed_smem(etile0[b + 1] - etile0[b], mtile0[b + 1] - mtile0[b], row0[b + 1] - row0[b]);
+    nres[b] = max(0, min(cls0[b + 1] - cls0[b], left / 8));
+}
+
+// One warp per multi-tid class: members of an active class as encoded rows (>= 0: slot in the owner's shared theta,
+// < 0: ~global row), its read count, and the flag that q must also go to global memory.
+__global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int32_t *__restrict__ blk_nres, const int32_t *__restrict__ kseg_k,
+                               const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
+                               const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof, const int32_t *__restrict__ cell_first,
+                               const int32_t *__restrict__ clsbase, const uint32_t *__restrict__ intbase, const int32_t *__restrict__ R,
+                               const int32_t *__restrict__ pos, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
+                               int32_t *__restrict__ newid2, int32_t *__restrict__ e_tid, uint32_t *__restrict__ e_R)
 {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_multi || !act[i]) return;
-    const int64_t cid = T + i;
-    const int j = newid[i];
-    const int s = seg_of_cid(kseg_cid0, n_kseg, cid);
-    const int k = kseg_k[s];
-    const int jl = j - st.j0[s];
-    const uint32_t o = cls_off[cid];
-    const uint32_t base = st.tid_off[s];
+    const int jo = newid[i];
+    const int cell = cellof[jo];
+    const int ob = cell / n_kseg, k = kseg_k[cell % n_kseg];
+    const int jl = jo - cell_first[cell];
+    const int jn = clsbase[cell] + jl;
+    const int r0 = row0[ob], r1 = row0[ob + 1];
+    const int nres = blk_nres[ob];
+    const uint32_t o = cls_off[T + i];
+    const uint32_t base = intbase[cell];
+    bool remote = false;
     for (int jj = lane; jj < k; jj += 32) {
-        int p = pos[cls_tid[o + jj]];
-        uint32_t dst = (k <= KT) ? base + (uint32_t)(jl >> 5) * 32u * k + (uint32_t)jj * 32u + (uint32_t)(jl & 31)
-                                 : base + (uint32_t)jl * k + jj;
-        e_tid[dst] = p;
+        const int p = pos[cls_tid[o + jj]];
+        const bool local = p >= r0 && p < r1;
+        remote = remote || !local;
+        const uint32_t dst = (k <= KT) ? base + (uint32_t)(jl >> 5) * 32u * (uint32_t)k + (uint32_t)jj * 32u + (uint32_t)(jl & 31)
+                                       : base + (uint32_t)jl * (uint32_t)k + (uint32_t)jj;
+        e_tid[dst] = local ? p - r0 : ~p;
     }
-    if (lane == 0) e_R[j] = R[cid];
+    remote = __any_sync(0xffffffffu, remote);
+    if (lane == 0) {
+        newid2[i] = jn;
+        const bool resident = (jn - cls0[ob]) < nres;
+        e_R[jn] = (uint32_t)R[T + i] | ((remote || !resident) ? 0x80000000u : 0u);
+    }
 }
 
-__global__ void k_etiles(int n_tiles, int n_kseg, const int32_t *__restrict__ kseg_k, SegTab st, int4 *__restrict__ tiles)
+// One warp per transcript: the ACTIVE entries of its transposed row, in ascending cid order, as encoded classes
+// (>= 0: slot in the row owner's shared q, < 0: ~global compact id).
+__global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk_nres, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
+                               const int32_t *__restrict__ act, const int32_t *__restrict__ newid2, const int32_t *__restrict__ pos,
+                               const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0, const uint32_t *__restrict__ row_off,
+                               int32_t *__restrict__ m_cls)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    const int p = pos[t];
+    if (p < 0) return;
+    const int b = block_of_row(row0, B, p);
+    const int c0 = cls0[b];
+    const int nres = blk_nres[b];
+    uint32_t out = row_off[p];
+    const uint32_t e0 = txm_off[t], e1 = txm_off[t + 1];
+    for (uint32_t e = e0; e < e1; e += 32) {
+        int a = 0, id = 0;
+        if (e + lane < e1) { int i = txm_cid[e + lane] - T; a = act[i]; if (a) id = newid2[i]; }
+        unsigned m = __ballot_sync(0xffffffffu, a != 0);
+        if (a) {
+            const int loc = id - c0;
+            m_cls[out + __popc(m & ((1u << lane) - 1))] = (loc >= 0 && loc < nres) ? loc : ~id;
+        }
+        out += __popc(m);
+    }
+}
+
+__global__ void k_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ tilebase,
+                         const int32_t *__restrict__ clsbase, const int32_t *__restrict__ cell_cnt, const uint32_t *__restrict__ intbase,
+                         int4 *__restrict__ tiles)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_tiles) return;
-    int lo = 0, hi = n_kseg - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (st.tile0[mid] <= g) lo = mid; else hi = mid - 1; }
-    // skip empty segments that share the same tile0
-    while (lo + 1 < n_kseg && st.tile0[lo + 1] <= g) lo++;
-    const int s = lo, k = kseg_k[s], cpt = st.cpt[s], lt = g - st.tile0[s];
+    int lo = 0, hi = n_cells - 1;      // largest cell with tilebase[cell] <= g (non-empty by construction)
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tilebase[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int c = lo, k = kseg_k[c % n_kseg], cpt = cls_per_tile(k), lt = g - tilebase[c];
     const int mode = k <= KT ? 0 : (k <= KSUB ? 1 : 2);
     int4 t;
-    t.x = st.j0[s] + lt * cpt;
-    t.y = min(cpt, st.cnt[s] - lt * cpt);
-    t.z = (int)(st.tid_off[s] + (uint32_t)lt * (uint32_t)cpt * (uint32_t)k);  // mode 0: cpt == 32 -> lt*32*k
+    t.x = clsbase[c] + lt * cpt;
+    t.y = min(cpt, cell_cnt[c] - lt * cpt);
+    t.z = (int)(intbase[c] + (uint32_t)lt * (uint32_t)cpt * (uint32_t)k);
     t.w = k | (mode << 16);
     tiles[g] = t;
 }
 
-// Short-row tiles: windows of M_WINDOW over cost(p) = row_off[p] + M_ROW_COST * p.
-__global__ void k_mtiles(int n_tiles, int n_short, const uint32_t *__restrict__ row_off, int2 *__restrict__ tiles)
+// Row tiles: windows of M_WINDOW over cost(p) = row_off[p] + M_ROW_COST * p, restarted at every CTA boundary.
+__device__ __forceinline__ unsigned long long mcost(const uint32_t *row_off, int p) { return (unsigned long long)row_off[p] + (unsigned long long)M_ROW_COST * (unsigned long long)p; }
+__global__ void k_mtile_counts(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ row_off, int32_t *__restrict__ mtile0)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int acc = 0;
+    for (int b = 0; b < B; b++) {
+        mtile0[b] = acc;
+        const unsigned long long c = mcost(row_off, row0[b + 1]) - mcost(row_off, row0[b]);
+        acc += (int)((c + M_WINDOW - 1) / M_WINDOW);
+    }
+    mtile0[B] = acc;
+}
+__global__ void k_mtiles(int n_tiles, int B, const int32_t *__restrict__ row0, const int32_t *__restrict__ mtile0,
+                         const uint32_t *__restrict__ row_off, int2 *__restrict__ tiles)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_tiles) return;
+    int lo = 0, hi = B - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (mtile0[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int b = lo, r0 = row0[b], r1 = row0[b + 1];
+    const unsigned long long base = mcost(row_off, r0) + (unsigned long long)(g - mtile0[b]) * M_WINDOW;
     int2 out;
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-        unsigned long long target = (unsigned long long)(g + side) * M_WINDOW;
-        int lo = 0, hi = n_short;   // first p in [0, n_short] with cost(p) >= target
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            unsigned long long c = (unsigned long long)row_off[mid] + (unsigned long long)M_ROW_COST * mid;
-            if (c >= target) hi = mid; else lo = mid + 1;
-        }
-        if (side == 0) out.x = lo; else out.y = lo;
+        const unsigned long long target = base + (unsigned long long)side * M_WINDOW;
+        int l = r0, h = r1;             // first p in [r0, r1] with cost(p) >= target
+        while (l < h) { int mid = (l + h) >> 1; if (mcost(row_off, mid) >= target) h = mid; else l = mid + 1; }
+        if (side == 0) out.x = l; else out.y = l;
     }
     tiles[g] = out;
 }
 
 __global__ void k_fill_double(double *p, int64_t n, double v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_fill_int(int32_t *p, int64_t n, int32_t v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -376,31 +469,39 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     } else {
         s->max_sid = ix->n_sets_nocut - 1;
     }
-    // ---- scratch carve-up (ints / flags / scans) ----
+    // ---- scratch carve-up ----
+    const int B = ctx->prop.multiProcessorCount * ctx->em_blocks_per_sm;
+    const int cap = ctx->em_smem_bytes / 8;
+    const int n_cells = B * (n_kseg > 0 ? n_kseg : 1);
     size_t cub_bytes = 0, b1 = 0, b2 = 0, b3 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, b1, (int32_t *)nullptr, (int32_t *)nullptr, (int)(nm + 1));
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, (unsigned long long *)nullptr, (unsigned long long *)nullptr, T + 1);
-    cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t *)nullptr, (uint32_t *)nullptr, T + 1);
+    const int scan_max = (int)std::max<int64_t>(std::max<int64_t>(nm + 1, (int64_t)T + 1), (int64_t)n_cells + 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, (int32_t *)nullptr, (int32_t *)nullptr, scan_max);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, scan_max);
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t *)nullptr, (int32_t *)nullptr, scan_max);
     cub_bytes = std::max(b1, std::max(b2, b3));
-    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 8 + (size_t)(T + 1) * (8 + 8 + 4 + 4 + 4) + (size_t)(n_kseg + 2) * 24 + 4096 + 256 * 16;
+    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 28 + (size_t)(n_cells + 1) * 28 + 64 * 256;
     void *scr = nullptr;
     TRY(ctx_scratch(ctx, need, &scr));
     char *cur = (char *)scr;
     void *d_cub = arena_take<char>(cur, cub_bytes);
     int32_t *d_act = arena_take<int32_t>(cur, (size_t)nm + 1);
     int32_t *d_newid = arena_take<int32_t>(cur, (size_t)nm + 1);
-    unsigned long long *d_rkey = arena_take<unsigned long long>(cur, (size_t)T + 1);
-    unsigned long long *d_rpre = arena_take<unsigned long long>(cur, (size_t)T + 1);
+    int32_t *d_newid2 = arena_take<int32_t>(cur, (size_t)nm + 1);
+    int32_t *d_cellof = arena_take<int32_t>(cur, (size_t)nm + 1);
+    uint32_t *d_rflag = arena_take<uint32_t>(cur, (size_t)T + 1);
     int32_t *d_deg = arena_take<int32_t>(cur, (size_t)T + 1);
-    int32_t *d_pos = s->d_pos;   // t -> permuted row (kept for finalize)
     uint32_t *d_degp = arena_take<uint32_t>(cur, (size_t)T + 1);
-    SegTab stab;
-    stab.j0 = arena_take<int32_t>(cur, (size_t)n_kseg + 1);
-    stab.cnt = arena_take<int32_t>(cur, (size_t)n_kseg + 1);
-    stab.tid_off = arena_take<uint32_t>(cur, (size_t)n_kseg + 1);
-    stab.tile0 = arena_take<int32_t>(cur, (size_t)n_kseg + 2);
-    stab.cpt = arena_take<int32_t>(cur, (size_t)n_kseg + 1);
-    stab.totals = arena_take<long long>(cur, 4);
+    int32_t *d_ecost = arena_take<int32_t>(cur, (size_t)T + 1);
+    uint32_t *d_cost = arena_take<uint32_t>(cur, (size_t)T + 1);
+    uint32_t *d_costp = arena_take<uint32_t>(cur, (size_t)T + 1);
+    int32_t *d_cell_cnt = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_cell_first = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    uint32_t *d_cell_ints = arena_take<uint32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_cell_tiles = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_clsbase = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    uint32_t *d_intbase = arena_take<uint32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_tilebase = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_pos = s->d_pos;   // t -> row (kept for finalize)
     // ---- class model + active scan ----
     const double nscale = (double)N / 1E6;
     const double p10 = pow(10, o.delta);
@@ -408,23 +509,18 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_act, d_newid, (int)(nm + 1), st));
     LAUNCHED(ctx);
-    // ---- row statistics, row classes, permutation ----
+    // ---- row statistics and the natural-order row numbering ----
     k_row_stats<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, ix->d_txm_off, ix->d_txm_cid, s->d_adj, s->d_amodel, d_act, d_in_model,
-                                                                          s->d_R, s->d_iE, s->d_A, s->d_Rs, d_deg, s->d_lone, d_rkey);
+                                                                          s->d_R, s->d_iE, s->d_A, s->d_Rs, d_deg, s->d_lone, d_rflag);
     LAUNCHED(ctx);
-    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_rkey, d_rpre, T + 1, st));
-    LAUNCHED(ctx);
-    k_seg_tables<<<1, 32, 0, st>>>(n_kseg, T, ix->d_kseg_cid0, ix->d_kseg_k, d_newid, stab);
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_rflag, (uint32_t *)d_pos, T + 1, st));
     LAUNCHED(ctx);
     CU(cudaGetLastError());
-    unsigned long long rtot = 0;
-    long long tot[3] = {0, 0, 0};
-    CU(cudaMemcpyAsync(&rtot, d_rpre + T, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(tot, stab.totals, 24, cudaMemcpyDeviceToHost, st));
+    int32_t P = 0, C_a32 = 0;
+    CU(cudaMemcpyAsync(&P, d_pos + T, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&C_a32, d_newid + nm, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    const int n_short = (int)(rtot & 0x1FFFFF), n_long = (int)((rtot >> 21) & 0x1FFFFF), n_hub = (int)((rtot >> 42) & 0x1FFFFF);
-    const int P = n_short + n_long + n_hub;
-    const int64_t n_etiles = tot[0], e_ints = tot[1], C_a = tot[2];
+    const int64_t C_a = C_a32;
     // ---- state: theta | q in one allocation ----
     size_t theta_bytes = (((size_t)(P > 0 ? P : 1) * 8 + 255) / 256) * 256;
     size_t q_bytes = (((size_t)(C_a > 0 ? C_a : 1) * 8 + 255) / 256) * 256;
@@ -438,22 +534,19 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     EmModel &m = s->m;
     memset(&m, 0, sizeof(m));
-    m.T = T; m.C_a = C_a;
+    m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.cap = cap;
     m.theta = s->d_state;
     m.q = (double *)((char *)s->d_state + theta_bytes);
-    // ---- packed arena (needs nnz_a: upper bound first, exact after the degree scan) ----
-    // row permutation writes degp; scan gives row_off; nnz_a = row_off[P]
+    // ---- packed arena: upper bounds that do not need another host round trip ----
+    const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)32 * KT * (size_t)KT * (size_t)B + 64;   // tile padding: <= 31*k per (CTA, k<=KT) cell
+    const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
+    const size_t m_tiles_max = ((size_t)ix->nnz_multi + (size_t)M_ROW_COST * (size_t)(P + 1)) / M_WINDOW + (size_t)B + 2;
     size_t arena_bytes = 0;
     {
         auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
-        arena_bytes += rnd((size_t)(e_ints > 0 ? e_ints : 1) * 4);        // e_tid
-        arena_bytes += rnd((size_t)(C_a > 0 ? C_a : 1) * 4);              // e_R
-        arena_bytes += rnd((size_t)(n_etiles > 0 ? n_etiles : 1) * 16);   // e_tiles
-        arena_bytes += rnd((size_t)(e_ints > 0 ? e_ints : 1) * 4);        // m_cls (nnz_a <= e_ints)
-        arena_bytes += rnd((size_t)(P + 1) * 4) * 2;                      // row_off, row_t
-        arena_bytes += rnd((size_t)(P + 1) * 16);                         // row_RsA
-        size_t mt_max = ((size_t)(e_ints > 0 ? e_ints : 0) + (size_t)M_ROW_COST * (size_t)(P + 1)) / M_WINDOW + 2;
-        arena_bytes += rnd(mt_max * 8);                                   // m_tiles
+        arena_bytes += rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16);
+        arena_bytes += rnd(((size_t)ix->nnz_multi + 1) * 4) + rnd((size_t)(P + 1) * 4) + rnd((size_t)(P + 1) * 16) + rnd(m_tiles_max * 8);
+        arena_bytes += 5 * rnd((size_t)(B + 1) * 4);
     }
     if (arena_bytes > s->pack_bytes) {
         if (s->d_pack) CU(cudaFree(s->d_pack));
@@ -464,42 +557,84 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         s->pack_bytes = arena_bytes;
     }
     char *ac = (char *)s->d_pack;
-    m.e_tid = arena_take<int32_t>(ac, (size_t)(e_ints > 0 ? e_ints : 1));
-    m.e_R = arena_take<int32_t>(ac, (size_t)(C_a > 0 ? C_a : 1));
-    m.e_tiles = arena_take<int4>(ac, (size_t)(n_etiles > 0 ? n_etiles : 1));
-    m.m_cls = arena_take<int32_t>(ac, (size_t)(e_ints > 0 ? e_ints : 1));
+    m.e_tid = arena_take<int32_t>(ac, e_ints_max);
+    m.e_R = arena_take<uint32_t>(ac, (size_t)C_a + 1);
+    m.e_tiles = arena_take<int4>(ac, e_tiles_max);
+    m.m_cls = arena_take<int32_t>(ac, (size_t)ix->nnz_multi + 1);
     m.row_off = arena_take<uint32_t>(ac, (size_t)P + 1);
-    m.row_t = arena_take<int32_t>(ac, (size_t)P + 1);
     m.row_RsA = arena_take<double2>(ac, (size_t)P + 1);
-    m.m_tiles = (int2 *)ac;
-    m.n_etiles = (int32_t)n_etiles;
-    m.n_short = n_short; m.n_long = n_long; m.n_hub = n_hub;
-    CU(cudaMemsetAsync(m.e_tid, 0, (size_t)(e_ints > 0 ? e_ints : 1) * 4, st));
-    k_row_perm<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rpre, d_rkey, d_deg, s->d_Rs, s->d_A, d_pos, m.row_t, d_degp, m.row_RsA);
+    m.m_tiles = arena_take<int2>(ac, m_tiles_max);
+    m.blk_row0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_cls0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_etile0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_mtile0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_nres = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.smem_bytes = ctx->em_smem_bytes;
+    // ---- rows: degrees, costs, ownership ranges ----
+    k_row_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_pos, d_deg, s->d_Rs, s->d_A, d_degp, m.row_RsA, d_ecost, P);
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_degp, m.row_off, P + 1, st));
     LAUNCHED(ctx);
-    k_scatter_rows<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid, d_pos, m.row_off, m.m_cls);
-    LAUNCHED(ctx);
     if (nm > 0) {
-        k_pack_classes<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, ix->d_kseg_cid0, ix->d_kseg_k, ix->d_cls_off, ix->d_cls_tid,
-                                                                          d_act, d_newid, s->d_R, d_pos, stab, m.e_tid, m.e_R);
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_pos, d_ecost);
         LAUNCHED(ctx);
     }
-    if (n_etiles > 0) {
-        k_etiles<<<(unsigned)((n_etiles + 255) / 256), 256, 0, st>>>((int)n_etiles, n_kseg, ix->d_kseg_k, stab, m.e_tiles);
+    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degp, d_ecost, d_cost);
+    LAUNCHED(ctx);
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cost, d_costp, P + 1, st));
+    LAUNCHED(ctx);
+    k_block_bounds<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, P, d_costp, m.blk_row0);
+    LAUNCHED(ctx);
+    // ---- classes: (owner CTA, cardinality) cells ----
+    CU(cudaMemsetAsync(d_cell_cnt, 0, (size_t)(n_cells + 1) * 4, st));
+    k_fill_int<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, st>>>(d_cell_first, n_cells + 1, 0x7fffffff);
+    LAUNCHED(ctx);
+    if (nm > 0 && n_kseg > 0) {
+        k_class_cells<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, B, ix->d_kseg_cid0, ix->d_cls_off, ix->d_cls_tid, d_act, d_newid,
+                                                                   d_pos, m.blk_row0, d_cellof, d_cell_cnt, d_cell_first);
         LAUNCHED(ctx);
     }
+    k_cell_sizes<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, st>>>(n_cells, n_kseg > 0 ? n_kseg : 1, ix->d_kseg_k, d_cell_cnt, d_cell_ints, d_cell_tiles);
+    LAUNCHED(ctx);
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cell_cnt, d_clsbase, n_cells + 1, st));
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cell_ints, d_intbase, n_cells + 1, st));
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cell_tiles, d_tilebase, n_cells + 1, st));
+    ctx->launches += 3;
+    k_block_tables<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_kseg > 0 ? n_kseg : 1, d_clsbase, d_tilebase, m.blk_cls0, m.blk_etile0);
+    LAUNCHED(ctx);
+    k_mtile_counts<<<1, 32, 0, st>>>(B, m.blk_row0, m.row_off, m.blk_mtile0);
+    LAUNCHED(ctx);
+    k_block_nres<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, ctx->em_smem_bytes, m.blk_row0, m.blk_cls0, m.blk_etile0, m.blk_mtile0, m.blk_nres);
+    LAUNCHED(ctx);
+    CU(cudaMemsetAsync(m.e_tid, 0, e_ints_max * 4, st));
+    if (nm > 0 && n_kseg > 0) {
+        k_pack_classes<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, m.blk_nres, ix->d_kseg_k, ix->d_cls_off, ix->d_cls_tid, d_act, d_newid,
+                                                                          d_cellof, d_cell_first, d_clsbase, d_intbase, s->d_R, d_pos, m.blk_row0,
+                                                                          m.blk_cls0, d_newid2, m.e_tid, m.e_R);
+        LAUNCHED(ctx);
+    }
+    k_scatter_rows<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, B, m.blk_nres, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid2, d_pos, m.blk_row0,
+                                                                             m.blk_cls0, m.row_off, m.m_cls);
+    LAUNCHED(ctx);
     CU(cudaGetLastError());
-    uint32_t off_short = 0, off_all = 0;
-    CU(cudaMemcpyAsync(&off_short, m.row_off + n_short, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&off_all, m.row_off + P, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t nnz_a = 0, e_ints = 0;
+    int32_t n_etiles = 0, n_mtiles = 0;
+    CU(cudaMemcpyAsync(&nnz_a, m.row_off + P, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&e_ints, d_intbase + n_cells, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&n_etiles, d_tilebase + n_cells, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&n_mtiles, m.blk_mtile0 + B, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    m.nnz_a = off_all;
-    const int64_t n_mtiles = ((int64_t)off_short + (int64_t)M_ROW_COST * n_short + M_WINDOW - 1) / M_WINDOW;
-    m.n_mtiles = (int32_t)n_mtiles;
+    if ((size_t)e_ints > e_ints_max || (size_t)n_etiles > e_tiles_max || (size_t)n_mtiles > m_tiles_max) {
+        emsar_set_err("internal: packed model exceeds its bounds (%u ints, %d/%d tiles)", e_ints, n_etiles, n_mtiles);
+        return EMSAR_ERR_STATE;
+    }
+    m.nnz_a = nnz_a; m.n_etiles = n_etiles; m.n_mtiles = n_mtiles;
+    if (n_etiles > 0) {
+        k_etiles<<<(unsigned)((n_etiles + 255) / 256), 256, 0, st>>>(n_etiles, n_cells, n_kseg, ix->d_kseg_k, d_tilebase, d_clsbase, d_cell_cnt, d_intbase, m.e_tiles);
+        LAUNCHED(ctx);
+    }
     if (n_mtiles > 0) {
-        k_mtiles<<<(unsigned)((n_mtiles + 255) / 256), 256, 0, st>>>((int)n_mtiles, n_short, m.row_off, m.m_tiles);
+        k_mtiles<<<(unsigned)((n_mtiles + 255) / 256), 256, 0, st>>>(n_mtiles, B, m.blk_row0, m.blk_mtile0, m.row_off, m.m_tiles);
         LAUNCHED(ctx);
     }
     // start point: theta = 1 for every row that takes part (A_t > 0)
@@ -513,11 +648,12 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     emsar_model_stats &ms_ = s->stats;
     memset(&ms_, 0, sizeof(ms_));
     ms_.T = T; ms_.C_a = C_a; ms_.nnz_a = m.nnz_a;
-    ms_.rows_short = n_short; ms_.rows_long = n_long; ms_.rows_hub = n_hub; ms_.rows_fixed = T - P;
+    ms_.rows_short = P; ms_.rows_long = 0; ms_.rows_hub = 0; ms_.rows_fixed = T - P;
     ms_.e_tiles = n_etiles; ms_.m_tiles = n_mtiles;
     ms_.bytes_per_iter = 8 * m.nnz_a + 24 * C_a + 44 * (int64_t)T;
-    // what the kernels stream: E: tids (padded) + R + q write + tiles; M: m_cls + row_off + RsA + theta r/w + tiles
-    ms_.stream_bytes_per_iter = 4 * e_ints + 4 * C_a + 8 * C_a + 16 * n_etiles + 4 * m.nnz_a + 4 * (int64_t)P + 16 * (int64_t)P + 16 * (int64_t)P + 8 * n_mtiles;
+    // what the kernel streams per iteration: E: encoded members (padded) + R + tiles (+ q to global for halo classes);
+    // M: encoded classes + row_off + {Rs,A} + theta write-through + tiles
+    ms_.stream_bytes_per_iter = 4 * (int64_t)e_ints + 4 * C_a + 16 * (int64_t)n_etiles + 4 * m.nnz_a + 4 * (int64_t)P + 16 * (int64_t)P + 8 * (int64_t)P + 8 * (int64_t)n_mtiles;
     s->prepared = true;
     s->n_iter = 0; s->final_delta = INFINITY; s->em_ms = 0;
     return EMSAR_OK;
