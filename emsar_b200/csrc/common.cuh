@@ -36,15 +36,9 @@ void emsar_set_err(const char *fmt, ...);
 #define EM_MIN_BLOCKS 1       // launch-bounds hint: resident CTAs per SM
 #endif
 constexpr int EM_WARPS = EM_BLOCK / 32;
-constexpr int KT = 8;             // classes with cardinality <= KT: thread-per-class, tile-transposed tids
-constexpr int KSUB = 32;          // KT < k <= KSUB: 8 lanes per class; k > KSUB: warp per class
-constexpr int E_TILE_TARGET = 256; // target gathers per warp tile for the long-class modes
-constexpr int M_SHORT_MAX = 128;  // transposed rows with more active entries are reduced by a whole warp
-constexpr int M_WINDOW = 192;     // cost window of a row tile (cost = entries + M_ROW_COST per row)
-constexpr int M_ROW_COST = 6;     // => at most M_WINDOW / M_ROW_COST = 32 rows per tile (one per lane)
-constexpr int STG_INTS = 352;     // ints per staging buffer (one tile's index chunk): >= M_WINDOW + M_SHORT_MAX + 4 and >= E_TILE_TARGET + 4
-constexpr int STG_BYTES_PER_WARP = 2 * STG_INTS * 4;   // double buffered
-constexpr int M_HUB_MIN = 4096;   // rows with more active entries are reduced by a whole CTA
+constexpr int KT = 32;            // classes with cardinality <= KT: one thread per class, members stored transposed in tiles of 32 classes
+constexpr int E_TILE_TARGET = 256; // larger classes: one warp per class, about this many members per tile
+constexpr int M_LONG = 256;       // transposed rows with more active entries: one warp per row; the rest go into SELL-32 slices
 
 struct KSeg {          // multi-tid classes of one cardinality, contiguous in cid order
     int32_t k;
@@ -92,20 +86,22 @@ struct emsar_index {
 };
 
 // per-sample packed model the EM kernel streams (all device pointers).
-// Ownership: the participating rows (transcripts with A_t > 0, natural order) are cut into B contiguous ranges of equal
-// cost, one per CTA of the persistent kernel; a class belongs to the CTA that owns its FIRST member row. Each CTA keeps
-// theta of its rows and q of (as many as fit of) its classes in shared memory; references that leave the CTA's range
-// ("halo") go through the global copies. Indices are pre-encoded: >= 0 = slot in the owner's shared memory,
+// Ownership: the participating rows (transcripts with A_t > 0) are cut, in natural order, into B contiguous ranges of
+// equal cost, one per CTA of the persistent kernel; a class belongs to the CTA that owns its FIRST member row. Each
+// CTA keeps theta of its rows and q of (as many as fit of) its classes in shared memory; references that leave the
+// CTA's range ("halo") go through the global copies. Indices are pre-encoded: >= 0 = slot in the owner's shared memory,
 // < 0 = ~(global index).
+// Both directions are stored as SELL-32 slices: inside a CTA the rows are sorted by length, 32 rows form a slice stored
+// transposed and padded to its longest row (one thread per row, sequential sum); classes are sorted by cardinality
+// (no padding needed), 32 classes form a tile stored transposed (one thread per class).
 struct EmModel {
     int32_t T, P, B;
     int64_t C_a, nnz_a;
-    int32_t cap;           // doubles of shared memory per CTA for theta | q
     int32_t *blk_row0;     // [B+1] first row of each CTA
     int32_t *blk_cls0;     // [B+1] first (compact) class of each CTA
     int32_t *blk_etile0;   // [B+1]
-    int32_t *blk_mtile0;   // [B+1]
-    int32_t *blk_nres;     // [B]   classes of the CTA whose q lives in shared memory
+    int32_t *blk_mitem0;   // [B+1]
+    int32_t *blk_nres;     // [B]   classes of the CTA whose q lives in shared memory (slot nres holds 0.0: padding target)
     int32_t smem_bytes;    // dynamic shared memory per CTA
     // E side
     int32_t *e_tid;        // encoded member rows (tile-transposed for k<=KT, row-major otherwise)
@@ -113,11 +109,11 @@ struct EmModel {
     int4 *e_tiles;         // {j0, cnt, tid_off, k | mode<<16}
     int32_t n_etiles;
     // M side
-    int32_t *m_cls;        // [nnz_a] encoded class per transposed entry
-    uint32_t *row_off;     // [P+1]
+    int32_t *m_cls;        // encoded classes: slices transposed + padded, long rows row-major
+    int4 *m_items;         // {first row slot, rows, entry offset, length | mode<<30}: mode 0 = slice, 1 = long row
     double2 *row_RsA;      // [P] {Rs, A}
-    int2 *m_tiles;         // row tiles {p0, p1}, never straddling a CTA boundary
-    int32_t n_mtiles;
+    int32_t n_mitems;
+    int64_t m_ints;        // entries stored (with padding)
     // state (global copies; the shared-memory copies are loaded from / written through to these)
     double *theta;         // [P]
     double *q;             // [C_a]
@@ -152,6 +148,8 @@ struct emsar_sample {
     size_t state_bytes;
     void *d_pack;          // packed model arena
     size_t pack_bytes;
+    int32_t *d_mcls;       // M-side entries (sized after the slices are known)
+    size_t mcls_bytes;
     EmModel m;
     emsar_model_stats stats;
     // solve bookkeeping
@@ -181,20 +179,19 @@ int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
 
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__
-// Shared-memory plan of one CTA of k_em_persistent: [index staging, 2 buffers per warp][E tile descriptors]
-// [M tile descriptors][row_off of its rows][theta of its rows][q of its first nres classes]
-struct SmemPlan { int off_etiles, off_mtiles, off_rowoff, off_theta, off_q; };
-__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int n_et, int n_mt, int nrows)
+// Shared-memory plan of one CTA of k_em_persistent: [E tile descriptors][M items][theta of its rows]
+// [q of its first nres classes][one zero slot]
+struct SmemPlan { int off_etiles, off_mitems, off_theta, off_q; };
+__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int n_et, int n_mi, int nrows)
 {
     SmemPlan p;
-    p.off_etiles = EM_WARPS * STG_BYTES_PER_WARP;
-    p.off_mtiles = p.off_etiles + ((n_et * 16 + 15) & ~15);
-    p.off_rowoff = p.off_mtiles + ((n_mt * 8 + 15) & ~15);
-    p.off_theta = p.off_rowoff + (((nrows + 1) * 4 + 15) & ~15);
+    p.off_etiles = 0;
+    p.off_mitems = p.off_etiles + n_et * 16;
+    p.off_theta = p.off_mitems + n_mi * 16;
     p.off_q = p.off_theta + nrows * 8;
     return p;
 }
-__host__ __device__ __forceinline__ int em_fixed_smem(int n_et, int n_mt, int nrows) { return em_smem_plan(n_et, n_mt, nrows).off_q; }
+__host__ __device__ __forceinline__ int em_fixed_smem(int n_et, int n_mi, int nrows) { return em_smem_plan(n_et, n_mi, nrows).off_q + 8; }
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;

@@ -51,20 +51,22 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
 // ---- shared-memory resident slices ---------------------------------------------------------------------
 struct BlockView {
     double *sm_theta;          // theta of the rows this CTA owns
-    double *sm_q;              // q of the resident classes this CTA owns
+    double *sm_q;              // q of the resident classes this CTA owns; sm_q[nres] == 0 (padding target)
     const int4 *sm_etiles;     // this CTA's E tile descriptors
-    const int2 *sm_mtiles;     // this CTA's row tiles
-    const uint32_t *sm_rowoff; // row_off[row0 .. row0+nrows]
+    const int4 *sm_mitems;     // this CTA's M items
     int row0, nrows, cls0, nres;
 };
 
+// branch-free: one generic load from either the CTA's shared slice or the global (halo) copy
 __device__ __forceinline__ double load_theta(const EmParams &p, const BlockView &v, int enc)
 {
-    return enc >= 0 ? v.sm_theta[enc] : p.m.theta[~enc];
+    const double *ptr = enc >= 0 ? v.sm_theta + enc : p.m.theta + ~enc;
+    return *ptr;
 }
 __device__ __forceinline__ double load_q(const EmParams &p, const BlockView &v, int enc)
 {
-    return enc >= 0 ? v.sm_q[enc] : p.m.q[~enc];
+    const double *ptr = enc >= 0 ? v.sm_q + enc : p.m.q + ~enc;
+    return *ptr;
 }
 __device__ __forceinline__ void store_q(const EmParams &p, const BlockView &v, int j, uint32_t rflag, double s)
 {
@@ -75,206 +77,84 @@ __device__ __forceinline__ void store_q(const EmParams &p, const BlockView &v, i
     if (rflag & 0x80000000u) p.m.q[j] = val;        // a row of another CTA reads it, or it does not fit in shared memory
 }
 
-// ---- index staging: a tile's chunk of the int32 index stream -> this warp's shared buffer via cp.async ------------
-// The chunk [g, g+n) is fetched from its 16-byte-aligned floor; entry i then sits at buf[shift + i].
-__device__ __forceinline__ int stage_issue(int *buf, const int32_t *g, int n, int lane)
-{
-    const uintptr_t ga = (uintptr_t)g & ~(uintptr_t)15;
-    const int shift = (int)(((uintptr_t)g - ga) >> 2);
-    const int chunks = (n + shift + 3) >> 2;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
-    for (int c = lane; c < chunks; c += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + c * 16), "l"(ga + (uintptr_t)c * 16));
-    return shift;
-}
-__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-struct Idx {                   // a tile's index chunk: staged in shared memory, or (oversized tiles) straight from global
-    const int *sm;
-    const int32_t *g;
-    bool staged;
-    __device__ __forceinline__ int operator[](int i) const { return staged ? sm[i] : __ldg(g + i); }
-};
-
-__device__ __forceinline__ int etile_ints(int4 t)
-{
-    const int k = t.w & 0xffff, mode = t.w >> 16;
-    return mode == 0 ? 32 * k : t.y * k;
-}
-
 // ---- E-phase: q_c = R_c / sum of theta over the class members --------------------------------------------------
-template <int K>
-__device__ __forceinline__ double esum_tp(const EmParams &p, const BlockView &v, const Idx &ix, int lane)
+__device__ __forceinline__ void e_phase(const EmParams &p, const BlockView &v, int n_tiles, int warp, int lane)
 {
-    int t[K];
-#pragma unroll
-    for (int j = 0; j < K; j++) t[j] = ix[j * 32 + lane];
-    double x[K];
-#pragma unroll
-    for (int j = 0; j < K; j++) x[j] = load_theta(p, v, t[j]);
-    double s = 0;
-#pragma unroll
-    for (int j = 0; j < K; j++) s += x[j];      // sequential member order
-    return s;
-}
-
-template <int G>
-__device__ __forceinline__ void etile_group(const EmParams &p, const BlockView &v, int4 tile, int k, const Idx &ix, int lane)
-{
-    constexpr int CPP = 32 / G;          // classes per pass
-    const int sub = lane / G, l = lane % G;
-    for (int c0 = 0; c0 < tile.y; c0 += CPP) {
-        const int cl = c0 + sub;
-        const bool valid = cl < tile.y;
-        double s = 0;
-        if (valid) {
-            const int base = cl * k;
-#pragma unroll 4
-            for (int i = l; i < k; i += G) s += load_theta(p, v, ix[base + i]);
-        }
-#pragma unroll
-        for (int d = G / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (valid && l == 0) store_q(p, v, tile.x + cl, __ldg(p.m.e_R + tile.x + cl), s);
-    }
-}
-
-__device__ __forceinline__ void e_phase(const EmParams &p, const BlockView &v, int n_tiles, int *stg, int warp, int lane)
-{
-    int g = warp, buf = 0;
-    int4 tile = make_int4(0, 0, 0, 0);
-    int shift = 0; bool staged = false;
-    if (g < n_tiles) {
-        tile = v.sm_etiles[g];
-        const int n = etile_ints(tile);
-        staged = n <= STG_INTS - 4;
-        if (staged) shift = stage_issue(stg, p.m.e_tid + (uint32_t)tile.z, n, lane);
-    }
-    stage_commit();
-    for (; g < n_tiles; g += EM_WARPS) {
-        // prefetch the next tile's members into the other buffer
-        const int gn = g + EM_WARPS;
-        int4 tile_n = make_int4(0, 0, 0, 0);
-        int shift_n = 0; bool staged_n = false;
-        if (gn < n_tiles) {
-            tile_n = v.sm_etiles[gn];
-            const int n = etile_ints(tile_n);
-            staged_n = n <= STG_INTS - 4;
-            if (staged_n) shift_n = stage_issue(stg + (buf ^ 1) * STG_INTS, p.m.e_tid + (uint32_t)tile_n.z, n, lane);
-        }
-        stage_commit();
+    // tiles are ordered by cardinality: walk them from the heaviest so that the tail of the phase is made of light tiles
+    for (int g = n_tiles - 1 - warp; g >= 0; g -= EM_WARPS) {
+        const int4 tile = v.sm_etiles[g];
         const int k = tile.w & 0xffff, mode = tile.w >> 16;
-        uint32_t rf = 0;
-        if (mode == 0 && lane < tile.y) rf = __ldg(p.m.e_R + tile.x + lane);      // in flight while the staging lands
-        stage_wait<1>();
-        __syncwarp();
-        Idx ix;
-        ix.sm = stg + buf * STG_INTS + shift; ix.g = p.m.e_tid + (uint32_t)tile.z; ix.staged = staged;
         if (mode == 0) {
-            double s;
-            switch (k) {
-            case 2: s = esum_tp<2>(p, v, ix, lane); break;
-            case 3: s = esum_tp<3>(p, v, ix, lane); break;
-            case 4: s = esum_tp<4>(p, v, ix, lane); break;
-            case 5: s = esum_tp<5>(p, v, ix, lane); break;
-            case 6: s = esum_tp<6>(p, v, ix, lane); break;
-            case 7: s = esum_tp<7>(p, v, ix, lane); break;
-            default: s = esum_tp<8>(p, v, ix, lane); break;
+            // one thread per class; member j of the 32 classes of the tile is one coalesced 128-byte line
+            const int32_t *__restrict__ tids = p.m.e_tid + (uint32_t)tile.z + lane;
+            uint32_t rf = 0;
+            if (lane < tile.y) rf = __ldg(p.m.e_R + tile.x + lane);
+            double s = 0;
+            int j = 0;
+            for (; j + 4 <= k; j += 4) {
+                const int t0 = __ldg(tids + j * 32), t1 = __ldg(tids + j * 32 + 32), t2 = __ldg(tids + j * 32 + 64), t3 = __ldg(tids + j * 32 + 96);
+                const double x0 = load_theta(p, v, t0), x1 = load_theta(p, v, t1), x2 = load_theta(p, v, t2), x3 = load_theta(p, v, t3);
+                s += x0; s += x1; s += x2; s += x3;          // sequential member order
             }
+            for (; j < k; j++) s += load_theta(p, v, __ldg(tids + j * 32));
             if (lane < tile.y) store_q(p, v, tile.x + lane, rf, s);
-        } else if (mode == 1) etile_group<8>(p, v, tile, k, ix, lane);
-        else etile_group<32>(p, v, tile, k, ix, lane);
-        __syncwarp();
-        tile = tile_n; shift = shift_n; staged = staged_n; buf ^= 1;
+        } else {
+            // long classes: one warp per class, members row-major
+            for (int cl = 0; cl < tile.y; cl++) {
+                const int32_t *__restrict__ tids = p.m.e_tid + (uint32_t)tile.z + (uint32_t)cl * (uint32_t)k;
+                double s = 0;
+#pragma unroll 4
+                for (int i = lane; i < k; i += 32) s += load_theta(p, v, __ldg(tids + i));
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                if (lane == 0) store_q(p, v, tile.x + cl, __ldg(p.m.e_R + tile.x + cl), s);
+            }
+        }
     }
-    stage_wait<0>();
 }
 
 // ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
-__device__ __forceinline__ double m_phase(const EmParams &p, const BlockView &v, int n_tiles, int *stg, int warp, int lane)
+__device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v, int slot, double Q)
+{
+    const double2 ra = p.m.row_RsA[v.row0 + slot];
+    const double th = v.sm_theta[slot];
+    const double n = ra.x + th * Q;
+    const double thn = n / ra.y;
+    v.sm_theta[slot] = thn;
+    p.m.theta[v.row0 + slot] = thn;                 // write-through: halo readers and the final result
+    return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
+}
+
+__device__ __forceinline__ double m_phase(const EmParams &p, const BlockView &v, int n_items, int warp, int lane)
 {
     double dmax = 0;
-    const int sub = lane >> 3, l = lane & 7;
-    int g = warp, buf = 0;
-    int2 tile = make_int2(0, 0);
-    int shift = 0; bool staged = false; uint32_t e0 = 0;
-    if (g < n_tiles) {
-        tile = v.sm_mtiles[g];
-        e0 = v.sm_rowoff[tile.x - v.row0];
-        const int n = (int)(v.sm_rowoff[tile.y - v.row0] - e0);
-        staged = n <= STG_INTS - 4;
-        if (staged && n > 0) shift = stage_issue(stg, p.m.m_cls + e0, n, lane);
-    }
-    stage_commit();
-    for (; g < n_tiles; g += EM_WARPS) {
-        const int gn = g + EM_WARPS;
-        int2 tile_n = make_int2(0, 0);
-        int shift_n = 0; bool staged_n = false; uint32_t e0_n = 0;
-        if (gn < n_tiles) {
-            tile_n = v.sm_mtiles[gn];
-            e0_n = v.sm_rowoff[tile_n.x - v.row0];
-            const int n = (int)(v.sm_rowoff[tile_n.y - v.row0] - e0_n);
-            staged_n = n <= STG_INTS - 4;
-            if (staged_n && n > 0) shift_n = stage_issue(stg + (buf ^ 1) * STG_INTS, p.m.m_cls + e0_n, n, lane);
-        }
-        stage_commit();
-        const int nrows = tile.y - tile.x;
-        // each lane owns one row of the tile; its {Rs, A} load overlaps the staging
-        uint32_t a_mine = 0, b_mine = 0;
-        double2 ra = make_double2(0.0, 1.0);
-        if (lane < nrows) {
-            a_mine = v.sm_rowoff[tile.x - v.row0 + lane] - e0;
-            b_mine = v.sm_rowoff[tile.x - v.row0 + lane + 1] - e0;
-            ra = p.m.row_RsA[tile.x + lane];
-        }
-        const bool is_long = (b_mine - a_mine) > (uint32_t)M_SHORT_MAX;
-        stage_wait<1>();
-        __syncwarp();
-        Idx ix;
-        ix.sm = stg + buf * STG_INTS + shift; ix.g = p.m.m_cls + e0; ix.staged = staged;
-        double Qmine = 0;
-        // short rows: 8 lanes per row, 4 rows per pass, fixed shuffle tree
-        for (int pass = 0; pass * 4 < nrows; pass++) {
-            const int r = pass * 4 + sub;
-            const uint32_t a = __shfl_sync(0xffffffffu, a_mine, r & 31), b = __shfl_sync(0xffffffffu, b_mine, r & 31);
-            const bool lng = __shfl_sync(0xffffffffu, (int)is_long, r & 31) != 0;
-            double s = 0;
-            if (r < nrows && !lng) {
-#pragma unroll 4
-                for (uint32_t e = a + l; e < b; e += 8) s += load_q(p, v, ix[(int)e]);
+    // items are ordered longest first (long rows, then slices by decreasing length)
+    for (int g = warp; g < n_items; g += EM_WARPS) {
+        const int4 it = v.sm_mitems[g];
+        const int len = it.w & 0x3fffffff;
+        if ((it.w >> 30) == 0) {
+            // a slice of 32 rows stored transposed: one thread per row, sequential sum in ascending class order
+            const int32_t *__restrict__ ent = p.m.m_cls + (uint32_t)it.z + lane;
+            double Q = 0;
+            int j = 0;
+            for (; j + 4 <= len; j += 4) {
+                const int c0 = __ldg(ent + j * 32), c1 = __ldg(ent + j * 32 + 32), c2 = __ldg(ent + j * 32 + 64), c3 = __ldg(ent + j * 32 + 96);
+                const double x0 = load_q(p, v, c0), x1 = load_q(p, v, c1), x2 = load_q(p, v, c2), x3 = load_q(p, v, c3);
+                Q += x0; Q += x1; Q += x2; Q += x3;
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const double got = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);
-            if ((lane >> 2) == pass) Qmine = got;
-        }
-        // long rows of the tile: the whole warp reduces one row at a time
-        unsigned longm = __ballot_sync(0xffffffffu, is_long);
-        while (longm) {
-            const int src = __ffs(longm) - 1;
-            longm &= longm - 1;
-            const uint32_t a = __shfl_sync(0xffffffffu, a_mine, src), b = __shfl_sync(0xffffffffu, b_mine, src);
+            for (; j < len; j++) Q += load_q(p, v, __ldg(ent + j * 32));
+            if (lane < it.y) dmax = fmax(dmax, m_update(p, v, it.x + lane, Q));
+        } else {
+            // a long row: the whole warp, fixed shuffle tree
+            const int32_t *__restrict__ ent = p.m.m_cls + (uint32_t)it.z;
             double s = 0;
 #pragma unroll 4
-            for (uint32_t e = a + lane; e < b; e += 32) s += load_q(p, v, ix[(int)e]);
+            for (int e = lane; e < len; e += 32) s += load_q(p, v, __ldg(ent + e));
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == src) Qmine = s;
+            if (lane == 0) dmax = fmax(dmax, m_update(p, v, it.x, s));
         }
-        if (lane < nrows) {
-            const int row = tile.x + lane;
-            const double th = v.sm_theta[row - v.row0];
-            const double n = ra.x + th * Qmine;
-            const double thn = n / ra.y;
-            v.sm_theta[row - v.row0] = thn;
-            p.m.theta[row] = thn;                       // write-through: halo readers and the final result
-            dmax = fmax(dmax, fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n));
-        }
-        __syncwarp();
-        tile = tile_n; shift = shift_n; staged = staged_n; e0 = e0_n; buf ^= 1;
     }
-    stage_wait<0>();
     return dmax;
 }
 
@@ -286,30 +166,28 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x;
     const int et0 = p.m.blk_etile0[b], n_et = p.m.blk_etile0[b + 1] - et0;
-    const int mt0 = p.m.blk_mtile0[b], n_mt = p.m.blk_mtile0[b + 1] - mt0;
+    const int mi0 = p.m.blk_mitem0[b], n_mi = p.m.blk_mitem0[b + 1] - mi0;
     BlockView v;
     v.row0 = p.m.blk_row0[b]; v.nrows = p.m.blk_row0[b + 1] - v.row0;
     v.cls0 = p.m.blk_cls0[b]; v.nres = p.m.blk_nres[b];
-    const SmemPlan pl = em_smem_plan(n_et, n_mt, v.nrows);
-    int *stg = (int *)sm_dyn + warp * (2 * STG_INTS);
+    const SmemPlan pl = em_smem_plan(n_et, n_mi, v.nrows);
     int4 *s_et = (int4 *)(sm_dyn + pl.off_etiles);
-    int2 *s_mt = (int2 *)(sm_dyn + pl.off_mtiles);
-    uint32_t *s_ro = (uint32_t *)(sm_dyn + pl.off_rowoff);
+    int4 *s_mi = (int4 *)(sm_dyn + pl.off_mitems);
     v.sm_theta = (double *)(sm_dyn + pl.off_theta);
     v.sm_q = (double *)(sm_dyn + pl.off_q);
-    v.sm_etiles = s_et; v.sm_mtiles = s_mt; v.sm_rowoff = s_ro;
+    v.sm_etiles = s_et; v.sm_mitems = s_mi;
     // per-CTA constants and the CTA's slice of theta -> shared memory, once
     for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_et[i] = p.m.e_tiles[et0 + i];
-    for (int i = threadIdx.x; i < n_mt; i += EM_BLOCK) s_mt[i] = p.m.m_tiles[mt0 + i];
-    for (int i = threadIdx.x; i <= v.nrows; i += EM_BLOCK) s_ro[i] = p.m.row_off[v.row0 + i];
+    for (int i = threadIdx.x; i < n_mi; i += EM_BLOCK) s_mi[i] = p.m.m_items[mi0 + i];
     for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = p.m.theta[v.row0 + i];
+    for (int i = threadIdx.x; i <= v.nres; i += EM_BLOCK) v.sm_q[i] = 0.0;
     __syncthreads();
     int it = 0;
     double d = INFINITY;
     while (it < p.max_iter) {
-        e_phase(p, v, n_et, stg, warp, lane);
+        e_phase(p, v, n_et, warp, lane);
         grid_barrier(p.bar, gridDim.x);
-        double dm = m_phase(p, v, n_mt, stg, warp, lane);
+        double dm = m_phase(p, v, n_mi, warp, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;
@@ -654,7 +532,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     cudaFree(s->d_rd_ptr); cudaFree(s->d_rd_tid); cudaFree(s->d_rd_fl);
     cudaFree(s->d_Wf); cudaFree(s->d_adj); cudaFree(s->d_amodel); cudaFree(s->d_in_model);
     cudaFree(s->d_A); cudaFree(s->d_Rs); cudaFree(s->d_iE); cudaFree(s->d_lone); cudaFree(s->d_pos);
-    cudaFree(s->d_state); cudaFree(s->d_pack);
+    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls);
     delete s;
     return EMSAR_OK;
 }

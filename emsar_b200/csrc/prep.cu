@@ -110,40 +110,35 @@ __global__ void k_row_stats(int32_t T, const uint32_t *__restrict__ txm_off, con
     }
 }
 
-// rows in natural order: pos[t] = rank among the participating transcripts (in place over the scan output), -1 otherwise
-__global__ void k_row_fill(int32_t T, const uint32_t *__restrict__ rflag, int32_t *__restrict__ pos, const int32_t *__restrict__ deg,
-                           const double *__restrict__ Rs, const double *__restrict__ A, uint32_t *__restrict__ degp,
-                           double2 *__restrict__ row_RsA, int32_t *__restrict__ ecost, int32_t P)
+// participating transcripts in natural order: n = rank, with their active row length
+__global__ void k_nat_fill(int32_t T, const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ nat, const int32_t *__restrict__ deg,
+                           int32_t *__restrict__ pos, uint32_t *__restrict__ degn, int32_t *__restrict__ tn, int32_t *__restrict__ ecost, int32_t P)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) { degp[P] = 0; ecost[P] = 0; }
+    if (t == 0) { degn[P] = 0; ecost[P] = 0; }
     if (t >= T) return;
-    if (rflag[t]) {
-        const int p = pos[t];
-        degp[p] = (uint32_t)deg[t];
-        row_RsA[p] = make_double2(Rs[t], A[t]);
-        ecost[p] = 0;
-    } else pos[t] = -1;
+    if (rflag[t]) { const int n = (int)nat[t]; degn[n] = (uint32_t)deg[t]; tn[n] = t; ecost[n] = 0; }
+    else pos[t] = -1;
 }
 
 // E-phase cost lands on the row that owns the class (its first member)
 __global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
-                             const int32_t *__restrict__ act, const int32_t *__restrict__ pos, int32_t *__restrict__ ecost)
+                             const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_multi || !act[i]) return;
     const uint32_t o = cls_off[T + i];
-    atomicAdd(&ecost[pos[cls_tid[o]]], (int)(cls_off[T + i + 1] - o));
+    atomicAdd(&ecost[nat[cls_tid[o]]], (int)(cls_off[T + i + 1] - o));
 }
 
-__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degp, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost)
+__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > P) return;
-    cost[p] = p < P ? degp[p] + (uint32_t)ecost[p] + 2u : 0u;
+    cost[p] = p < P ? degn[p] + (uint32_t)ecost[p] + 2u : 0u;
 }
 
-// cut the rows into B ranges of equal cost
+// cut the rows (natural order) into B ranges of equal cost
 __global__ void k_block_bounds(int B, int32_t P, const uint32_t *__restrict__ costp, int32_t *__restrict__ row0)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,8 +164,90 @@ __device__ __forceinline__ int block_of_row(const int32_t *row0, int B, int p)
     return lo;
 }
 
+// sort key: (owner CTA, longest row first); the radix sort is stable, so ties keep their natural order
+__global__ void k_sort_keys(int32_t P, int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ degn,
+                            unsigned long long *__restrict__ key, int32_t *__restrict__ val)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P) return;
+    key[n] = ((unsigned long long)block_of_row(row0, B, n) << 32) | (unsigned long long)(0xFFFFFFFFu - degn[n]);
+    val[n] = n;
+}
+
+__global__ void k_apply_perm(int32_t P, const int32_t *__restrict__ perm, const int32_t *__restrict__ tn, const uint32_t *__restrict__ degn,
+                             const double *__restrict__ Rs, const double *__restrict__ A, int32_t *__restrict__ pos,
+                             uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int n = perm[p], t = tn[n];
+    pos[t] = p;
+    degp[p] = degn[n];
+    row_RsA[p] = make_double2(Rs[t], A[t]);
+}
+
+// M items of every CTA: first its long rows (one item each), then slices of 32 rows
+__global__ void k_block_items(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ degp, int32_t *__restrict__ nlong,
+                              int32_t *__restrict__ item0)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int acc = 0;
+    for (int b = 0; b < B; b++) {
+        const int r0 = row0[b], r1 = row0[b + 1];
+        int lo = r0, hi = r1;            // rows are sorted longest first: first row with degp <= M_LONG
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (degp[mid] <= (uint32_t)M_LONG) hi = mid; else lo = mid + 1; }
+        const int nl = lo - r0;
+        nlong[b] = nl;
+        item0[b] = acc;
+        acc += nl + ((r1 - r0 - nl) + 31) / 32;
+    }
+    item0[B] = acc;
+}
+
+__global__ void k_item_sizes(int n_items, int B, const int32_t *__restrict__ row0, const int32_t *__restrict__ nlong,
+                             const int32_t *__restrict__ item0, const uint32_t *__restrict__ degp, uint32_t *__restrict__ size, int4 *__restrict__ items)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_items) return;
+    if (g == n_items) { size[g] = 0; return; }
+    int lo = 0, hi = B - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (item0[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int b = lo, li = g - item0[b], nl = nlong[b], nrows = row0[b + 1] - row0[b];
+    int4 it;
+    if (li < nl) {
+        const uint32_t d = degp[row0[b] + li];
+        it.x = li; it.y = 1; it.z = 0; it.w = (int)(d | (1u << 30));
+        size[g] = d;
+    } else {
+        const int slot0 = nl + 32 * (li - nl);
+        const uint32_t d = degp[row0[b] + slot0];
+        it.x = slot0; it.y = min(32, nrows - slot0); it.z = 0; it.w = (int)d;
+        size[g] = 32u * d;
+    }
+    items[g] = it;
+}
+
+// entry offsets into the items; the unused lanes of a CTA's last (partial) slice point at the zero slot
+__global__ void k_item_finish(int n_items, int B, const int32_t *__restrict__ item0, const int32_t *__restrict__ nres,
+                              const uint32_t *__restrict__ item_off, int4 *__restrict__ items, int32_t *__restrict__ m_cls)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_items) return;
+    int4 it = items[g];
+    it.z = (int)item_off[g];
+    items[g] = it;
+    if ((it.w >> 30) == 0 && it.y < 32) {
+        int lo = 0, hi = B - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (item0[mid] <= g) lo = mid; else hi = mid - 1; }
+        const int zero = nres[lo], len = it.w;
+        for (int j = 0; j < len; j++)
+            for (int l = it.y; l < 32; l++) m_cls[item_off[g] + (uint32_t)j * 32u + (uint32_t)l] = zero;
+    }
+}
+
 // cell = (owner CTA, cardinality segment). Classes of one cell are contiguous in cid order (first tids ascend inside a
-// cardinality segment), so a class's rank inside its cell is (old compact id - smallest old compact id of the cell).
+// cardinality segment and CTA ranges are natural-order ranges), so a class's rank inside its cell is
+// (old compact id - smallest old compact id of the cell).
 __global__ void k_class_cells(int64_t n_multi, int32_t T, int n_kseg, int B, const int64_t *__restrict__ kseg_cid0,
                               const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
                               const int32_t *__restrict__ newid, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
@@ -186,12 +263,7 @@ __global__ void k_class_cells(int64_t n_multi, int32_t T, int n_kseg, int B, con
     atomicMin(&cell_first[cell], j);
 }
 
-__device__ __forceinline__ int cls_per_tile(int k)
-{
-    if (k <= KT) return 32;
-    if (k <= KSUB) return min(32, max(4, (E_TILE_TARGET / k) & ~3));
-    return max(1, E_TILE_TARGET / k);
-}
+__device__ __forceinline__ int cls_per_tile(int k) { return k <= KT ? 32 : max(1, E_TILE_TARGET / k); }
 
 __global__ void k_cell_sizes(int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ cell_cnt,
                              uint32_t *__restrict__ cell_ints, int32_t *__restrict__ cell_tiles)
@@ -214,11 +286,11 @@ __global__ void k_block_tables(int B, int n_kseg, const int32_t *__restrict__ cl
 }
 
 __global__ void k_block_nres(int B, int smem_bytes, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
-                             const int32_t *__restrict__ etile0, const int32_t *__restrict__ mtile0, int32_t *__restrict__ nres)
+                             const int32_t *__restrict__ etile0, const int32_t *__restrict__ mitem0, int32_t *__restrict__ nres)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const int left = smem_bytes - em_fixed_smem(etile0[b + 1] - etile0[b], mtile0[b + 1] - mtile0[b], row0[b + 1] - row0[b]);
+    const int left = smem_bytes - em_fixed_smem(etile0[b + 1] - etile0[b], mitem0[b + 1] - mitem0[b], row0[b + 1] - row0[b]);
     nres[b] = max(0, min(cls0[b + 1] - cls0[b], left / 8));
 }
 
@@ -261,11 +333,12 @@ __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int
 }
 
 // One warp per transcript: the ACTIVE entries of its transposed row, in ascending cid order, as encoded classes
-// (>= 0: slot in the row owner's shared q, < 0: ~global compact id).
+// (>= 0: slot in the row owner's shared q, < 0: ~global compact id), written into the row's slice column (padded with
+// the zero slot up to the slice's length) or, for a long row, contiguously.
 __global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk_nres, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
                                const int32_t *__restrict__ act, const int32_t *__restrict__ newid2, const int32_t *__restrict__ pos,
-                               const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0, const uint32_t *__restrict__ row_off,
-                               int32_t *__restrict__ m_cls)
+                               const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0, const int32_t *__restrict__ nlong,
+                               const int32_t *__restrict__ item0, const int4 *__restrict__ items, int32_t *__restrict__ m_cls)
 {
     const int lane = threadIdx.x & 31;
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -273,9 +346,15 @@ __global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk
     const int p = pos[t];
     if (p < 0) return;
     const int b = block_of_row(row0, B, p);
-    const int c0 = cls0[b];
-    const int nres = blk_nres[b];
-    uint32_t out = row_off[p];
+    const int c0 = cls0[b], nres = blk_nres[b];
+    const int slot = p - row0[b], nl = nlong[b];
+    uint32_t base, stride, len;
+    if (slot < nl) { const int4 it = items[item0[b] + slot]; base = (uint32_t)it.z; stride = 1; len = (uint32_t)it.w & 0x3fffffffu; }
+    else {
+        const int4 it = items[item0[b] + nl + ((slot - nl) >> 5)];
+        base = (uint32_t)it.z + (uint32_t)((slot - nl) & 31); stride = 32; len = (uint32_t)it.w & 0x3fffffffu;
+    }
+    uint32_t out = 0;
     const uint32_t e0 = txm_off[t], e1 = txm_off[t + 1];
     for (uint32_t e = e0; e < e1; e += 32) {
         int a = 0, id = 0;
@@ -283,10 +362,11 @@ __global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk
         unsigned m = __ballot_sync(0xffffffffu, a != 0);
         if (a) {
             const int loc = id - c0;
-            m_cls[out + __popc(m & ((1u << lane) - 1))] = (loc >= 0 && loc < nres) ? loc : ~id;
+            m_cls[base + (out + (uint32_t)__popc(m & ((1u << lane) - 1))) * stride] = (loc >= 0 && loc < nres) ? loc : ~id;
         }
         out += __popc(m);
     }
+    for (uint32_t j = out + lane; j < len; j += 32) m_cls[base + j * stride] = nres;    // padding -> the zero slot
 }
 
 __global__ void k_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ tilebase,
@@ -298,46 +378,12 @@ __global__ void k_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__
     int lo = 0, hi = n_cells - 1;      // largest cell with tilebase[cell] <= g (non-empty by construction)
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tilebase[mid] <= g) lo = mid; else hi = mid - 1; }
     const int c = lo, k = kseg_k[c % n_kseg], cpt = cls_per_tile(k), lt = g - tilebase[c];
-    const int mode = k <= KT ? 0 : (k <= KSUB ? 1 : 2);
     int4 t;
     t.x = clsbase[c] + lt * cpt;
     t.y = min(cpt, cell_cnt[c] - lt * cpt);
     t.z = (int)(intbase[c] + (uint32_t)lt * (uint32_t)cpt * (uint32_t)k);
-    t.w = k | (mode << 16);
+    t.w = k | ((k <= KT ? 0 : 1) << 16);
     tiles[g] = t;
-}
-
-// Row tiles: windows of M_WINDOW over cost(p) = row_off[p] + M_ROW_COST * p, restarted at every CTA boundary.
-__device__ __forceinline__ unsigned long long mcost(const uint32_t *row_off, int p) { return (unsigned long long)row_off[p] + (unsigned long long)M_ROW_COST * (unsigned long long)p; }
-__global__ void k_mtile_counts(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ row_off, int32_t *__restrict__ mtile0)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    int acc = 0;
-    for (int b = 0; b < B; b++) {
-        mtile0[b] = acc;
-        const unsigned long long c = mcost(row_off, row0[b + 1]) - mcost(row_off, row0[b]);
-        acc += (int)((c + M_WINDOW - 1) / M_WINDOW);
-    }
-    mtile0[B] = acc;
-}
-__global__ void k_mtiles(int n_tiles, int B, const int32_t *__restrict__ row0, const int32_t *__restrict__ mtile0,
-                         const uint32_t *__restrict__ row_off, int2 *__restrict__ tiles)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_tiles) return;
-    int lo = 0, hi = B - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (mtile0[mid] <= g) lo = mid; else hi = mid - 1; }
-    const int b = lo, r0 = row0[b], r1 = row0[b + 1];
-    const unsigned long long base = mcost(row_off, r0) + (unsigned long long)(g - mtile0[b]) * M_WINDOW;
-    int2 out;
-#pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const unsigned long long target = base + (unsigned long long)side * M_WINDOW;
-        int l = r0, h = r1;             // first p in [r0, r1] with cost(p) >= target
-        while (l < h) { int mid = (l + h) >> 1; if (mcost(row_off, mid) >= target) h = mid; else l = mid + 1; }
-        if (side == 0) out.x = l; else out.y = l;
-    }
-    tiles[g] = out;
 }
 
 __global__ void k_fill_double(double *p, int64_t n, double v)
@@ -471,15 +517,15 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     // ---- scratch carve-up ----
     const int B = ctx->prop.multiProcessorCount * ctx->em_blocks_per_sm;
-    const int cap = ctx->em_smem_bytes / 8;
     const int n_cells = B * (n_kseg > 0 ? n_kseg : 1);
-    size_t cub_bytes = 0, b1 = 0, b2 = 0, b3 = 0;
+    size_t cub_bytes = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
     const int scan_max = (int)std::max<int64_t>(std::max<int64_t>(nm + 1, (int64_t)T + 1), (int64_t)n_cells + 1);
     cub::DeviceScan::ExclusiveSum(nullptr, b1, (int32_t *)nullptr, (int32_t *)nullptr, scan_max);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, scan_max);
     cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t *)nullptr, (int32_t *)nullptr, scan_max);
-    cub_bytes = std::max(b1, std::max(b2, b3));
-    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 28 + (size_t)(n_cells + 1) * 28 + 64 * 256;
+    cub::DeviceRadixSort::SortPairs(nullptr, b4, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, T + 1, 0, 44);
+    cub_bytes = std::max(std::max(b1, b2), std::max(b3, b4));
+    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 64 + (size_t)(2 * (size_t)T + B + 64) * 8 + (size_t)(n_cells + 1) * 28 + 64 * 256;
     void *scr = nullptr;
     TRY(ctx_scratch(ctx, need, &scr));
     char *cur = (char *)scr;
@@ -489,11 +535,18 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     int32_t *d_newid2 = arena_take<int32_t>(cur, (size_t)nm + 1);
     int32_t *d_cellof = arena_take<int32_t>(cur, (size_t)nm + 1);
     uint32_t *d_rflag = arena_take<uint32_t>(cur, (size_t)T + 1);
+    uint32_t *d_nat = arena_take<uint32_t>(cur, (size_t)T + 1);
     int32_t *d_deg = arena_take<int32_t>(cur, (size_t)T + 1);
+    uint32_t *d_degn = arena_take<uint32_t>(cur, (size_t)T + 1);
     uint32_t *d_degp = arena_take<uint32_t>(cur, (size_t)T + 1);
+    int32_t *d_tn = arena_take<int32_t>(cur, (size_t)T + 1);
     int32_t *d_ecost = arena_take<int32_t>(cur, (size_t)T + 1);
     uint32_t *d_cost = arena_take<uint32_t>(cur, (size_t)T + 1);
     uint32_t *d_costp = arena_take<uint32_t>(cur, (size_t)T + 1);
+    unsigned long long *d_key = arena_take<unsigned long long>(cur, (size_t)T + 1);
+    unsigned long long *d_key2 = arena_take<unsigned long long>(cur, (size_t)T + 1);
+    int32_t *d_val = arena_take<int32_t>(cur, (size_t)T + 1);
+    int32_t *d_perm = arena_take<int32_t>(cur, (size_t)T + 1);
     int32_t *d_cell_cnt = arena_take<int32_t>(cur, (size_t)n_cells + 1);
     int32_t *d_cell_first = arena_take<int32_t>(cur, (size_t)n_cells + 1);
     uint32_t *d_cell_ints = arena_take<uint32_t>(cur, (size_t)n_cells + 1);
@@ -501,6 +554,9 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     int32_t *d_clsbase = arena_take<int32_t>(cur, (size_t)n_cells + 1);
     uint32_t *d_intbase = arena_take<uint32_t>(cur, (size_t)n_cells + 1);
     int32_t *d_tilebase = arena_take<int32_t>(cur, (size_t)n_cells + 1);
+    int32_t *d_nlong = arena_take<int32_t>(cur, (size_t)B + 1);
+    uint32_t *d_isize = arena_take<uint32_t>(cur, 2 * (size_t)T + B + 64);
+    uint32_t *d_ioff = arena_take<uint32_t>(cur, 2 * (size_t)T + B + 64);
     int32_t *d_pos = s->d_pos;   // t -> row (kept for finalize)
     // ---- class model + active scan ----
     const double nscale = (double)N / 1E6;
@@ -509,17 +565,18 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_act, d_newid, (int)(nm + 1), st));
     LAUNCHED(ctx);
-    // ---- row statistics and the natural-order row numbering ----
+    // ---- row statistics and the natural-order numbering of the participating rows ----
     k_row_stats<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, ix->d_txm_off, ix->d_txm_cid, s->d_adj, s->d_amodel, d_act, d_in_model,
                                                                           s->d_R, s->d_iE, s->d_A, s->d_Rs, d_deg, s->d_lone, d_rflag);
     LAUNCHED(ctx);
-    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_rflag, (uint32_t *)d_pos, T + 1, st));
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_rflag, d_nat, T + 1, st));
     LAUNCHED(ctx);
     CU(cudaGetLastError());
-    int32_t P = 0, C_a32 = 0;
-    CU(cudaMemcpyAsync(&P, d_pos + T, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t P32 = 0; int32_t C_a32 = 0;
+    CU(cudaMemcpyAsync(&P32, d_nat + T, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&C_a32, d_newid + nm, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    const int32_t P = (int32_t)P32;
     const int64_t C_a = C_a32;
     // ---- state: theta | q in one allocation ----
     size_t theta_bytes = (((size_t)(P > 0 ? P : 1) * 8 + 255) / 256) * 256;
@@ -534,56 +591,56 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     EmModel &m = s->m;
     memset(&m, 0, sizeof(m));
-    m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.cap = cap;
+    m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.smem_bytes = ctx->em_smem_bytes;
     m.theta = s->d_state;
     m.q = (double *)((char *)s->d_state + theta_bytes);
-    // ---- packed arena: upper bounds that do not need another host round trip ----
+    // ---- arena part 1: everything whose size is known now ----
     const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)32 * KT * (size_t)KT * (size_t)B + 64;   // tile padding: <= 31*k per (CTA, k<=KT) cell
     const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
-    const size_t m_tiles_max = ((size_t)ix->nnz_multi + (size_t)M_ROW_COST * (size_t)(P + 1)) / M_WINDOW + (size_t)B + 2;
-    size_t arena_bytes = 0;
-    {
-        auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
-        arena_bytes += rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16);
-        arena_bytes += rnd(((size_t)ix->nnz_multi + 1) * 4) + rnd((size_t)(P + 1) * 4) + rnd((size_t)(P + 1) * 16) + rnd(m_tiles_max * 8);
-        arena_bytes += 5 * rnd((size_t)(B + 1) * 4);
-    }
-    if (arena_bytes > s->pack_bytes) {
+    const size_t m_items_max = (size_t)P / 32 + 2 * (size_t)B + std::min<size_t>((size_t)P, (size_t)ix->nnz_multi / M_LONG + 1) + 64;   // slices + long rows
+    auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
+    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd(m_items_max * 16) + 6 * rnd((size_t)(B + 1) * 4);
+    if (arena1 > s->pack_bytes) {
         if (s->d_pack) CU(cudaFree(s->d_pack));
         s->d_pack = nullptr;
         char *p = nullptr;
-        TRY(dev_alloc(&p, arena_bytes));
+        TRY(dev_alloc(&p, arena1));
         s->d_pack = p;
-        s->pack_bytes = arena_bytes;
+        s->pack_bytes = arena1;
     }
     char *ac = (char *)s->d_pack;
     m.e_tid = arena_take<int32_t>(ac, e_ints_max);
     m.e_R = arena_take<uint32_t>(ac, (size_t)C_a + 1);
     m.e_tiles = arena_take<int4>(ac, e_tiles_max);
-    m.m_cls = arena_take<int32_t>(ac, (size_t)ix->nnz_multi + 1);
-    m.row_off = arena_take<uint32_t>(ac, (size_t)P + 1);
     m.row_RsA = arena_take<double2>(ac, (size_t)P + 1);
-    m.m_tiles = arena_take<int2>(ac, m_tiles_max);
+    m.m_items = arena_take<int4>(ac, m_items_max);
     m.blk_row0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_cls0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_etile0 = arena_take<int32_t>(ac, (size_t)B + 1);
-    m.blk_mtile0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_mitem0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_nres = arena_take<int32_t>(ac, (size_t)B + 1);
-    m.smem_bytes = ctx->em_smem_bytes;
-    // ---- rows: degrees, costs, ownership ranges ----
-    k_row_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_pos, d_deg, s->d_Rs, s->d_A, d_degp, m.row_RsA, d_ecost, P);
-    LAUNCHED(ctx);
-    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_degp, m.row_off, P + 1, st));
+    // ---- rows: costs, ownership ranges, length-sorted order inside each CTA ----
+    k_nat_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_nat, d_deg, d_pos, d_degn, d_tn, d_ecost, P);
     LAUNCHED(ctx);
     if (nm > 0) {
-        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_pos, d_ecost);
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_nat, d_ecost);
         LAUNCHED(ctx);
     }
-    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degp, d_ecost, d_cost);
+    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost);
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cost, d_costp, P + 1, st));
     LAUNCHED(ctx);
     k_block_bounds<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, P, d_costp, m.blk_row0);
+    LAUNCHED(ctx);
+    if (P > 0) {
+        k_sort_keys<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, B, m.blk_row0, d_degn, d_key, d_val);
+        LAUNCHED(ctx);
+        CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_key, d_key2, d_val, d_perm, P, 0, 44, st));
+        ctx->launches += 4;
+        k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA);
+        LAUNCHED(ctx);
+    }
+    k_block_items<<<1, 32, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, m.blk_mitem0);
     LAUNCHED(ctx);
     // ---- classes: (owner CTA, cardinality) cells ----
     CU(cudaMemsetAsync(d_cell_cnt, 0, (size_t)(n_cells + 1) * 4, st));
@@ -602,9 +659,39 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     ctx->launches += 3;
     k_block_tables<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_kseg > 0 ? n_kseg : 1, d_clsbase, d_tilebase, m.blk_cls0, m.blk_etile0);
     LAUNCHED(ctx);
-    k_mtile_counts<<<1, 32, 0, st>>>(B, m.blk_row0, m.row_off, m.blk_mtile0);
+    k_block_nres<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, ctx->em_smem_bytes, m.blk_row0, m.blk_cls0, m.blk_etile0, m.blk_mitem0, m.blk_nres);
     LAUNCHED(ctx);
-    k_block_nres<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, ctx->em_smem_bytes, m.blk_row0, m.blk_cls0, m.blk_etile0, m.blk_mtile0, m.blk_nres);
+    CU(cudaGetLastError());
+    uint32_t e_ints = 0;
+    int32_t n_etiles = 0, n_mitems = 0;
+    CU(cudaMemcpyAsync(&e_ints, d_intbase + n_cells, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&n_etiles, d_tilebase + n_cells, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&n_mitems, m.blk_mitem0 + B, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((size_t)e_ints > e_ints_max || (size_t)n_etiles > e_tiles_max || (size_t)n_mitems > m_items_max) {
+        emsar_set_err("internal: packed model exceeds its bounds (%u ints, %d tiles, %d items)", e_ints, n_etiles, n_mitems);
+        return EMSAR_ERR_STATE;
+    }
+    // ---- M items: sizes -> offsets ----
+    if ((size_t)n_mitems + 1 > 2 * (size_t)T + B + 64) { emsar_set_err("internal: item scratch too small"); return EMSAR_ERR_STATE; }
+    k_item_sizes<<<(unsigned)((n_mitems + 1 + 255) / 256), 256, 0, st>>>(n_mitems, B, m.blk_row0, d_nlong, m.blk_mitem0, d_degp, d_isize, m.m_items);
+    LAUNCHED(ctx);
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_isize, d_ioff, n_mitems + 1, st));
+    LAUNCHED(ctx);
+    uint32_t m_ints = 0;
+    CU(cudaMemcpyAsync(&m_ints, d_ioff + n_mitems, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((size_t)(m_ints + 1) * 4 > s->mcls_bytes) {
+        if (s->d_mcls) CU(cudaFree(s->d_mcls));
+        s->d_mcls = nullptr;
+        int32_t *p = nullptr;
+        TRY(dev_alloc(&p, (size_t)m_ints + (m_ints >> 3) + 64));
+        s->d_mcls = p;
+        s->mcls_bytes = ((size_t)m_ints + (m_ints >> 3) + 64) * 4;
+    }
+    m.m_cls = s->d_mcls;
+    m.n_etiles = n_etiles; m.n_mitems = n_mitems; m.m_ints = m_ints;
+    k_item_finish<<<(unsigned)((n_mitems + 255) / 256 + 1), 256, 0, st>>>(n_mitems, B, m.blk_mitem0, m.blk_nres, d_ioff, m.m_items, m.m_cls);
     LAUNCHED(ctx);
     CU(cudaMemsetAsync(m.e_tid, 0, e_ints_max * 4, st));
     if (nm > 0 && n_kseg > 0) {
@@ -614,34 +701,24 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         LAUNCHED(ctx);
     }
     k_scatter_rows<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, B, m.blk_nres, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid2, d_pos, m.blk_row0,
-                                                                             m.blk_cls0, m.row_off, m.m_cls);
+                                                                             m.blk_cls0, d_nlong, m.blk_mitem0, m.m_items, m.m_cls);
     LAUNCHED(ctx);
-    CU(cudaGetLastError());
-    uint32_t nnz_a = 0, e_ints = 0;
-    int32_t n_etiles = 0, n_mtiles = 0;
-    CU(cudaMemcpyAsync(&nnz_a, m.row_off + P, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&e_ints, d_intbase + n_cells, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&n_etiles, d_tilebase + n_cells, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&n_mtiles, m.blk_mtile0 + B, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if ((size_t)e_ints > e_ints_max || (size_t)n_etiles > e_tiles_max || (size_t)n_mtiles > m_tiles_max) {
-        emsar_set_err("internal: packed model exceeds its bounds (%u ints, %d/%d tiles)", e_ints, n_etiles, n_mtiles);
-        return EMSAR_ERR_STATE;
-    }
-    m.nnz_a = nnz_a; m.n_etiles = n_etiles; m.n_mtiles = n_mtiles;
     if (n_etiles > 0) {
         k_etiles<<<(unsigned)((n_etiles + 255) / 256), 256, 0, st>>>(n_etiles, n_cells, n_kseg, ix->d_kseg_k, d_tilebase, d_clsbase, d_cell_cnt, d_intbase, m.e_tiles);
-        LAUNCHED(ctx);
-    }
-    if (n_mtiles > 0) {
-        k_mtiles<<<(unsigned)((n_mtiles + 255) / 256), 256, 0, st>>>(n_mtiles, B, m.blk_row0, m.blk_mtile0, m.row_off, m.m_tiles);
         LAUNCHED(ctx);
     }
     // start point: theta = 1 for every row that takes part (A_t > 0)
     if (P > 0) { k_fill_double<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(m.theta, P, 1.0); LAUNCHED(ctx); }
     CU(cudaGetLastError());
+    uint32_t nnz_a = 0;
+    {   // nnz_a = sum of the active row lengths
+        CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_degn, d_cost, P + 1, st));
+        LAUNCHED(ctx);
+        CU(cudaMemcpyAsync(&nnz_a, d_cost + P, 4, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaEventRecord(e1, st));
     CU(cudaStreamSynchronize(st));
+    m.nnz_a = nnz_a;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     s->prep_ms = ms;
@@ -649,11 +726,11 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     memset(&ms_, 0, sizeof(ms_));
     ms_.T = T; ms_.C_a = C_a; ms_.nnz_a = m.nnz_a;
     ms_.rows_short = P; ms_.rows_long = 0; ms_.rows_hub = 0; ms_.rows_fixed = T - P;
-    ms_.e_tiles = n_etiles; ms_.m_tiles = n_mtiles;
+    ms_.e_tiles = n_etiles; ms_.m_tiles = n_mitems;
     ms_.bytes_per_iter = 8 * m.nnz_a + 24 * C_a + 44 * (int64_t)T;
-    // what the kernel streams per iteration: E: encoded members (padded) + R + tiles (+ q to global for halo classes);
-    // M: encoded classes + row_off + {Rs,A} + theta write-through + tiles
-    ms_.stream_bytes_per_iter = 4 * (int64_t)e_ints + 4 * C_a + 16 * (int64_t)n_etiles + 4 * m.nnz_a + 4 * (int64_t)P + 16 * (int64_t)P + 8 * (int64_t)P + 8 * (int64_t)n_mtiles;
+    // what the kernel streams per iteration: E: encoded members (padded) + R (+ q to global for halo classes);
+    // M: encoded classes (padded) + {Rs,A} + theta write-through; tile descriptors live in shared memory
+    ms_.stream_bytes_per_iter = 4 * (int64_t)e_ints + 4 * C_a + 4 * (int64_t)m_ints + 16 * (int64_t)P + 8 * (int64_t)P;
     s->prepared = true;
     s->n_iter = 0; s->final_delta = INFINITY; s->em_ms = 0;
     return EMSAR_OK;
