@@ -55,8 +55,10 @@ extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
-    CU(cudaMalloc(&ctx->d_barrier, 64));
-    CU(cudaMemset(ctx->d_barrier, 0, 64));
+    // [0..63] scalars of the EM kernel (delta slots, iteration count), then one 128-byte barrier line per CTA
+    const size_t bar_bytes = 256 + (size_t)ctx->prop.multiProcessorCount * 4 * 128;
+    CU(cudaMalloc(&ctx->d_barrier, bar_bytes));
+    CU(cudaMemset(ctx->d_barrier, 0, bar_bytes));
     // L2 persistence carve-out for theta|q (north star: keep the theta vector L2-resident)
     size_t want = (size_t)ctx->prop.persistingL2CacheMaxSize;
     if (want > (size_t)64 << 20) want = (size_t)64 << 20;

@@ -38,7 +38,12 @@ void emsar_set_err(const char *fmt, ...);
 constexpr int EM_WARPS = EM_BLOCK / 32;
 constexpr int KT = 32;            // classes with cardinality <= KT: one thread per class, members stored transposed in tiles of 32 classes
 constexpr int E_TILE_TARGET = 256; // larger classes: one warp per class, about this many members per tile
-constexpr int M_LONG = 256;       // transposed rows with more active entries: one warp per row; the rest go into SELL-32 slices
+constexpr int M_LONG = 64;        // transposed rows with more active entries: one warp per row; the rest go into SELL-32 slices
+constexpr int M_GROUP_ENTRIES = 768;  // a group of long rows (<= M_GROUP_ROWS rows, one warp) holds at most this many entries unless a single row is longer
+constexpr int M_GROUP_ROWS = 8;
+constexpr int CH_INTS = 4096;     // ints per staged chunk of an index stream (indices + read counts): 16 KB per pipeline stage
+constexpr int CH_BYTES = CH_INTS * 4 + 64;
+constexpr int NSTAGE = 4;         // stages of the TMA pipeline (producer warp -> consumer warps)
 
 struct KSeg {          // multi-tid classes of one cardinality, contiguous in cid order
     int32_t k;
@@ -101,7 +106,14 @@ struct EmModel {
     int32_t *blk_cls0;     // [B+1] first (compact) class of each CTA
     int32_t *blk_etile0;   // [B+1]
     int32_t *blk_mitem0;   // [B+1]
+    int32_t *blk_ech0, *blk_mch0;  // [B+1] chunk ranges
+    int4 *e_chunks, *m_chunks;     // {first item, end item, stream offset (ints), ints}; ints < 0: not staged (oversized item)
     int32_t *blk_nres;     // [B]   classes of the CTA whose q lives in shared memory (slot nres holds 0.0: padding target)
+    // halo: distinct remote rows / classes a CTA references; copied into its shared memory at the start of each phase
+    int32_t *blk_hr0, *blk_hc0;   // [B+1] ranges in halo_rows / halo_cls
+    int32_t *blk_nhr, *blk_nhc;   // [B]   how many of them got a shared-memory slot (the rest falls back to global loads)
+    int32_t *halo_rows;    // global row of each halo slot
+    int32_t *halo_cls;     // global compact class of each halo slot
     int32_t smem_bytes;    // dynamic shared memory per CTA
     // E side
     int32_t *e_tid;        // encoded member rows (tile-transposed for k<=KT, row-major otherwise)
@@ -110,7 +122,8 @@ struct EmModel {
     int32_t n_etiles;
     // M side
     int32_t *m_cls;        // encoded classes: slices transposed + padded, long rows row-major
-    int4 *m_items;         // {first row slot, rows, entry offset, length | mode<<30}: mode 0 = slice, 1 = long row
+    int4 *m_items;         // {first row slot, rows, entry offset, length | mode<<30}: mode 0 = slice (length = longest row),
+                           // 1 = group of long rows (length = all entries; a header of `rows` lengths precedes them)
     double2 *row_RsA;      // [P] {Rs, A}
     int32_t n_mitems;
     int64_t m_ints;        // entries stored (with padding)
@@ -150,6 +163,11 @@ struct emsar_sample {
     size_t pack_bytes;
     int32_t *d_mcls;       // M-side entries (sized after the slices are known)
     size_t mcls_bytes;
+    int32_t *d_halo;       // halo_rows | halo_cls
+    size_t halo_bytes;
+    void *d_chunks;        // chunk tables
+    size_t chunk_bytes;
+    unsigned long long *d_trace;   // tuning aid
     EmModel m;
     emsar_model_stats stats;
     // solve bookkeeping
@@ -179,19 +197,27 @@ int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
 
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__
-// Shared-memory plan of one CTA of k_em_persistent: [E tile descriptors][M items][theta of its rows]
-// [q of its first nres classes][one zero slot]
-struct SmemPlan { int off_etiles, off_mitems, off_theta, off_q; };
-__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int n_et, int n_mi, int nrows)
+// Shared-memory plan of one CTA of k_em_persistent:
+// [stage buffer 0][stage buffer 1][E tile descriptors][M items][E chunks][M chunks][halo row list][halo class list]
+// [{Rs,A} of its rows][theta: own rows | halo rows][q: resident classes | 0.0 | halo classes]
+struct SmemPlan { int off_etiles, off_mitems, off_ech, off_mch, off_hrl, off_hcl, off_rsa, off_theta, off_q, total; };
+__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int n_et, int n_mi, int n_ech, int n_mch, int nrows, int nhr, int nres, int nhc)
 {
     SmemPlan p;
-    p.off_etiles = 0;
+    p.off_etiles = NSTAGE * CH_BYTES;
     p.off_mitems = p.off_etiles + n_et * 16;
-    p.off_theta = p.off_mitems + n_mi * 16;
-    p.off_q = p.off_theta + nrows * 8;
+    p.off_ech = p.off_mitems + n_mi * 16;
+    p.off_mch = p.off_ech + n_ech * 16;
+    p.off_hrl = p.off_mch + n_mch * 16;
+    p.off_hcl = p.off_hrl + nhr * 4;
+    p.off_rsa = (p.off_hcl + nhc * 4 + 15) & ~15;
+    p.off_theta = p.off_rsa + nrows * 16;
+    p.off_q = p.off_theta + (nrows + nhr) * 8;
+    p.total = p.off_q + (nres + 1 + nhc) * 8;
     return p;
 }
-__host__ __device__ __forceinline__ int em_fixed_smem(int n_et, int n_mi, int nrows) { return em_smem_plan(n_et, n_mi, nrows).off_q + 8; }
+// chunks a CTA can need at most for a stream of `ints` ints cut greedily at CH_INTS (every two consecutive chunks hold > CH_INTS)
+__host__ __device__ __forceinline__ int em_max_chunks(long long ints, int n_items) { long long c = 2 * (ints / CH_INTS) + 2; return (int)(c < n_items + 1 ? c : n_items + 1); }
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;

@@ -21,43 +21,44 @@ struct EmParams {
     EmModel m;
     double eps_abs, eps_rel;
     int max_iter, stop_on_conv;
-    unsigned *bar;                 // [0] count, [1] generation
+    int direct;                    // 1: no staging pipeline, every warp reads its items' indices straight from L2
+    unsigned *bar;                 // one generation flag per CTA, 128 bytes apart
     unsigned long long *dmax;      // [2] alternating slots for the reduced delta (bit pattern of a double >= 0)
     int *iters_done;
     double *final_delta;
+    unsigned long long *trace;     // optional [B*8] globaltimer stamps of the last iteration (tuning aid)
 };
 
-// Sense-reversing grid barrier. All CTAs are co-resident (cooperative launch). The __threadfence() pair makes the
-// writes of the phase visible device-wide and drops stale L1 lines before the next phase gathers.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// tuning aid: globaltimer stamps of the last iteration of a launch, per CTA (see emsar_debug_em_trace)
+#define TRACE(slot) do { if (p.trace && it == p.max_iter - 1 && threadIdx.x == 0) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+
+// Grid barrier for the co-resident CTAs (cooperative launch), without atomics: every CTA publishes the barrier's
+// generation in its own 128-byte line with a release store; thread i of every CTA polls CTA i's line with acquire
+// loads. The release / acquire pairs make the phase's global writes (theta / q write-through) visible to the CTAs that
+// read them as halo. Latency: one store + one poll round trip after the last arrival.
+__device__ __forceinline__ void grid_barrier(unsigned *flags, unsigned nblocks, unsigned gen)
 {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned *gen = bar + 1;
-        const unsigned g = *gen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == nblocks - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g) { }
-        }
-        __threadfence();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(flags + blockIdx.x * 32), "r"(gen) : "memory");
+    for (unsigned i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        unsigned cur;
+        do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(flags + i * 32) : "memory"); } while ((int)(cur - gen) < 0);
     }
     __syncthreads();
 }
 
 // ---- shared-memory resident slices ---------------------------------------------------------------------
 struct BlockView {
-    double *sm_theta;          // theta of the rows this CTA owns
-    double *sm_q;              // q of the resident classes this CTA owns; sm_q[nres] == 0 (padding target)
+    double *sm_theta;          // theta of the rows this CTA owns, then its halo rows
+    double *sm_q;              // q of the resident classes this CTA owns; sm_q[nres] == 0 (padding target); then halo classes
+    const double2 *sm_rsa;     // {Rs, A} of the rows this CTA owns
     const int4 *sm_etiles;     // this CTA's E tile descriptors
     const int4 *sm_mitems;     // this CTA's M items
-    int row0, nrows, cls0, nres;
+    int row0, nrows, cls0, nres, nhr, nhc;
 };
 
-// branch-free: one generic load from either the CTA's shared slice or the global (halo) copy
+// branch-free: one generic load from either the CTA's shared slice or the global copy (overflow only)
 __device__ __forceinline__ double load_theta(const EmParams &p, const BlockView &v, int enc)
 {
     const double *ptr = enc >= 0 ? v.sm_theta + enc : p.m.theta + ~enc;
@@ -77,46 +78,132 @@ __device__ __forceinline__ void store_q(const EmParams &p, const BlockView &v, i
     if (rflag & 0x80000000u) p.m.q[j] = val;        // a row of another CTA reads it, or it does not fit in shared memory
 }
 
-// ---- E-phase: q_c = R_c / sum of theta over the class members --------------------------------------------------
-__device__ __forceinline__ void e_phase(const EmParams &p, const BlockView &v, int n_tiles, int warp, int lane)
+// ---- chunk staging: a contiguous piece of an int32 stream -> shared memory with one TMA bulk copy (cp.async.bulk), -----
+// completion signalled on an mbarrier. [g, g+n) is fetched from its 16-byte-aligned floor; element i then sits at
+// buf[shift + i]. Geometry (shift, bytes) is computed by every thread; only thread 0 issues the copy.
+__device__ __forceinline__ int stage_shift(const void *g) { return (int)(((uintptr_t)g & 15) >> 2); }
+__device__ __forceinline__ uint32_t stage_bytes(const void *g, int n) { return (uint32_t)((n + stage_shift(g) + 3) >> 2) * 16u; }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 {
-    // tiles are ordered by cardinality: walk them from the heaviest so that the tail of the phase is made of light tiles
-    for (int g = n_tiles - 1 - warp; g >= 0; g -= EM_WARPS) {
-        const int4 tile = v.sm_etiles[g];
-        const int k = tile.w & 0xffff, mode = tile.w >> 16;
-        if (mode == 0) {
-            // one thread per class; member j of the 32 classes of the tile is one coalesced 128-byte line
-            const int32_t *__restrict__ tids = p.m.e_tid + (uint32_t)tile.z + lane;
-            uint32_t rf = 0;
-            if (lane < tile.y) rf = __ldg(p.m.e_R + tile.x + lane);
-            double s = 0;
-            int j = 0;
-            for (; j + 4 <= k; j += 4) {
-                const int t0 = __ldg(tids + j * 32), t1 = __ldg(tids + j * 32 + 32), t2 = __ldg(tids + j * 32 + 64), t3 = __ldg(tids + j * 32 + 96);
-                const double x0 = load_theta(p, v, t0), x1 = load_theta(p, v, t1), x2 = load_theta(p, v, t2), x3 = load_theta(p, v, t3);
-                s += x0; s += x1; s += x2; s += x3;          // sequential member order
-            }
-            for (; j < k; j++) s += load_theta(p, v, __ldg(tids + j * 32));
-            if (lane < tile.y) store_q(p, v, tile.x + lane, rf, s);
-        } else {
-            // long classes: one warp per class, members row-major
-            for (int cl = 0; cl < tile.y; cl++) {
-                const int32_t *__restrict__ tids = p.m.e_tid + (uint32_t)tile.z + (uint32_t)cl * (uint32_t)k;
-                double s = 0;
-#pragma unroll 4
-                for (int i = lane; i < k; i += 32) s += load_theta(p, v, __ldg(tids + i));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *g, uint32_t bytes, unsigned long long *bar)
+{
+    const uintptr_t ga = (uintptr_t)g & ~(uintptr_t)15;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(ga), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+// one chunk copy split into EM_WARPS pieces, each issued by lane 0 of a different warp (TMA issue is slow per thread)
+__device__ __forceinline__ void bulk_g2s_split(void *dst, const void *g, uint32_t bytes, unsigned long long *bar, int warp, int lane)
+{
+    (void)warp;
+    if (lane >= 1) return;                        // one bulk copy per stream piece: issuing costs ~55 ns each, so do not split
+    const uint32_t piece = bytes;
+    const uint32_t o = 0;
+    if (o >= bytes) return;
+    const uint32_t n = min(piece, bytes - o);
+    const uintptr_t ga = ((uintptr_t)g & ~(uintptr_t)15) + o;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst) + o), "l"(ga), "r"(n),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra LAB_DONE;\nbra LAB_WAIT;\nLAB_DONE:\n}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"((EM_WARPS - 1) * 32) : "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// work queue of one chunk: items sorted by decreasing cost, warps take the next one (results do not depend on who computes)
+__device__ __forceinline__ int next_item(int *counter, int lane)
+{
+    int t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+
+// ---- E-phase: q_c = R_c / sum of theta over the class members --------------------------------------------------
+// tids / rfl point at the tile's member indices / read counts (shared memory when staged, global otherwise)
+template <int K, int G>
+__device__ __forceinline__ void etile_small(const EmParams &p, const BlockView &v, int4 tile, const int *tids, const uint32_t *rfl, int lane)
+{
+    int t[K * G];
+    uint32_t rf[G];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-                if (lane == 0) store_q(p, v, tile.x + cl, __ldg(p.m.e_R + tile.x + cl), s);
-            }
+    for (int u = 0; u < K * G; u++) t[u] = (u / K) * 32 < tile.y ? tids[u * 32 + lane] : 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) rf[g] = (g * 32 + lane < tile.y) ? rfl[g * 32 + lane] : 0u;
+    double x[K * G];
+#pragma unroll
+    for (int u = 0; u < K * G; u++) x[u] = load_theta(p, v, t[u]);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) s += x[g * K + j];       // sequential member order
+        if (g * 32 + lane < tile.y) store_q(p, v, tile.x + g * 32 + lane, rf[g], s);
+    }
+}
+
+__device__ __forceinline__ void e_tile(const EmParams &p, const BlockView &v, int4 tile, const int *tids, const uint32_t *rfl, int lane)
+{
+    const int k = tile.w & 0xffff, mode = tile.w >> 16;
+    if (mode == 0) {
+        if (k == 2) { etile_small<2, 4>(p, v, tile, tids, rfl, lane); return; }
+        if (k == 3) { etile_small<3, 2>(p, v, tile, tids, rfl, lane); return; }
+        if (k == 4) { etile_small<4, 2>(p, v, tile, tids, rfl, lane); return; }
+        // one thread per class; member j of the 32 classes of the tile is one 128-byte line
+        uint32_t rf = 0;
+        if (lane < tile.y) rf = rfl[lane];
+        tids += lane;
+        double s = 0;
+        int j = 0;
+        for (; j + 4 <= k; j += 4) {
+            int t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = tids[(j + u) * 32];
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = load_theta(p, v, t[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) s += x[u];       // sequential member order
         }
+        for (; j < k; j++) s += load_theta(p, v, tids[j * 32]);
+        if (lane < tile.y) store_q(p, v, tile.x + lane, rf, s);
+    } else {
+        // long classes: one warp per class, members row-major; lane cl keeps the sum of class cl, then all classes of the
+        // tile are finished together (one division per lane instead of a serial chain per class)
+        double mine = 0;
+        for (int cl = 0; cl < tile.y; cl++) {
+            const int *m = tids + cl * k;
+            double s = 0;
+#pragma unroll 4
+            for (int i = lane; i < k; i += 32) s += load_theta(p, v, m[i]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == cl) mine = s;
+        }
+        if (lane < tile.y) store_q(p, v, tile.x + lane, rfl[lane], mine);
     }
 }
 
 // ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
 __device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v, int slot, double Q)
 {
-    const double2 ra = p.m.row_RsA[v.row0 + slot];
+    const double2 ra = v.sm_rsa[slot];
     const double th = v.sm_theta[slot];
     const double n = ra.x + th * Q;
     const double thn = n / ra.y;
@@ -125,37 +212,175 @@ __device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v
     return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
 }
 
-__device__ __forceinline__ double m_phase(const EmParams &p, const BlockView &v, int n_items, int warp, int lane)
+__device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, int4 it, const int *ent, int lane)
 {
-    double dmax = 0;
-    // items are ordered longest first (long rows, then slices by decreasing length)
-    for (int g = warp; g < n_items; g += EM_WARPS) {
-        const int4 it = v.sm_mitems[g];
-        const int len = it.w & 0x3fffffff;
-        if ((it.w >> 30) == 0) {
-            // a slice of 32 rows stored transposed: one thread per row, sequential sum in ascending class order
-            const int32_t *__restrict__ ent = p.m.m_cls + (uint32_t)it.z + lane;
-            double Q = 0;
-            int j = 0;
-            for (; j + 4 <= len; j += 4) {
-                const int c0 = __ldg(ent + j * 32), c1 = __ldg(ent + j * 32 + 32), c2 = __ldg(ent + j * 32 + 64), c3 = __ldg(ent + j * 32 + 96);
-                const double x0 = load_q(p, v, c0), x1 = load_q(p, v, c1), x2 = load_q(p, v, c2), x3 = load_q(p, v, c3);
-                Q += x0; Q += x1; Q += x2; Q += x3;
-            }
-            for (; j < len; j++) Q += load_q(p, v, __ldg(ent + j * 32));
-            if (lane < it.y) dmax = fmax(dmax, m_update(p, v, it.x + lane, Q));
-        } else {
-            // a long row: the whole warp, fixed shuffle tree
-            const int32_t *__restrict__ ent = p.m.m_cls + (uint32_t)it.z;
+    const int len = it.w & 0x3fffffff;
+    double d = 0;
+    if ((it.w >> 30) == 0) {
+        // a slice of 32 rows stored transposed: one thread per row, sequential sum in ascending class order
+        ent += lane;
+        double Q = 0;
+        int j = 0;
+        for (; j + 4 <= len; j += 4) {
+            int c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) c[u] = ent[(j + u) * 32];
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = load_q(p, v, c[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) Q += x[u];       // ascending class order
+        }
+        for (; j < len; j++) Q += load_q(p, v, ent[j * 32]);
+        if (lane < it.y) d = m_update(p, v, it.x + lane, Q);
+    } else {
+        // a group of long rows: header = the rows' lengths, then their entries; the warp reduces one row at a time with a
+        // fixed shuffle tree, lane r keeps row r's sum, then all rows are updated together
+        const int n = it.y;
+        const int mylen = lane < n ? ent[lane] : 0;
+        int start = mylen;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
+        start += n - mylen;                          // exclusive prefix, after the header
+        double mine = 0;
+        for (int r = 0; r < n; r++) {
+            const int a = __shfl_sync(0xffffffffu, start, r), L = __shfl_sync(0xffffffffu, mylen, r);
             double s = 0;
 #pragma unroll 4
-            for (int e = lane; e < len; e += 32) s += load_q(p, v, __ldg(ent + e));
+            for (int e = lane; e < L; e += 32) s += load_q(p, v, ent[a + e]);
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
+            if (lane == r) mine = s;
+        }
+        if (lane < n) d = m_update(p, v, it.x + lane, mine);
+    }
+    return d;
+}
+
+// ---- fast path: the chunk is staged and every index of this CTA is a shared-memory slot. All addresses are 32-bit
+// offsets from the CTA's dynamic shared memory, so the loops are LDS + LDS.64 + DADD with almost no address arithmetic.
+struct SmView {
+    unsigned char *base;   // sm_dyn
+    int theta8, q8, rsa16; // element offsets of theta / q / {Rs,A} inside sm_dyn
+    int row0, cls0, nres;
+};
+#define S32(v) ((const int *)(v).base)
+#define S64(v) ((double *)(v).base)
+// where an item's int32 indices come from: the staged chunk in shared memory, or straight from global memory (L2)
+struct IdxS { const unsigned char *base; __device__ __forceinline__ int operator()(int i) const { return ((const int *)base)[i]; } };
+struct IdxG { const int32_t *g; __device__ __forceinline__ int operator()(int i) const { return __ldg(g + i); } };
+
+__device__ __forceinline__ void f_store_q(const EmParams &p, const SmView &v, int j, uint32_t rflag, double s)
+{
+    const double r = (double)(rflag & 0x7fffffffu);
+    const double val = s > 0 ? r / s : 0.0;
+    S64(v)[v.q8 + (j - v.cls0)] = val;              // fast path: every owned class is resident
+    if (rflag & 0x80000000u) p.m.q[j] = val;        // a row of another CTA reads it
+}
+
+template <int K, int G, class IT, class IR>
+__device__ __forceinline__ void f_etile_small(const EmParams &p, const SmView &v, int4 tile, IT T_, IR R_, int ti, int ri, int lane)
+{
+    int t[K * G];
+    uint32_t rf[G];
+#pragma unroll
+    for (int u = 0; u < K * G; u++) t[u] = (u / K) * 32 < tile.y ? T_(ti + u * 32 + lane) : 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) rf[g] = (g * 32 + lane < tile.y) ? (uint32_t)R_(ri + g * 32 + lane) : 0u;
+    double x[K * G];
+#pragma unroll
+    for (int u = 0; u < K * G; u++) x[u] = S64(v)[v.theta8 + t[u]];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) s += x[g * K + j];       // sequential member order
+        if (g * 32 + lane < tile.y) f_store_q(p, v, tile.x + g * 32 + lane, rf[g], s);
+    }
+}
+
+template <class IT, class IR>
+__device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int4 tile, IT T_, IR R_, int ti, int ri, int lane)
+{
+    const int k = tile.w & 0xffff, mode = tile.w >> 16;
+    if (mode == 0) {
+        if (k == 2) { f_etile_small<2, 4>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (k == 3) { f_etile_small<3, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (k == 4) { f_etile_small<4, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        uint32_t rf = 0;
+        if (lane < tile.y) rf = (uint32_t)R_(ri + lane);
+        ti += lane;
+        double s = 0;
+        int j = 0;
+        for (; j + 4 <= k; j += 4) {
+            const int t0 = T_(ti + j * 32), t1 = T_(ti + j * 32 + 32), t2 = T_(ti + j * 32 + 64), t3 = T_(ti + j * 32 + 96);
+            const double x0 = S64(v)[v.theta8 + t0], x1 = S64(v)[v.theta8 + t1], x2 = S64(v)[v.theta8 + t2], x3 = S64(v)[v.theta8 + t3];
+            s += x0; s += x1; s += x2; s += x3;          // sequential member order
+        }
+        for (; j < k; j++) s += S64(v)[v.theta8 + T_(ti + j * 32)];
+        if (lane < tile.y) f_store_q(p, v, tile.x + lane, rf, s);
+    } else {
+        double mine = 0;
+        for (int cl = 0; cl < tile.y; cl++) {
+            const int m = ti + cl * k;
+            double s = 0;
+#pragma unroll 4
+            for (int i = lane; i < k; i += 32) s += S64(v)[v.theta8 + T_(m + i)];
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == 0) dmax = fmax(dmax, m_update(p, v, it.x, s));
+            if (lane == cl) mine = s;
         }
+        if (lane < tile.y) f_store_q(p, v, tile.x + lane, (uint32_t)R_(ri + lane), mine);
     }
-    return dmax;
+}
+
+__device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v, int slot, double Q)
+{
+    const double2 ra = ((const double2 *)v.base)[v.rsa16 + slot];
+    const double th = S64(v)[v.theta8 + slot];
+    const double n = ra.x + th * Q;
+    const double thn = n / ra.y;
+    S64(v)[v.theta8 + slot] = thn;
+    p.m.theta[v.row0 + slot] = thn;                 // write-through: halo readers and the final result
+    return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
+}
+
+template <class IT>
+__device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, int4 it, IT T_, int ei, int lane)
+{
+    const int len = it.w & 0x3fffffff;
+    double d = 0;
+    if ((it.w >> 30) == 0) {
+        ei += lane;
+        double Q = 0;
+        int j = 0;
+        for (; j + 4 <= len; j += 4) {
+            const int c0 = T_(ei + j * 32), c1 = T_(ei + j * 32 + 32), c2 = T_(ei + j * 32 + 64), c3 = T_(ei + j * 32 + 96);
+            const double x0 = S64(v)[v.q8 + c0], x1 = S64(v)[v.q8 + c1], x2 = S64(v)[v.q8 + c2], x3 = S64(v)[v.q8 + c3];
+            Q += x0; Q += x1; Q += x2; Q += x3;          // ascending class order
+        }
+        for (; j < len; j++) Q += S64(v)[v.q8 + T_(ei + j * 32)];
+        if (lane < it.y) d = f_m_update(p, v, it.x + lane, Q);
+    } else {
+        const int n = it.y;
+        const int mylen = lane < n ? T_(ei + lane) : 0;
+        int start = mylen;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
+        start += n - mylen;
+        double mine = 0;
+        for (int r = 0; r < n; r++) {
+            const int a = ei + __shfl_sync(0xffffffffu, start, r), L = __shfl_sync(0xffffffffu, mylen, r);
+            double s = 0;
+#pragma unroll 4
+            for (int e = lane; e < L; e += 32) s += S64(v)[v.q8 + T_(a + e)];
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
+            if (lane == r) mine = s;
+        }
+        if (lane < n) d = f_m_update(p, v, it.x + lane, mine);
+    }
+    return d;
 }
 
 template <int MINB>
@@ -163,31 +388,124 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
 {
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     __shared__ double sm_red[EM_WARPS];
+    __shared__ int sm_ctr[NSTAGE];     // work-queue tickets, one counter per pipeline stage
+    __shared__ __align__(8) unsigned long long sm_full[NSTAGE], sm_empty[NSTAGE];   // TMA landed / consumers done
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == EM_WARPS - 1;
     const int b = blockIdx.x;
     const int et0 = p.m.blk_etile0[b], n_et = p.m.blk_etile0[b + 1] - et0;
     const int mi0 = p.m.blk_mitem0[b], n_mi = p.m.blk_mitem0[b + 1] - mi0;
+    const int ec0 = p.m.blk_ech0[b], n_ech = p.m.blk_ech0[b + 1] - ec0;
+    const int mc0 = p.m.blk_mch0[b], n_mch = p.m.blk_mch0[b + 1] - mc0;
     BlockView v;
     v.row0 = p.m.blk_row0[b]; v.nrows = p.m.blk_row0[b + 1] - v.row0;
     v.cls0 = p.m.blk_cls0[b]; v.nres = p.m.blk_nres[b];
-    const SmemPlan pl = em_smem_plan(n_et, n_mi, v.nrows);
+    v.nhr = p.m.blk_nhr[b]; v.nhc = p.m.blk_nhc[b];
+    const int hr0 = p.m.blk_hr0[b], hc0 = p.m.blk_hc0[b];
+    const SmemPlan pl = em_smem_plan(n_et, n_mi, n_ech, n_mch, v.nrows, v.nhr, v.nres, v.nhc);
     int4 *s_et = (int4 *)(sm_dyn + pl.off_etiles);
     int4 *s_mi = (int4 *)(sm_dyn + pl.off_mitems);
+    int4 *s_ech = (int4 *)(sm_dyn + pl.off_ech);
+    int4 *s_mch = (int4 *)(sm_dyn + pl.off_mch);
+    int32_t *s_hrl = (int32_t *)(sm_dyn + pl.off_hrl);
+    int32_t *s_hcl = (int32_t *)(sm_dyn + pl.off_hcl);
+    double2 *s_rsa = (double2 *)(sm_dyn + pl.off_rsa);
     v.sm_theta = (double *)(sm_dyn + pl.off_theta);
     v.sm_q = (double *)(sm_dyn + pl.off_q);
-    v.sm_etiles = s_et; v.sm_mitems = s_mi;
+    v.sm_etiles = s_et; v.sm_mitems = s_mi; v.sm_rsa = s_rsa;
+    SmView f;
+    f.base = sm_dyn; f.theta8 = pl.off_theta / 8; f.q8 = pl.off_q / 8; f.rsa16 = pl.off_rsa / 16;
+    f.row0 = v.row0; f.cls0 = v.cls0; f.nres = v.nres;
+    // every index of this CTA is a shared-memory slot (the host plan gave all its halo rows / classes a slot)
+    const bool all_local = v.nhr == p.m.blk_hr0[b + 1] - hr0 && v.nhc == p.m.blk_hc0[b + 1] - hc0 && v.nres == p.m.blk_cls0[b + 1] - v.cls0;
     // per-CTA constants and the CTA's slice of theta -> shared memory, once
     for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_et[i] = p.m.e_tiles[et0 + i];
     for (int i = threadIdx.x; i < n_mi; i += EM_BLOCK) s_mi[i] = p.m.m_items[mi0 + i];
-    for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = p.m.theta[v.row0 + i];
-    for (int i = threadIdx.x; i <= v.nres; i += EM_BLOCK) v.sm_q[i] = 0.0;
+    for (int i = threadIdx.x; i < n_ech; i += EM_BLOCK) s_ech[i] = p.m.e_chunks[ec0 + i];
+    for (int i = threadIdx.x; i < n_mch; i += EM_BLOCK) s_mch[i] = p.m.m_chunks[mc0 + i];
+    for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) s_hrl[i] = p.m.halo_rows[hr0 + i];
+    for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) s_hcl[i] = p.m.halo_cls[hc0 + i];
+    for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) { s_rsa[i] = p.m.row_RsA[v.row0 + i]; v.sm_theta[i] = p.m.theta[v.row0 + i]; }
+    for (int i = threadIdx.x; i <= v.nres + v.nhc; i += EM_BLOCK) v.sm_q[i] = 0.0;
+    if (threadIdx.x == 0)
+        for (int sg = 0; sg < NSTAGE; sg++) { mbar_init(&sm_full[sg], 1); mbar_init(&sm_empty[sg], EM_WARPS - 1); }
     __syncthreads();
+    // chunk sequence number: chunk g lives in stage g % NSTAGE, its barriers are in phase (g / NSTAGE) & 1
+    int gseq = 0;            // consumers: next chunk to consume; producer: next chunk to issue
+    int m_pre = 0;           // producer: M chunks of this iteration already issued before the grid barrier
     int it = 0;
     double d = INFINITY;
-    while (it < p.max_iter) {
-        e_phase(p, v, n_et, warp, lane);
-        grid_barrier(p.bar, gridDim.x);
-        double dm = m_phase(p, v, n_mi, warp, lane);
+
+    // ---- producer: wait until the stage is free, reset its ticket counter, launch the TMA copies of one chunk ----
+    auto issue_e = [&](int ci, int g) {
+        const int sg = g % NSTAGE;
+        mbar_wait(&sm_empty[sg], ((g / NSTAGE) & 1) ^ 1);
+        const int4 c = s_ech[ci];
+        if (lane == 0) sm_ctr[sg] = 0;
+        if (c.w >= 0) {
+            const int j0 = s_et[c.x].x, j1 = s_et[c.y - 1].x + s_et[c.y - 1].y;
+            const int n_idx = c.w - (j1 - j0);
+            const int32_t *gi = p.m.e_tid + (uint32_t)c.z;
+            const uint32_t *gr = p.m.e_R + j0;
+            const int ro = (stage_shift(gi) + n_idx + 3) & ~3;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&sm_full[sg], stage_bytes(gi, n_idx) + stage_bytes(gr, j1 - j0));
+            __syncwarp();
+            bulk_g2s_split(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, n_idx), &sm_full[sg], warp, lane);
+            bulk_g2s_split((int *)(sm_dyn + sg * CH_BYTES) + ro, gr, stage_bytes(gr, j1 - j0), &sm_full[sg], warp, lane);
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm_full[sg]);       // oversized item: read straight from global
+        }
+    };
+    auto issue_m = [&](int ci, int g) {
+        const int sg = g % NSTAGE;
+        mbar_wait(&sm_empty[sg], ((g / NSTAGE) & 1) ^ 1);
+        const int4 c = s_mch[ci];
+        if (lane == 0) sm_ctr[sg] = 0;
+        __syncwarp();
+        if (c.w >= 0) {
+            const int32_t *gi = p.m.m_cls + (uint32_t)c.z;
+            if (lane == 0) mbar_expect_tx(&sm_full[sg], stage_bytes(gi, c.w));
+            __syncwarp();
+            bulk_g2s_split(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, c.w), &sm_full[sg], warp, lane);
+        } else if (lane == 0) mbar_arrive(&sm_full[sg]);
+    };
+
+    while (it < p.max_iter && p.direct) {
+        // ---- direct mode: one work queue per phase, all 32 warps, indices straight from global memory (L2) ----
+        TRACE(0);
+        for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + s_hrl[i]);
+        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
+        __syncthreads();
+        if (all_local) {
+            for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                const int4 tile = s_et[n_et - 1 - tk];
+                f_e_tile(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+            }
+        } else {
+            for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                const int4 tile = s_et[n_et - 1 - tk];
+                e_tile(p, v, tile, p.m.e_tid + (uint32_t)tile.z, p.m.e_R + tile.x, lane);
+            }
+        }
+        TRACE(1);
+        grid_barrier(p.bar, gridDim.x, 2 * it + 1);
+        TRACE(2);
+        for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
+        __syncthreads();
+        double dm = 0;
+        if (all_local) {
+            for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                const int4 itm = s_mi[tk];
+                dm = fmax(dm, f_m_item(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
+            }
+        } else {
+            for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                const int4 itm = s_mi[tk];
+                dm = fmax(dm, m_item(p, v, itm, p.m.m_cls + (uint32_t)itm.z, lane));
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;
@@ -197,7 +515,113 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
             for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
             atomicMax(p.dmax + (it & 1), (unsigned long long)__double_as_longlong(bm));
         }
-        grid_barrier(p.bar, gridDim.x);
+        TRACE(3);
+        grid_barrier(p.bar, gridDim.x, 2 * it + 2);
+        TRACE(4);
+        d = __longlong_as_double((long long)*((volatile unsigned long long *)(p.dmax + (it & 1))));
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.dmax[(it + 1) & 1] = 0ULL;
+        it++;
+        if (p.stop_on_conv && d <= 1.0) break;
+    }
+    while (it < p.max_iter && !p.direct) {
+        TRACE(0);
+        double dm = 0;
+        if (producer) {
+            // ================= producer warp =================
+            for (int ci = 0; ci < n_ech; ci++) issue_e(ci, gseq + ci);
+            gseq += n_ech;
+            // the M stream does not depend on the E results: prefetch its first chunks before the grid barrier. Only
+            // chunks whose stage was last used by an E chunk may be issued here (the consumers release those without
+            // waiting for anybody), i.e. at most NSTAGE of them.
+            m_pre = min(NSTAGE, n_mch);
+            for (int ci = 0; ci < m_pre; ci++) issue_m(ci, gseq + ci);
+        } else {
+            // ================= consumer warps: E-phase =================
+            for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK - 32) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + s_hrl[i]);
+            if (v.nhr > 0) consumer_sync();             // halo theta visible to every consumer
+            for (int ci = 0; ci < n_ech; ci++) {
+                const int g = gseq + ci, sg = g % NSTAGE;
+                const int4 c = s_ech[ci];
+                mbar_wait(&sm_full[sg], (g / NSTAGE) & 1);
+                const int n_items = c.y - c.x;
+                const bool staged = c.w >= 0;
+                const int jbase = s_et[c.x].x;
+                const int32_t *gi = p.m.e_tid + (uint32_t)c.z;
+                const int sh = stage_shift(gi);
+                const int n_idx = c.w - (s_et[c.y - 1].x + s_et[c.y - 1].y - jbase);
+                const int ro = (sh + n_idx + 3) & ~3, sr = stage_shift(p.m.e_R + jbase);
+                // tiles are ordered by cardinality: take them from the heaviest end
+                if (p.eps_abs < 0) { /* tuning aid: stream only */ } else
+                if (staged && all_local) {
+                    const int tbase = sg * (CH_BYTES / 4) + sh - c.z, rbase = sg * (CH_BYTES / 4) + ro + sr - jbase;
+                    for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
+                        const int4 tile = s_et[c.y - 1 - tk];
+                        f_e_tile(p, f, tile, IdxS{sm_dyn}, IdxS{sm_dyn}, tbase + tile.z, rbase + tile.x, lane);
+                    }
+                } else {
+                    int *buf = (int *)(sm_dyn + sg * CH_BYTES);
+                    for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
+                        const int4 tile = s_et[c.y - 1 - tk];
+                        const int *tids = staged ? buf + sh + (tile.z - c.z) : p.m.e_tid + (uint32_t)tile.z;
+                        const uint32_t *rfl = staged ? (const uint32_t *)(buf + ro + sr + (tile.x - jbase)) : p.m.e_R + tile.x;
+                        e_tile(p, v, tile, tids, rfl, lane);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm_empty[sg]);   // this warp is done with the stage
+            }
+            gseq += n_ech;
+        }
+        TRACE(1);
+        grid_barrier(p.bar, gridDim.x, 2 * it + 1);
+        TRACE(2);
+        if (producer) {
+            for (int ci = m_pre; ci < n_mch; ci++) issue_m(ci, gseq + ci);
+            gseq += n_mch;
+        } else {
+            // ================= consumer warps: M-phase =================
+            for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK - 32) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
+            if (v.nhc > 0) consumer_sync();
+            for (int ci = 0; ci < n_mch; ci++) {
+                const int g = gseq + ci, sg = g % NSTAGE;
+                const int4 c = s_mch[ci];
+                mbar_wait(&sm_full[sg], (g / NSTAGE) & 1);
+                const int n_items = c.y - c.x;
+                const bool staged = c.w >= 0;
+                const int sh = stage_shift(p.m.m_cls + (uint32_t)c.z);
+                // items are ordered longest first
+                if (p.eps_abs < 0) { /* tuning aid: stream only */ } else
+                if (staged && all_local) {
+                    const int ebase = sg * (CH_BYTES / 4) + sh - c.z;
+                    for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
+                        const int4 itm = s_mi[c.x + tk];
+                        dm = fmax(dm, f_m_item(p, f, itm, IdxS{sm_dyn}, ebase + itm.z, lane));
+                    }
+                } else {
+                    int *buf = (int *)(sm_dyn + sg * CH_BYTES);
+                    for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
+                        const int4 itm = s_mi[c.x + tk];
+                        const int *ent = staged ? buf + sh + (itm.z - c.z) : p.m.m_cls + (uint32_t)itm.z;
+                        dm = fmax(dm, m_item(p, v, itm, ent, lane));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm_empty[sg]);
+            }
+            gseq += n_mch;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        if (lane == 0) sm_red[warp] = dm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bm = 0;
+            for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
+            atomicMax(p.dmax + (it & 1), (unsigned long long)__double_as_longlong(bm));
+        }
+        TRACE(3);
+        grid_barrier(p.bar, gridDim.x, 2 * it + 2);
+        TRACE(4);
         d = __longlong_as_double((long long)*((volatile unsigned long long *)(p.dmax + (it & 1))));
         if (blockIdx.x == 0 && threadIdx.x == 0) p.dmax[(it + 1) & 1] = 0ULL;
         it++;
@@ -229,13 +653,15 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cudaStream_t st = ctx->stream;
     EmParams p;
     p.m = s->m;
-    p.eps_abs = s->opts.eps_abs; p.eps_rel = s->opts.eps_rel;
+    p.eps_abs = getenv("EMSAR_DEBUG_STREAM_ONLY") ? -1.0 : s->opts.eps_abs; p.eps_rel = s->opts.eps_rel;
     p.max_iter = max_iter; p.stop_on_conv = stop_on_conv;
-    p.bar = ctx->d_barrier;
+    p.bar = ctx->d_barrier + 64;                                   // one 128-byte line per CTA
     p.dmax = (unsigned long long *)(ctx->d_barrier + 4);
     p.iters_done = (int *)(ctx->d_barrier + 8);
     p.final_delta = (double *)(ctx->d_barrier + 10);
-    CU(cudaMemsetAsync(ctx->d_barrier, 0, 64, st));
+    { const char *e = getenv("EMSAR_EM_MODE"); p.direct = (e && !strcmp(e, "pipe")) ? 0 : 1; }
+    p.trace = s->d_trace;
+    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + (size_t)s->m.B * 128, st));
     const int grid = s->m.B;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -282,6 +708,26 @@ __global__ void k_fill_double2(double *p, int64_t n, double v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+// tuning aid (not part of include/emsar_cuda.h): run `iters` iterations and return, per CTA, the globaltimer stamps (ns) of
+// the last iteration: [0] E start, [1] E end, [2] after barrier 1, [3] M end, [4] after barrier 2
+extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long long *out, int *n_blocks)
+{
+    if (!s || !s->prepared) return EMSAR_ERR_STATE;
+    CU(cudaSetDevice(s->ctx->device));
+    const int B = s->m.B;
+    TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64));
+    CU(cudaMemset(s->d_trace, 0, (size_t)B * 64 + 512));
+    int it = 0; double fd = 0, ms = 0;
+    int rc = em_launch(s, iters, 0, &it, &fd, &ms);
+    if (rc == EMSAR_OK) {
+        CU(cudaMemcpy(out, s->d_trace, (size_t)B * 64 + 512, cudaMemcpyDeviceToHost));
+        *n_blocks = B;
+    }
+    cudaFree(s->d_trace);
+    s->d_trace = nullptr;
+    return rc;
 }
 
 extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
@@ -532,7 +978,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     cudaFree(s->d_rd_ptr); cudaFree(s->d_rd_tid); cudaFree(s->d_rd_fl);
     cudaFree(s->d_Wf); cudaFree(s->d_adj); cudaFree(s->d_amodel); cudaFree(s->d_in_model);
     cudaFree(s->d_A); cudaFree(s->d_Rs); cudaFree(s->d_iE); cudaFree(s->d_lone); cudaFree(s->d_pos);
-    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls);
+    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls); cudaFree(s->d_halo); cudaFree(s->d_chunks);
     delete s;
     return EMSAR_OK;
 }

@@ -186,62 +186,92 @@ __global__ void k_apply_perm(int32_t P, const int32_t *__restrict__ perm, const 
     row_RsA[p] = make_double2(Rs[t], A[t]);
 }
 
-// M items of every CTA: first its long rows (one item each), then slices of 32 rows
-__global__ void k_block_items(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ degp, int32_t *__restrict__ nlong,
-                              int32_t *__restrict__ item0)
+// M items of every CTA: first groups of its long rows (<= 32 rows and <= M_GROUP_ENTRIES entries each, one warp per
+// group), then slices of 32 rows. Pass 1 counts the items of each CTA (greedy grouping), pass 2 (after the prefix over
+// CTAs) writes them.
+__device__ __forceinline__ int count_long(const uint32_t *degp, int r0, int r1)
+{
+    int lo = r0, hi = r1;            // rows are sorted longest first: first row with degp <= M_LONG
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (degp[mid] <= (uint32_t)M_LONG) hi = mid; else lo = mid + 1; }
+    return lo - r0;
+}
+__global__ void k_block_items_count(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ degp, int32_t *__restrict__ nlong,
+                                    int32_t *__restrict__ nitems, int32_t *__restrict__ ngroups)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int r0 = row0[b], r1 = row0[b + 1];
+    const int nl = count_long(degp, r0, r1);
+    int groups = 0, rows = 0; uint32_t ent = 0;
+    for (int i = 0; i < nl; i++) {
+        const uint32_t d = degp[r0 + i];
+        if (rows > 0 && (rows == M_GROUP_ROWS || ent + d > (uint32_t)M_GROUP_ENTRIES)) { groups++; rows = 0; ent = 0; }
+        rows++; ent += d;
+    }
+    if (rows > 0) groups++;
+    nlong[b] = nl;
+    ngroups[b] = groups;
+    nitems[b] = groups + ((r1 - r0 - nl) + 31) / 32;
+}
+__global__ void k_block_items_prefix(int B, const int32_t *__restrict__ nitems, int32_t *__restrict__ item0)
 {
     if (threadIdx.x || blockIdx.x) return;
     int acc = 0;
-    for (int b = 0; b < B; b++) {
-        const int r0 = row0[b], r1 = row0[b + 1];
-        int lo = r0, hi = r1;            // rows are sorted longest first: first row with degp <= M_LONG
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (degp[mid] <= (uint32_t)M_LONG) hi = mid; else lo = mid + 1; }
-        const int nl = lo - r0;
-        nlong[b] = nl;
-        item0[b] = acc;
-        acc += nl + ((r1 - r0 - nl) + 31) / 32;
-    }
+    for (int b = 0; b < B; b++) { item0[b] = acc; acc += nitems[b]; }
     item0[B] = acc;
 }
-
-__global__ void k_item_sizes(int n_items, int B, const int32_t *__restrict__ row0, const int32_t *__restrict__ nlong,
-                             const int32_t *__restrict__ item0, const uint32_t *__restrict__ degp, uint32_t *__restrict__ size, int4 *__restrict__ items)
+// one thread per CTA: item descriptors (offsets come later), item sizes, and for every long row its offset inside the group
+__global__ void k_block_items_fill(int B, const int32_t *__restrict__ row0, const uint32_t *__restrict__ degp, const int32_t *__restrict__ nlong,
+                                   const int32_t *__restrict__ item0, uint32_t *__restrict__ size, int4 *__restrict__ items,
+                                   uint32_t *__restrict__ rowbase, int32_t *__restrict__ rowitem)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > n_items) return;
-    if (g == n_items) { size[g] = 0; return; }
-    int lo = 0, hi = B - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (item0[mid] <= g) lo = mid; else hi = mid - 1; }
-    const int b = lo, li = g - item0[b], nl = nlong[b], nrows = row0[b + 1] - row0[b];
-    int4 it;
-    if (li < nl) {
-        const uint32_t d = degp[row0[b] + li];
-        it.x = li; it.y = 1; it.z = 0; it.w = (int)(d | (1u << 30));
-        size[g] = d;
-    } else {
-        const int slot0 = nl + 32 * (li - nl);
-        const uint32_t d = degp[row0[b] + slot0];
-        it.x = slot0; it.y = min(32, nrows - slot0); it.z = 0; it.w = (int)d;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) size[item0[B]] = 0;
+    if (b >= B) return;
+    const int r0 = row0[b], r1 = row0[b + 1], nl = nlong[b];
+    int g = item0[b];
+    int rows = 0, first = 0; uint32_t ent = 0;
+    for (int i = 0; i <= nl; i++) {
+        const uint32_t d = i < nl ? degp[r0 + i] : 0;
+        if (rows > 0 && (i == nl || rows == M_GROUP_ROWS || ent + d > (uint32_t)M_GROUP_ENTRIES)) {
+            items[g] = make_int4(first, rows, 0, (int)(ent | (1u << 30)));
+            size[g] = ent + (uint32_t)rows;          // header + entries
+            g++; rows = 0; ent = 0;
+        }
+        if (i == nl) break;
+        if (rows == 0) first = i;
+        rowbase[r0 + i] = ent;                      // entries of the earlier rows of the group
+        rowitem[r0 + i] = g;
+        rows++; ent += d;
+    }
+    const int nrows = r1 - r0;
+    for (int slot0 = nl; slot0 < nrows; slot0 += 32, g++) {
+        const uint32_t d = degp[r0 + slot0];
+        items[g] = make_int4(slot0, min(32, nrows - slot0), 0, (int)d);
         size[g] = 32u * d;
     }
-    items[g] = it;
 }
 
-// entry offsets into the items; the unused lanes of a CTA's last (partial) slice point at the zero slot
-__global__ void k_item_finish(int n_items, int B, const int32_t *__restrict__ item0, const int32_t *__restrict__ nres,
-                              const uint32_t *__restrict__ item_off, int4 *__restrict__ items, int32_t *__restrict__ m_cls)
+__global__ void k_item_offsets(int n_items, const uint32_t *__restrict__ item_off, int4 *__restrict__ items)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_items) items[g].z = (int)item_off[g];
+}
+// group headers (row lengths); the unused lanes of a CTA's last (partial) slice point at the zero slot
+__global__ void k_item_finish(int n_items, int B, const int32_t *__restrict__ item0, const int32_t *__restrict__ row0, const int32_t *__restrict__ nres,
+                              const uint32_t *__restrict__ degp, const int4 *__restrict__ items, int32_t *__restrict__ m_cls)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_items) return;
-    int4 it = items[g];
-    it.z = (int)item_off[g];
-    items[g] = it;
-    if ((it.w >> 30) == 0 && it.y < 32) {
-        int lo = 0, hi = B - 1;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (item0[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int4 it = items[g];
+    int lo = 0, hi = B - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (item0[mid] <= g) lo = mid; else hi = mid - 1; }
+    if ((it.w >> 30) == 1) {
+        for (int r = 0; r < it.y; r++) m_cls[(uint32_t)it.z + r] = (int32_t)degp[row0[lo] + it.x + r];
+    } else if (it.y < 32) {
         const int zero = nres[lo], len = it.w;
         for (int j = 0; j < len; j++)
-            for (int l = it.y; l < 32; l++) m_cls[item_off[g] + (uint32_t)j * 32u + (uint32_t)l] = zero;
+            for (int l = it.y; l < 32; l++) m_cls[(uint32_t)it.z + (uint32_t)j * 32u + (uint32_t)l] = zero;
     }
 }
 
@@ -263,7 +293,17 @@ __global__ void k_class_cells(int64_t n_multi, int32_t T, int n_kseg, int B, con
     atomicMin(&cell_first[cell], j);
 }
 
-__device__ __forceinline__ int cls_per_tile(int k) { return k <= KT ? 32 : max(1, E_TILE_TARGET / k); }
+__global__ void k_class_newid(int64_t n_multi, const int32_t *__restrict__ act, const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof,
+                              const int32_t *__restrict__ cell_first, const int32_t *__restrict__ clsbase, int32_t *__restrict__ newid2)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi || !act[i]) return;
+    const int jo = newid[i], cell = cellof[jo];
+    newid2[i] = clsbase[cell] + jo - cell_first[cell];
+}
+
+// classes per E tile: small cardinalities are grouped (k=2: 4 sub-tiles of 32, k=3,4: 2) so that a lane keeps ~8 loads in flight
+__device__ __forceinline__ int cls_per_tile(int k) { return k <= KT ? (k == 2 ? 128 : (k <= 4 ? 64 : 32)) : max(1, E_TILE_TARGET / k); }
 
 __global__ void k_cell_sizes(int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ cell_cnt,
                              uint32_t *__restrict__ cell_ints, int32_t *__restrict__ cell_tiles)
@@ -285,23 +325,75 @@ __global__ void k_block_tables(int B, int n_kseg, const int32_t *__restrict__ cl
     etile0[b] = tilebase[b * n_kseg];
 }
 
-__global__ void k_block_nres(int B, int smem_bytes, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
-                             const int32_t *__restrict__ etile0, const int32_t *__restrict__ mitem0, int32_t *__restrict__ nres)
+// ---- halo lists -----------------------------------------------------------------------------------------
+// every reference that leaves the owner's range is appended as (CTA << 32 | global index); sorting + unique gives each
+// CTA its list of distinct remote rows (E side) / classes (M side), in a deterministic order
+__global__ void k_halo_collect_e(int64_t n_multi, int32_t T, int B, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
+                                 const int32_t *__restrict__ act, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
+                                 unsigned long long *__restrict__ keys, unsigned int *__restrict__ count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_multi || !act[i]) return;
+    const uint32_t o = cls_off[T + i], e = cls_off[T + i + 1];
+    const int ob = block_of_row(row0, B, pos[cls_tid[o]]);
+    const int r0 = row0[ob], r1 = row0[ob + 1];
+    for (uint32_t j = o + lane; j < e; j += 32) {
+        const int p = pos[cls_tid[j]];
+        if (p < r0 || p >= r1) keys[atomicAdd(count, 1u)] = ((unsigned long long)ob << 32) | (unsigned long long)(uint32_t)p;
+    }
+}
+
+__global__ void k_halo_collect_m(int32_t T, int B, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
+                                 const int32_t *__restrict__ act, const int32_t *__restrict__ newid2, const int32_t *__restrict__ pos,
+                                 const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
+                                 unsigned long long *__restrict__ keys, unsigned int *__restrict__ count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    const int p = pos[t];
+    if (p < 0) return;
+    const int b = block_of_row(row0, B, p);
+    const int c0 = cls0[b], c1 = cls0[b + 1];
+    for (uint32_t e = txm_off[t] + lane; e < txm_off[t + 1]; e += 32) {
+        const int i = txm_cid[e] - T;
+        if (!act[i]) continue;
+        const int id = newid2[i];
+        if (id < c0 || id >= c1) keys[atomicAdd(count, 1u)] = ((unsigned long long)b << 32) | (unsigned long long)(uint32_t)id;
+    }
+}
+
+__global__ void k_halo_ranges(int B, unsigned int n, const unsigned long long *__restrict__ uniq, int32_t *__restrict__ h0)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const int left = smem_bytes - em_fixed_smem(etile0[b + 1] - etile0[b], mitem0[b + 1] - mitem0[b], row0[b + 1] - row0[b]);
-    nres[b] = max(0, min(cls0[b + 1] - cls0[b], left / 8));
+    if (b > B) return;
+    const unsigned long long target = (unsigned long long)b << 32;
+    unsigned int lo = 0, hi = n;
+    while (lo < hi) { unsigned int mid = (lo + hi) >> 1; if (uniq[mid] >= target) hi = mid; else lo = mid + 1; }
+    h0[b] = (int32_t)lo;
+}
+__global__ void k_halo_list(unsigned int n, const unsigned long long *__restrict__ uniq, int32_t *__restrict__ list)
+{
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) list[i] = (int32_t)(uint32_t)uniq[i];
+}
+__device__ __forceinline__ int halo_find(const unsigned long long *uniq, int h0, int h1, unsigned long long key)
+{
+    int lo = h0, hi = h1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (uniq[mid] >= key) hi = mid; else lo = mid + 1; }
+    return lo - h0;       // the key is present by construction
 }
 
 // One warp per multi-tid class: members of an active class as encoded rows (>= 0: slot in the owner's shared theta,
 // < 0: ~global row), its read count, and the flag that q must also go to global memory.
-__global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int32_t *__restrict__ blk_nres, const int32_t *__restrict__ kseg_k,
+__global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int32_t *__restrict__ blk_nres, const int32_t *__restrict__ blk_hr0,
+                               const int32_t *__restrict__ blk_nhr, const unsigned long long *__restrict__ uniq_e, const int32_t *__restrict__ kseg_k,
                                const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
                                const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof, const int32_t *__restrict__ cell_first,
                                const int32_t *__restrict__ clsbase, const uint32_t *__restrict__ intbase, const int32_t *__restrict__ R,
                                const int32_t *__restrict__ pos, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
-                               int32_t *__restrict__ newid2, int32_t *__restrict__ e_tid, uint32_t *__restrict__ e_R)
+                               int32_t *__restrict__ e_tid, uint32_t *__restrict__ e_R)
 {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -322,11 +414,15 @@ __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int
         remote = remote || !local;
         const uint32_t dst = (k <= KT) ? base + (uint32_t)(jl >> 5) * 32u * (uint32_t)k + (uint32_t)jj * 32u + (uint32_t)(jl & 31)
                                        : base + (uint32_t)jl * (uint32_t)k + (uint32_t)jj;
-        e_tid[dst] = local ? p - r0 : ~p;
+        int enc = p - r0;
+        if (!local) {
+            const int h = halo_find(uniq_e, blk_hr0[ob], blk_hr0[ob + 1], ((unsigned long long)ob << 32) | (unsigned long long)(uint32_t)p);
+            enc = h < blk_nhr[ob] ? (r1 - r0) + h : ~p;
+        }
+        e_tid[dst] = enc;
     }
     remote = __any_sync(0xffffffffu, remote);
     if (lane == 0) {
-        newid2[i] = jn;
         const bool resident = (jn - cls0[ob]) < nres;
         e_R[jn] = (uint32_t)R[T + i] | ((remote || !resident) ? 0x80000000u : 0u);
     }
@@ -335,10 +431,13 @@ __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int
 // One warp per transcript: the ACTIVE entries of its transposed row, in ascending cid order, as encoded classes
 // (>= 0: slot in the row owner's shared q, < 0: ~global compact id), written into the row's slice column (padded with
 // the zero slot up to the slice's length) or, for a long row, contiguously.
-__global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk_nres, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
+__global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk_nres, const int32_t *__restrict__ blk_hc0, const int32_t *__restrict__ blk_nhc,
+                               const unsigned long long *__restrict__ uniq_m, const uint32_t *__restrict__ txm_off, const int32_t *__restrict__ txm_cid,
                                const int32_t *__restrict__ act, const int32_t *__restrict__ newid2, const int32_t *__restrict__ pos,
                                const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0, const int32_t *__restrict__ nlong,
-                               const int32_t *__restrict__ item0, const int4 *__restrict__ items, int32_t *__restrict__ m_cls)
+                               const int32_t *__restrict__ item0, const uint32_t *__restrict__ rowbase,
+                               const int32_t *__restrict__ rowitem, const int32_t *__restrict__ ngroups, const int4 *__restrict__ items,
+                               int32_t *__restrict__ m_cls)
 {
     const int lane = threadIdx.x & 31;
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -346,12 +445,14 @@ __global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk
     const int p = pos[t];
     if (p < 0) return;
     const int b = block_of_row(row0, B, p);
-    const int c0 = cls0[b], nres = blk_nres[b];
+    const int c0 = cls0[b], c1 = cls0[b + 1], nres = blk_nres[b];
     const int slot = p - row0[b], nl = nlong[b];
     uint32_t base, stride, len;
-    if (slot < nl) { const int4 it = items[item0[b] + slot]; base = (uint32_t)it.z; stride = 1; len = (uint32_t)it.w & 0x3fffffffu; }
-    else {
-        const int4 it = items[item0[b] + nl + ((slot - nl) >> 5)];
+    if (slot < nl) {
+        const int4 it = items[rowitem[p]];
+        base = (uint32_t)it.z + (uint32_t)it.y + rowbase[p]; stride = 1; len = 0;      // long rows are never padded
+    } else {
+        const int4 it = items[item0[b] + ngroups[b] + ((slot - nl) >> 5)];
         base = (uint32_t)it.z + (uint32_t)((slot - nl) & 31); stride = 32; len = (uint32_t)it.w & 0x3fffffffu;
     }
     uint32_t out = 0;
@@ -361,12 +462,17 @@ __global__ void k_scatter_rows(int32_t T, int B, const int32_t *__restrict__ blk
         if (e + lane < e1) { int i = txm_cid[e + lane] - T; a = act[i]; if (a) id = newid2[i]; }
         unsigned m = __ballot_sync(0xffffffffu, a != 0);
         if (a) {
-            const int loc = id - c0;
-            m_cls[base + (out + (uint32_t)__popc(m & ((1u << lane) - 1))) * stride] = (loc >= 0 && loc < nres) ? loc : ~id;
+            int enc;
+            if (id >= c0 && id < c1) enc = (id - c0) < nres ? id - c0 : ~id;
+            else {
+                const int h = halo_find(uniq_m, blk_hc0[b], blk_hc0[b + 1], ((unsigned long long)b << 32) | (unsigned long long)(uint32_t)id);
+                enc = h < blk_nhc[b] ? nres + 1 + h : ~id;
+            }
+            m_cls[base + (out + (uint32_t)__popc(m & ((1u << lane) - 1))) * stride] = enc;
         }
         out += __popc(m);
     }
-    for (uint32_t j = out + lane; j < len; j += 32) m_cls[base + j * stride] = nres;    // padding -> the zero slot
+    for (uint32_t j = out + lane; j < len; j += 32) m_cls[base + j * stride] = nres;    // slice padding -> the zero slot
 }
 
 __global__ void k_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ tilebase,
@@ -524,8 +630,12 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, scan_max);
     cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t *)nullptr, (int32_t *)nullptr, scan_max);
     cub::DeviceRadixSort::SortPairs(nullptr, b4, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, T + 1, 0, 44);
-    cub_bytes = std::max(std::max(b1, b2), std::max(b3, b4));
-    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 64 + (size_t)(2 * (size_t)T + B + 64) * 8 + (size_t)(n_cells + 1) * 28 + 64 * 256;
+    const size_t href_max = (size_t)ix->nnz_multi + 1;          // remote references of one side: at most every member entry
+    size_t b5 = 0, b6 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b5, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)href_max, 0, 44);
+    cub::DeviceSelect::Unique(nullptr, b6, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (unsigned int *)nullptr, (int)href_max);
+    cub_bytes = std::max(std::max(std::max(b1, b2), std::max(b3, b4)), std::max(b5, b6));
+    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 72 + (size_t)(2 * (size_t)T + B + 64) * 8 + (size_t)(B + 1) * 16 + (size_t)(n_cells + 1) * 28 + 4 * href_max * 8 + 64 * 256;
     void *scr = nullptr;
     TRY(ctx_scratch(ctx, need, &scr));
     char *cur = (char *)scr;
@@ -555,8 +665,17 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     uint32_t *d_intbase = arena_take<uint32_t>(cur, (size_t)n_cells + 1);
     int32_t *d_tilebase = arena_take<int32_t>(cur, (size_t)n_cells + 1);
     int32_t *d_nlong = arena_take<int32_t>(cur, (size_t)B + 1);
+    int32_t *d_nitems = arena_take<int32_t>(cur, (size_t)B + 1);
+    int32_t *d_ngroups = arena_take<int32_t>(cur, (size_t)B + 1);
+    uint32_t *d_rowbase = arena_take<uint32_t>(cur, (size_t)T + 1);
+    int32_t *d_rowitem = arena_take<int32_t>(cur, (size_t)T + 1);
     uint32_t *d_isize = arena_take<uint32_t>(cur, 2 * (size_t)T + B + 64);
     uint32_t *d_ioff = arena_take<uint32_t>(cur, 2 * (size_t)T + B + 64);
+    unsigned long long *d_hkeys = arena_take<unsigned long long>(cur, href_max);
+    unsigned long long *d_hsort = arena_take<unsigned long long>(cur, href_max);
+    unsigned long long *d_uniq_e = arena_take<unsigned long long>(cur, href_max);
+    unsigned long long *d_uniq_m = arena_take<unsigned long long>(cur, href_max);
+    unsigned int *d_hcount = (unsigned int *)arena_take<unsigned int>(cur, 8);
     int32_t *d_pos = s->d_pos;   // t -> row (kept for finalize)
     // ---- class model + active scan ----
     const double nscale = (double)N / 1E6;
@@ -599,7 +718,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
     const size_t m_items_max = (size_t)P / 32 + 2 * (size_t)B + std::min<size_t>((size_t)P, (size_t)ix->nnz_multi / M_LONG + 1) + 64;   // slices + long rows
     auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
-    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd(m_items_max * 16) + 6 * rnd((size_t)(B + 1) * 4);
+    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd(m_items_max * 16) + 12 * rnd((size_t)(B + 1) * 4);
     if (arena1 > s->pack_bytes) {
         if (s->d_pack) CU(cudaFree(s->d_pack));
         s->d_pack = nullptr;
@@ -619,6 +738,10 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.blk_etile0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_mitem0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_nres = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_hr0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_hc0 = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_nhr = arena_take<int32_t>(ac, (size_t)B + 1);
+    m.blk_nhc = arena_take<int32_t>(ac, (size_t)B + 1);
     // ---- rows: costs, ownership ranges, length-sorted order inside each CTA ----
     k_nat_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_nat, d_deg, d_pos, d_degn, d_tn, d_ecost, P);
     LAUNCHED(ctx);
@@ -640,8 +763,9 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA);
         LAUNCHED(ctx);
     }
-    k_block_items<<<1, 32, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, m.blk_mitem0);
-    LAUNCHED(ctx);
+    k_block_items_count<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, d_nitems, d_ngroups);
+    k_block_items_prefix<<<1, 32, 0, st>>>(B, d_nitems, m.blk_mitem0);
+    ctx->launches += 2;
     // ---- classes: (owner CTA, cardinality) cells ----
     CU(cudaMemsetAsync(d_cell_cnt, 0, (size_t)(n_cells + 1) * 4, st));
     k_fill_int<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, st>>>(d_cell_first, n_cells + 1, 0x7fffffff);
@@ -659,28 +783,177 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     ctx->launches += 3;
     k_block_tables<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_kseg > 0 ? n_kseg : 1, d_clsbase, d_tilebase, m.blk_cls0, m.blk_etile0);
     LAUNCHED(ctx);
-    k_block_nres<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, ctx->em_smem_bytes, m.blk_row0, m.blk_cls0, m.blk_etile0, m.blk_mitem0, m.blk_nres);
-    LAUNCHED(ctx);
     CU(cudaGetLastError());
     uint32_t e_ints = 0;
     int32_t n_etiles = 0, n_mitems = 0;
     CU(cudaMemcpyAsync(&e_ints, d_intbase + n_cells, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&n_etiles, d_tilebase + n_cells, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&n_mitems, m.blk_mitem0 + B, 4, cudaMemcpyDeviceToHost, st));
+    // ---- halo lists: distinct remote rows (E side) and remote classes (M side) per CTA ----
+    unsigned int h_cnt[4] = {0, 0, 0, 0};    // collected e, unique e, collected m, unique m
+    CU(cudaMemsetAsync(d_hcount, 0, 32, st));
+    if (nm > 0 && n_kseg > 0) {
+        k_class_newid<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, d_act, d_newid, d_cellof, d_cell_first, d_clsbase, d_newid2);
+        LAUNCHED(ctx);
+        k_halo_collect_e<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, B, ix->d_cls_off, ix->d_cls_tid, d_act, d_pos, m.blk_row0, d_hkeys, d_hcount);
+        LAUNCHED(ctx);
+    }
+    CU(cudaMemcpyAsync(&h_cnt[0], d_hcount, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (h_cnt[0] > 0) {
+        CU(cub::DeviceRadixSort::SortKeys(d_cub, cub_bytes, d_hkeys, d_hsort, (int)h_cnt[0], 0, 44, st));
+        CU(cub::DeviceSelect::Unique(d_cub, cub_bytes, d_hsort, d_uniq_e, d_hcount + 1, (int)h_cnt[0], st));
+        ctx->launches += 4;
+    }
+    if (nm > 0 && n_kseg > 0) {
+        k_halo_collect_m<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, B, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid2, d_pos, m.blk_row0,
+                                                                                   m.blk_cls0, d_hkeys, d_hcount + 2);
+        LAUNCHED(ctx);
+    }
+    CU(cudaMemcpyAsync(&h_cnt[1], d_hcount + 1, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_cnt[2], d_hcount + 2, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_cnt[2] > 0) {
+        CU(cub::DeviceRadixSort::SortKeys(d_cub, cub_bytes, d_hkeys, d_hsort, (int)h_cnt[2], 0, 44, st));
+        CU(cub::DeviceSelect::Unique(d_cub, cub_bytes, d_hsort, d_uniq_m, d_hcount + 3, (int)h_cnt[2], st));
+        ctx->launches += 4;
+        CU(cudaMemcpyAsync(&h_cnt[3], d_hcount + 3, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    const unsigned int n_ue = h_cnt[0] ? h_cnt[1] : 0, n_um = h_cnt[2] ? h_cnt[3] : 0;
+    if ((size_t)(n_ue + n_um + 2) * 4 > s->halo_bytes) {
+        if (s->d_halo) CU(cudaFree(s->d_halo));
+        s->d_halo = nullptr;
+        int32_t *p = nullptr;
+        TRY(dev_alloc(&p, (size_t)n_ue + n_um + 64));
+        s->d_halo = p;
+        s->halo_bytes = ((size_t)n_ue + n_um + 64) * 4;
+    }
+    m.halo_rows = s->d_halo;
+    m.halo_cls = s->d_halo + n_ue;
+    k_halo_ranges<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_ue, d_uniq_e, m.blk_hr0);
+    k_halo_ranges<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_um, d_uniq_m, m.blk_hc0);
+    ctx->launches += 2;
+    if (n_ue) { k_halo_list<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, m.halo_rows); LAUNCHED(ctx); }
+    if (n_um) { k_halo_list<<<(n_um + 255) / 256, 256, 0, st>>>(n_um, d_uniq_m, m.halo_cls); LAUNCHED(ctx); }
+    CU(cudaGetLastError());
     if ((size_t)e_ints > e_ints_max || (size_t)n_etiles > e_tiles_max || (size_t)n_mitems > m_items_max) {
         emsar_set_err("internal: packed model exceeds its bounds (%u ints, %d tiles, %d items)", e_ints, n_etiles, n_mitems);
         return EMSAR_ERR_STATE;
     }
-    // ---- M items: sizes -> offsets ----
+    // ---- M items: sizes -> offsets; E tile descriptors ----
     if ((size_t)n_mitems + 1 > 2 * (size_t)T + B + 64) { emsar_set_err("internal: item scratch too small"); return EMSAR_ERR_STATE; }
-    k_item_sizes<<<(unsigned)((n_mitems + 1 + 255) / 256), 256, 0, st>>>(n_mitems, B, m.blk_row0, d_nlong, m.blk_mitem0, d_degp, d_isize, m.m_items);
+    k_block_items_fill<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, m.blk_mitem0, d_isize, m.m_items, d_rowbase, d_rowitem);
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_isize, d_ioff, n_mitems + 1, st));
     LAUNCHED(ctx);
+    if (n_mitems > 0) { k_item_offsets<<<(unsigned)((n_mitems + 255) / 256), 256, 0, st>>>(n_mitems, d_ioff, m.m_items); LAUNCHED(ctx); }
+    if (n_etiles > 0) {
+        k_etiles<<<(unsigned)((n_etiles + 255) / 256), 256, 0, st>>>(n_etiles, n_cells, n_kseg, ix->d_kseg_k, d_tilebase, d_clsbase, d_cell_cnt, d_intbase, m.e_tiles);
+        LAUNCHED(ctx);
+    }
+    // ---- host: cut each CTA's two index streams into staged chunks and plan its shared memory ----
+    std::vector<int4> h_et((size_t)n_etiles), h_mi((size_t)n_mitems);
+    std::vector<int32_t> h_row0(B + 1), h_cls0(B + 1), h_et0(B + 1), h_mi0(B + 1), h_hr0(B + 1), h_hc0(B + 1);
     uint32_t m_ints = 0;
     CU(cudaMemcpyAsync(&m_ints, d_ioff + n_mitems, 4, cudaMemcpyDeviceToHost, st));
+    if (n_etiles) CU(cudaMemcpyAsync(h_et.data(), m.e_tiles, (size_t)n_etiles * 16, cudaMemcpyDeviceToHost, st));
+    if (n_mitems) CU(cudaMemcpyAsync(h_mi.data(), m.m_items, (size_t)n_mitems * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_row0.data(), m.blk_row0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_cls0.data(), m.blk_cls0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_et0.data(), m.blk_etile0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_mi0.data(), m.blk_mitem0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_hr0.data(), m.blk_hr0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_hc0.data(), m.blk_hc0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    std::vector<int4> h_ech, h_mch;
+    std::vector<int32_t> h_ech0(B + 1), h_mch0(B + 1), h_nhr(B + 1, 0), h_nres(B + 1, 0), h_nhc(B + 1, 0);
+    const int lim = CH_INTS - 16;
+    for (int b = 0; b < B; b++) {
+        h_ech0[b] = (int32_t)h_ech.size();
+        {   // E: tiles in order; a chunk carries the tiles' member indices followed by their read counts
+            int i0 = h_et0[b], cur = 0;
+            for (int i = h_et0[b]; i < h_et0[b + 1]; i++) {
+                const int4 t = h_et[(size_t)i];
+                const int k = t.w & 0xffff, mode = t.w >> 16;
+                const int ints = mode == 0 ? ((t.y + 31) / 32) * 32 * k : t.y * k;
+                const int cost = ints + t.y;
+                if (cost > lim) {            // oversized tile: its own, unstaged chunk
+                    if (i > i0) h_ech.push_back(make_int4(i0 - h_et0[b], i - h_et0[b], h_et[(size_t)i0].z, cur));
+                    h_ech.push_back(make_int4(i - h_et0[b], i + 1 - h_et0[b], t.z, -1));
+                    i0 = i + 1; cur = 0;
+                    continue;
+                }
+                if (cur + cost > lim) { h_ech.push_back(make_int4(i0 - h_et0[b], i - h_et0[b], h_et[(size_t)i0].z, cur)); i0 = i; cur = 0; }
+                cur += cost;
+            }
+            if (h_et0[b + 1] > i0) h_ech.push_back(make_int4(i0 - h_et0[b], h_et0[b + 1] - h_et0[b], h_et[(size_t)i0].z, cur));
+        }
+        h_mch0[b] = (int32_t)h_mch.size();
+        {
+            int i0 = h_mi0[b], cur = 0;
+            for (int i = h_mi0[b]; i < h_mi0[b + 1]; i++) {
+                const int4 t = h_mi[(size_t)i];
+                const int len = t.w & 0x3fffffff;
+                const int cost = (t.w >> 30) == 0 ? 32 * len : len + t.y;
+                if (cost > lim) {
+                    if (i > i0) h_mch.push_back(make_int4(i0 - h_mi0[b], i - h_mi0[b], h_mi[(size_t)i0].z, cur));
+                    h_mch.push_back(make_int4(i - h_mi0[b], i + 1 - h_mi0[b], t.z, -1));
+                    i0 = i + 1; cur = 0;
+                    continue;
+                }
+                if (cur + cost > lim) { h_mch.push_back(make_int4(i0 - h_mi0[b], i - h_mi0[b], h_mi[(size_t)i0].z, cur)); i0 = i; cur = 0; }
+                cur += cost;
+            }
+            if (h_mi0[b + 1] > i0) h_mch.push_back(make_int4(i0 - h_mi0[b], h_mi0[b + 1] - h_mi0[b], h_mi[(size_t)i0].z, cur));
+        }
+    }
+    h_ech0[B] = (int32_t)h_ech.size(); h_mch0[B] = (int32_t)h_mch.size();
+    if (getenv("EMSAR_DEBUG_PLAN")) {      // tuning aid: what every CTA owns
+        for (int b = 0; b < B; b++) {
+            int groups = 0, unst_m = 0, unst_e = 0; long long gent = 0, sent = 0;
+            for (int i = h_mi0[b]; i < h_mi0[b + 1]; i++) { const int4 t = h_mi[(size_t)i]; if (t.w >> 30) { groups++; gent += t.w & 0x3fffffff; } else sent += 32LL * (t.w & 0x3fffffff); }
+            for (int i = h_mch0[b]; i < h_mch0[b + 1]; i++) unst_m += h_mch[(size_t)i].w < 0;
+            for (int i = h_ech0[b]; i < h_ech0[b + 1]; i++) unst_e += h_ech[(size_t)i].w < 0;
+            fprintf(stderr, "cta %3d rows %5d cls %6d etiles %4d echunks %3d (unstaged %d) mitems %4d groups %4d group_ent %7lld slice_ent %7lld mchunks %3d (unstaged %d)\n", b,
+                    h_row0[b + 1] - h_row0[b], h_cls0[b + 1] - h_cls0[b], h_et0[b + 1] - h_et0[b], h_ech0[b + 1] - h_ech0[b], unst_e, h_mi0[b + 1] - h_mi0[b], groups,
+                    gent, sent, h_mch0[b + 1] - h_mch0[b], unst_m);
+        }
+    }
+    for (int b = 0; b < B; b++) {
+        // what of a CTA's state gets a shared-memory slot: its rows (always), then halo rows, then its classes, then halo classes
+        const int nrows = h_row0[b + 1] - h_row0[b];
+        int left = ctx->em_smem_bytes - em_smem_plan(h_et0[b + 1] - h_et0[b], h_mi0[b + 1] - h_mi0[b], h_ech0[b + 1] - h_ech0[b], h_mch0[b + 1] - h_mch0[b], nrows, 0, 0, 0).total - 64;
+        if (left < 0) { emsar_set_err("a CTA's rows and tables do not fit in shared memory (%d rows)", nrows); return EMSAR_ERR_UNSUPPORTED; }
+        int a = std::max(0, std::min(h_hr0[b + 1] - h_hr0[b], left / 12)); left -= a * 12;
+        int r = std::max(0, std::min(h_cls0[b + 1] - h_cls0[b], left / 8)); left -= r * 8;
+        int c = std::max(0, std::min(h_hc0[b + 1] - h_hc0[b], left / 12));
+        h_nhr[b] = a; h_nres[b] = r; h_nhc[b] = c;
+    }
+    {
+        const size_t nb = (h_ech.size() + h_mch.size() + 2) * 16 + 2 * (size_t)(B + 1) * 4 + 512;
+        if (nb > s->chunk_bytes) {
+            if (s->d_chunks) CU(cudaFree(s->d_chunks));
+            s->d_chunks = nullptr;
+            char *p = nullptr;
+            TRY(dev_alloc(&p, nb + (nb >> 2)));
+            s->d_chunks = p;
+            s->chunk_bytes = nb + (nb >> 2);
+        }
+        char *cc = (char *)s->d_chunks;
+        m.e_chunks = arena_take<int4>(cc, h_ech.size() + 1);
+        m.m_chunks = arena_take<int4>(cc, h_mch.size() + 1);
+        m.blk_ech0 = arena_take<int32_t>(cc, (size_t)B + 1);
+        m.blk_mch0 = arena_take<int32_t>(cc, (size_t)B + 1);
+        if (!h_ech.empty()) CU(cudaMemcpyAsync(m.e_chunks, h_ech.data(), h_ech.size() * 16, cudaMemcpyHostToDevice, st));
+        if (!h_mch.empty()) CU(cudaMemcpyAsync(m.m_chunks, h_mch.data(), h_mch.size() * 16, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.blk_ech0, h_ech0.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.blk_mch0, h_mch0.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.blk_nhr, h_nhr.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.blk_nres, h_nres.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.blk_nhc, h_nhc.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));     // the host vectors go out of scope below
+    }
     if ((size_t)(m_ints + 1) * 4 > s->mcls_bytes) {
         if (s->d_mcls) CU(cudaFree(s->d_mcls));
         s->d_mcls = nullptr;
@@ -691,22 +964,18 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     m.m_cls = s->d_mcls;
     m.n_etiles = n_etiles; m.n_mitems = n_mitems; m.m_ints = m_ints;
-    k_item_finish<<<(unsigned)((n_mitems + 255) / 256 + 1), 256, 0, st>>>(n_mitems, B, m.blk_mitem0, m.blk_nres, d_ioff, m.m_items, m.m_cls);
+    k_item_finish<<<(unsigned)((n_mitems + 255) / 256 + 1), 256, 0, st>>>(n_mitems, B, m.blk_mitem0, m.blk_row0, m.blk_nres, d_degp, m.m_items, m.m_cls);
     LAUNCHED(ctx);
     CU(cudaMemsetAsync(m.e_tid, 0, e_ints_max * 4, st));
     if (nm > 0 && n_kseg > 0) {
-        k_pack_classes<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, m.blk_nres, ix->d_kseg_k, ix->d_cls_off, ix->d_cls_tid, d_act, d_newid,
-                                                                          d_cellof, d_cell_first, d_clsbase, d_intbase, s->d_R, d_pos, m.blk_row0,
-                                                                          m.blk_cls0, d_newid2, m.e_tid, m.e_R);
+        k_pack_classes<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, m.blk_nres, m.blk_hr0, m.blk_nhr, d_uniq_e, ix->d_kseg_k, ix->d_cls_off,
+                                                                          ix->d_cls_tid, d_act, d_newid, d_cellof, d_cell_first, d_clsbase, d_intbase, s->d_R,
+                                                                          d_pos, m.blk_row0, m.blk_cls0, m.e_tid, m.e_R);
         LAUNCHED(ctx);
     }
-    k_scatter_rows<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, B, m.blk_nres, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid2, d_pos, m.blk_row0,
-                                                                             m.blk_cls0, d_nlong, m.blk_mitem0, m.m_items, m.m_cls);
+    k_scatter_rows<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, B, m.blk_nres, m.blk_hc0, m.blk_nhc, d_uniq_m, ix->d_txm_off, ix->d_txm_cid, d_act, d_newid2, d_pos, m.blk_row0,
+                                                                             m.blk_cls0, d_nlong, m.blk_mitem0, d_rowbase, d_rowitem, d_ngroups, m.m_items, m.m_cls);
     LAUNCHED(ctx);
-    if (n_etiles > 0) {
-        k_etiles<<<(unsigned)((n_etiles + 255) / 256), 256, 0, st>>>(n_etiles, n_cells, n_kseg, ix->d_kseg_k, d_tilebase, d_clsbase, d_cell_cnt, d_intbase, m.e_tiles);
-        LAUNCHED(ctx);
-    }
     // start point: theta = 1 for every row that takes part (A_t > 0)
     if (P > 0) { k_fill_double<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(m.theta, P, 1.0); LAUNCHED(ctx); }
     CU(cudaGetLastError());
