@@ -36,8 +36,15 @@ void emsar_set_err(const char *fmt, ...);
 #define EM_MIN_BLOCKS 1       // launch-bounds hint: resident CTAs per SM
 #endif
 constexpr int EM_WARPS = EM_BLOCK / 32;
-constexpr int KT = 32;            // classes with cardinality <= KT: one thread per class, members stored transposed in tiles of 32 classes
-constexpr int E_TILE_TARGET = 256; // larger classes: one warp per class, about this many members per tile
+// E side: G lanes share a class (G = 1, 4, 16, 32 by cardinality) so that a lane's dependent chain stays <= ~16 members;
+// a tile is one 32-lane row block of 32/G classes stored transposed (step j of every lane is one 128-byte line), classes
+// shorter than steps*G are padded with the zero-theta slot
+constexpr int KT = 16;            // cardinality <= KT: one thread per class
+__host__ __device__ __forceinline__ int e_lgG(int k) { return k <= KT ? 0 : (k <= 64 ? 2 : (k <= 256 ? 4 : 5)); }
+__host__ __device__ __forceinline__ int e_steps(int k) { const int lg = e_lgG(k); return (k + (1 << lg) - 1) >> lg; }
+// classes per tile: small cardinalities are grouped (k=2: 4 row blocks, k=3,4: 2) so that a lane keeps ~8 loads in flight
+__host__ __device__ __forceinline__ int e_cls_per_tile(int k) { return k == 2 ? 128 : (k <= 4 ? 64 : (32 >> e_lgG(k))); }
+__host__ __device__ __forceinline__ int e_cls_per_block(int k) { return 32 >> e_lgG(k); }
 constexpr int M_LONG = 64;        // transposed rows with more active entries: one warp per row; the rest go into SELL-32 slices
 constexpr int M_GROUP_ENTRIES = 768;  // a group of long rows (<= M_GROUP_ROWS rows, one warp) holds at most this many entries unless a single row is longer
 constexpr int M_GROUP_ROWS = 8;
@@ -108,6 +115,9 @@ struct EmModel {
     int32_t *blk_mitem0;   // [B+1]
     int32_t *blk_ech0, *blk_mch0;  // [B+1] chunk ranges
     int4 *e_chunks, *m_chunks;     // {first item, end item, stream offset (ints), ints}; ints < 0: not staged (oversized item)
+    int32_t *e_res, *m_res;        // per E tile / M item: int offset of its resident copy in the CTA's shared-memory index cache, -1 = none
+    int32_t *blk_res_ints;         // [B] ints of the CTA's resident index cache
+    int32_t direct;                // 1: direct mode (index cache, no staging pipeline)
     int32_t *blk_nres;     // [B]   classes of the CTA whose q lives in shared memory (slot nres holds 0.0: padding target)
     // halo: distinct remote rows / classes a CTA references; copied into its shared memory at the start of each phase
     int32_t *blk_hr0, *blk_hc0;   // [B+1] ranges in halo_rows / halo_cls
@@ -118,7 +128,7 @@ struct EmModel {
     // E side
     int32_t *e_tid;        // encoded member rows (tile-transposed for k<=KT, row-major otherwise)
     uint32_t *e_R;         // [C_a] read count | bit31: q must also be stored to global (halo / not resident)
-    int4 *e_tiles;         // {j0, cnt, tid_off, k | mode<<16}
+    int4 *e_tiles;         // {j0, cnt, tid_off, steps | log2(G) << 12}
     int32_t n_etiles;
     // M side
     int32_t *m_cls;        // encoded classes: slices transposed + padded, long rows row-major
@@ -200,20 +210,23 @@ int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
 // Shared-memory plan of one CTA of k_em_persistent:
 // [stage buffer 0][stage buffer 1][E tile descriptors][M items][E chunks][M chunks][halo row list][halo class list]
 // [{Rs,A} of its rows][theta: own rows | halo rows][q: resident classes | 0.0 | halo classes]
-struct SmemPlan { int off_etiles, off_mitems, off_ech, off_mch, off_hrl, off_hcl, off_rsa, off_theta, off_q, total; };
-__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int n_et, int n_mi, int n_ech, int n_mch, int nrows, int nhr, int nres, int nhc)
+struct SmemPlan { int off_etiles, off_mitems, off_ech, off_mch, off_hrl, off_hcl, off_rsa, off_theta, off_q, off_res, total; };
+// `stage_bytes`: NSTAGE * CH_BYTES in pipelined mode, 0 in direct mode; `n_res_tab`: tiles + items with a resident-cache entry table;
+// in direct mode the chunk-table slots (n_ech) hold the CTA's super-tile rounds instead
+__host__ __device__ __forceinline__ SmemPlan em_smem_plan(int stage_bytes, int n_et, int n_mi, int n_ech, int n_mch, int n_res_tab, int nrows, int nhr, int nres, int nhc)
 {
     SmemPlan p;
-    p.off_etiles = NSTAGE * CH_BYTES;
+    p.off_etiles = stage_bytes;
     p.off_mitems = p.off_etiles + n_et * 16;
     p.off_ech = p.off_mitems + n_mi * 16;
     p.off_mch = p.off_ech + n_ech * 16;
     p.off_hrl = p.off_mch + n_mch * 16;
     p.off_hcl = p.off_hrl + nhr * 4;
-    p.off_rsa = (p.off_hcl + nhc * 4 + 15) & ~15;
+    p.off_rsa = (p.off_hcl + nhc * 4 + n_res_tab * 4 + 15) & ~15;      // the resident-offset tables sit right after the halo lists
     p.off_theta = p.off_rsa + nrows * 16;
-    p.off_q = p.off_theta + (nrows + nhr) * 8;
-    p.total = p.off_q + (nres + 1 + nhc) * 8;
+    p.off_q = p.off_theta + (nrows + nhr + 1) * 8;       // + the zero-theta slot (padding target of the E tiles)
+    p.off_res = p.off_q + (nres + 1 + nhc) * 8;
+    p.total = p.off_res;
     return p;
 }
 // chunks a CTA can need at most for a stream of `ints` ints cut greedily at CH_INTS (every two consecutive chunks hold > CH_INTS)

@@ -21,7 +21,6 @@ struct EmParams {
     EmModel m;
     double eps_abs, eps_rel;
     int max_iter, stop_on_conv;
-    int direct;                    // 1: no staging pipeline, every warp reads its items' indices straight from L2
     unsigned *bar;                 // one generation flag per CTA, 128 bytes apart
     unsigned long long *dmax;      // [2] alternating slots for the reduced delta (bit pattern of a double >= 0)
     int *iters_done;
@@ -160,44 +159,33 @@ __device__ __forceinline__ void etile_small(const EmParams &p, const BlockView &
 
 __device__ __forceinline__ void e_tile(const EmParams &p, const BlockView &v, int4 tile, const int *tids, const uint32_t *rfl, int lane)
 {
-    const int k = tile.w & 0xffff, mode = tile.w >> 16;
-    if (mode == 0) {
-        if (k == 2) { etile_small<2, 4>(p, v, tile, tids, rfl, lane); return; }
-        if (k == 3) { etile_small<3, 2>(p, v, tile, tids, rfl, lane); return; }
-        if (k == 4) { etile_small<4, 2>(p, v, tile, tids, rfl, lane); return; }
-        // one thread per class; member j of the 32 classes of the tile is one 128-byte line
-        uint32_t rf = 0;
-        if (lane < tile.y) rf = rfl[lane];
-        tids += lane;
-        double s = 0;
-        int j = 0;
-        for (; j + 4 <= k; j += 4) {
-            int t[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) t[u] = tids[(j + u) * 32];
-            double x[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = load_theta(p, v, t[u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++) s += x[u];       // sequential member order
-        }
-        for (; j < k; j++) s += load_theta(p, v, tids[j * 32]);
-        if (lane < tile.y) store_q(p, v, tile.x + lane, rf, s);
-    } else {
-        // long classes: one warp per class, members row-major; lane cl keeps the sum of class cl, then all classes of the
-        // tile are finished together (one division per lane instead of a serial chain per class)
-        double mine = 0;
-        for (int cl = 0; cl < tile.y; cl++) {
-            const int *m = tids + cl * k;
-            double s = 0;
-#pragma unroll 4
-            for (int i = lane; i < k; i += 32) s += load_theta(p, v, m[i]);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == cl) mine = s;
-        }
-        if (lane < tile.y) store_q(p, v, tile.x + lane, rfl[lane], mine);
+    const int steps = tile.w & 0xfff, lg = (tile.w >> 12) & 0xf;
+    if (lg == 0) {
+        if (steps == 2) { etile_small<2, 4>(p, v, tile, tids, rfl, lane); return; }
+        if (steps == 3) { etile_small<3, 2>(p, v, tile, tids, rfl, lane); return; }
+        if (steps == 4) { etile_small<4, 2>(p, v, tile, tids, rfl, lane); return; }
     }
+    // G = 1 << lg lanes per class; step j of all 32 lanes is one 128-byte line
+    const int cls = lane >> lg, G = 1 << lg;
+    const bool head = cls < tile.y && (lane & (G - 1)) == 0;
+    uint32_t rf = 0;
+    if (head) rf = rfl[cls];
+    tids += lane;
+    double s = 0;
+    int j = 0;
+    for (; j + 4 <= steps; j += 4) {
+        int t[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) t[u] = tids[(j + u) * 32];
+        double x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) x[u] = load_theta(p, v, t[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) s += x[u];
+    }
+    for (; j < steps; j++) s += load_theta(p, v, tids[j * 32]);
+    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (head) store_q(p, v, tile.x + cls, rf, s);
 }
 
 // ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
@@ -302,36 +290,38 @@ __device__ __forceinline__ void f_etile_small(const EmParams &p, const SmView &v
 template <class IT, class IR>
 __device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int4 tile, IT T_, IR R_, int ti, int ri, int lane)
 {
-    const int k = tile.w & 0xffff, mode = tile.w >> 16;
-    if (mode == 0) {
-        if (k == 2) { f_etile_small<2, 4>(p, v, tile, T_, R_, ti, ri, lane); return; }
-        if (k == 3) { f_etile_small<3, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
-        if (k == 4) { f_etile_small<4, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
-        uint32_t rf = 0;
-        if (lane < tile.y) rf = (uint32_t)R_(ri + lane);
-        ti += lane;
-        double s = 0;
-        int j = 0;
-        for (; j + 4 <= k; j += 4) {
-            const int t0 = T_(ti + j * 32), t1 = T_(ti + j * 32 + 32), t2 = T_(ti + j * 32 + 64), t3 = T_(ti + j * 32 + 96);
-            const double x0 = S64(v)[v.theta8 + t0], x1 = S64(v)[v.theta8 + t1], x2 = S64(v)[v.theta8 + t2], x3 = S64(v)[v.theta8 + t3];
-            s += x0; s += x1; s += x2; s += x3;          // sequential member order
-        }
-        for (; j < k; j++) s += S64(v)[v.theta8 + T_(ti + j * 32)];
-        if (lane < tile.y) f_store_q(p, v, tile.x + lane, rf, s);
-    } else {
-        double mine = 0;
-        for (int cl = 0; cl < tile.y; cl++) {
-            const int m = ti + cl * k;
-            double s = 0;
-#pragma unroll 4
-            for (int i = lane; i < k; i += 32) s += S64(v)[v.theta8 + T_(m + i)];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == cl) mine = s;
-        }
-        if (lane < tile.y) f_store_q(p, v, tile.x + lane, (uint32_t)R_(ri + lane), mine);
+    const int steps = tile.w & 0xfff, lg = (tile.w >> 12) & 0xf;
+    if (lg == 0) {
+        if (steps == 2) { f_etile_small<2, 4>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (steps == 3) { f_etile_small<3, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (steps == 4) { f_etile_small<4, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
     }
+    // G = 1 << lg lanes per class; step j of all 32 lanes is one 128-byte line
+    const int cls = lane >> lg, G = 1 << lg;
+    const bool head = cls < tile.y && (lane & (G - 1)) == 0;
+    uint32_t rf = 0;
+    if (head) rf = (uint32_t)R_(ri + cls);
+    ti += lane;
+    double s = 0;
+    int j = 0;
+    for (; j + 8 <= steps; j += 8) {
+        int t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = T_(ti + (j + u) * 32);
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) x[u] = S64(v)[v.theta8 + t[u]];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += x[u];
+    }
+    for (; j + 4 <= steps; j += 4) {
+        const int t0 = T_(ti + j * 32), t1 = T_(ti + j * 32 + 32), t2 = T_(ti + j * 32 + 64), t3 = T_(ti + j * 32 + 96);
+        const double x0 = S64(v)[v.theta8 + t0], x1 = S64(v)[v.theta8 + t1], x2 = S64(v)[v.theta8 + t2], x3 = S64(v)[v.theta8 + t3];
+        s += x0; s += x1; s += x2; s += x3;
+    }
+    for (; j < steps; j++) s += S64(v)[v.theta8 + T_(ti + j * 32)];
+    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (head) f_store_q(p, v, tile.x + cls, rf, s);
 }
 
 __device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v, int slot, double Q)
@@ -354,6 +344,16 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
         ei += lane;
         double Q = 0;
         int j = 0;
+        for (; j + 8 <= len; j += 8) {
+            int c[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) c[u] = T_(ei + (j + u) * 32);
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = S64(v)[v.q8 + c[u]];
+#pragma unroll
+            for (int u = 0; u < 8; u++) Q += x[u];       // ascending class order
+        }
         for (; j + 4 <= len; j += 4) {
             const int c0 = T_(ei + j * 32), c1 = T_(ei + j * 32 + 32), c2 = T_(ei + j * 32 + 64), c3 = T_(ei + j * 32 + 96);
             const double x0 = S64(v)[v.q8 + c0], x1 = S64(v)[v.q8 + c1], x2 = S64(v)[v.q8 + c2], x3 = S64(v)[v.q8 + c3];
@@ -383,13 +383,14 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
     return d;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
+template <bool DIRECT>
+__global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
 {
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     __shared__ double sm_red[EM_WARPS];
     __shared__ int sm_ctr[NSTAGE];     // work-queue tickets, one counter per pipeline stage
     __shared__ __align__(8) unsigned long long sm_full[NSTAGE], sm_empty[NSTAGE];   // TMA landed / consumers done
+    constexpr bool direct = DIRECT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool producer = warp == EM_WARPS - 1;
     const int b = blockIdx.x;
@@ -402,13 +403,14 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
     v.cls0 = p.m.blk_cls0[b]; v.nres = p.m.blk_nres[b];
     v.nhr = p.m.blk_nhr[b]; v.nhc = p.m.blk_nhc[b];
     const int hr0 = p.m.blk_hr0[b], hc0 = p.m.blk_hc0[b];
-    const SmemPlan pl = em_smem_plan(n_et, n_mi, n_ech, n_mch, v.nrows, v.nhr, v.nres, v.nhc);
+    const SmemPlan pl = em_smem_plan(direct ? 0 : NSTAGE * CH_BYTES, n_et, n_mi, direct ? 0 : n_ech, direct ? 0 : n_mch, direct ? n_et + n_mi : 0, v.nrows, v.nhr, v.nres, v.nhc);
     int4 *s_et = (int4 *)(sm_dyn + pl.off_etiles);
     int4 *s_mi = (int4 *)(sm_dyn + pl.off_mitems);
     int4 *s_ech = (int4 *)(sm_dyn + pl.off_ech);
     int4 *s_mch = (int4 *)(sm_dyn + pl.off_mch);
     int32_t *s_hrl = (int32_t *)(sm_dyn + pl.off_hrl);
     int32_t *s_hcl = (int32_t *)(sm_dyn + pl.off_hcl);
+    int32_t *s_eres = s_hcl + v.nhc, *s_mres = s_eres + n_et;      // direct mode: resident-cache offset of every tile / item (-1: none)
     double2 *s_rsa = (double2 *)(sm_dyn + pl.off_rsa);
     v.sm_theta = (double *)(sm_dyn + pl.off_theta);
     v.sm_q = (double *)(sm_dyn + pl.off_q);
@@ -421,15 +423,43 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
     // per-CTA constants and the CTA's slice of theta -> shared memory, once
     for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_et[i] = p.m.e_tiles[et0 + i];
     for (int i = threadIdx.x; i < n_mi; i += EM_BLOCK) s_mi[i] = p.m.m_items[mi0 + i];
-    for (int i = threadIdx.x; i < n_ech; i += EM_BLOCK) s_ech[i] = p.m.e_chunks[ec0 + i];
-    for (int i = threadIdx.x; i < n_mch; i += EM_BLOCK) s_mch[i] = p.m.m_chunks[mc0 + i];
+    if (!direct) {
+        for (int i = threadIdx.x; i < n_ech; i += EM_BLOCK) s_ech[i] = p.m.e_chunks[ec0 + i];
+        for (int i = threadIdx.x; i < n_mch; i += EM_BLOCK) s_mch[i] = p.m.m_chunks[mc0 + i];
+    } else {
+        for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_eres[i] = p.m.e_res[et0 + i];
+        for (int i = threadIdx.x; i < n_mi; i += EM_BLOCK) s_mres[i] = p.m.m_res[mi0 + i];
+    }
     for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) s_hrl[i] = p.m.halo_rows[hr0 + i];
     for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) s_hcl[i] = p.m.halo_cls[hc0 + i];
     for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) { s_rsa[i] = p.m.row_RsA[v.row0 + i]; v.sm_theta[i] = p.m.theta[v.row0 + i]; }
     for (int i = threadIdx.x; i <= v.nres + v.nhc; i += EM_BLOCK) v.sm_q[i] = 0.0;
+    if (threadIdx.x == 0) v.sm_theta[v.nrows + v.nhr] = 0.0;            // zero-theta slot: padding target of the E tiles
     if (threadIdx.x == 0)
         for (int sg = 0; sg < NSTAGE; sg++) { mbar_init(&sm_full[sg], 1); mbar_init(&sm_empty[sg], EM_WARPS - 1); }
     __syncthreads();
+    if (direct) {
+        // fill the resident index cache: [members | read counts] of the chosen E tiles, entries of the chosen M items
+        int *res = (int *)(sm_dyn + pl.off_res);
+        for (int i = warp; i < n_et; i += EM_WARPS) {
+            const int o = s_eres[i];
+            if (o < 0) continue;
+            const int4 t = s_et[i];
+            const int cpb = 32 >> ((t.w >> 12) & 0xf);
+            const int ints = ((t.y + cpb - 1) / cpb) * 32 * (t.w & 0xfff);
+            for (int j = lane; j < ints; j += 32) res[o + j] = p.m.e_tid[(uint32_t)t.z + j];
+            for (int j = lane; j < t.y; j += 32) res[o + ints + j] = (int)p.m.e_R[t.x + j];
+        }
+        for (int i = warp; i < n_mi; i += EM_WARPS) {
+            const int o = s_mres[i];
+            if (o < 0) continue;
+            const int4 t = s_mi[i];
+            const int len = t.w & 0x3fffffff;
+            const int ints = (t.w >> 30) == 0 ? 32 * len : len + t.y;
+            for (int j = lane; j < ints; j += 32) res[o + j] = p.m.m_cls[(uint32_t)t.z + j];
+        }
+        __syncthreads();
+    }
     // chunk sequence number: chunk g lives in stage g % NSTAGE, its barriers are in phase (g / NSTAGE) & 1
     int gseq = 0;            // consumers: next chunk to consume; producer: next chunk to issue
     int m_pre = 0;           // producer: M chunks of this iteration already issued before the grid barrier
@@ -472,7 +502,8 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
         } else if (lane == 0) mbar_arrive(&sm_full[sg]);
     };
 
-    while (it < p.max_iter && p.direct) {
+    const int res4 = pl.off_res / 4;
+    while (it < p.max_iter && direct) {
         // ---- direct mode: one work queue per phase, all 32 warps, indices straight from global memory (L2) ----
         TRACE(0);
         for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + s_hrl[i]);
@@ -480,8 +511,18 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
         __syncthreads();
         if (all_local) {
             for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
-                const int4 tile = s_et[n_et - 1 - tk];
-                f_e_tile(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+                const int ti = n_et - 1 - tk;
+                const int4 tile = s_et[ti];
+                const int ro = s_eres[ti];
+                const unsigned long long tt0 = (p.trace && it == p.max_iter - 1 && blockIdx.x == 0) ? gtime() : 0ULL;
+                if (ro >= 0) {
+                    const int cpb = 32 >> ((tile.w >> 12) & 0xf), ints = ((tile.y + cpb - 1) / cpb) * 32 * (tile.w & 0xfff);
+                    f_e_tile(p, f, tile, IdxS{sm_dyn}, IdxS{sm_dyn}, res4 + ro, res4 + ro + ints, lane);
+                } else f_e_tile(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+                if (tt0 && lane == 0 && tk < 400) {
+                    unsigned long long *tr = p.trace + gridDim.x * 8 + 64 + (size_t)tk * 4;
+                    tr[0] = tt0; tr[1] = gtime(); tr[2] = (unsigned long long)tile.w | ((unsigned long long)(ro >= 0) << 40) | ((unsigned long long)warp << 48); tr[3] = (unsigned long long)tile.y;
+                }
             }
         } else {
             for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
@@ -498,7 +539,9 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
         if (all_local) {
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
                 const int4 itm = s_mi[tk];
-                dm = fmax(dm, f_m_item(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
+                const int ro = s_mres[tk];
+                if (ro >= 0) dm = fmax(dm, f_m_item(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
+                else dm = fmax(dm, f_m_item(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
             }
         } else {
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
@@ -523,7 +566,7 @@ __global__ void __launch_bounds__(EM_BLOCK, MINB) k_em_persistent(EmParams p)
         it++;
         if (p.stop_on_conv && d <= 1.0) break;
     }
-    while (it < p.max_iter && !p.direct) {
+    while (it < p.max_iter && !direct) {
         TRACE(0);
         double dm = 0;
         if (producer) {
@@ -638,9 +681,10 @@ int em_query_occupancy(emsar_ctx *ctx)
     const char *e = getenv("EMSAR_EM_SMEM_KB");
     if (e && atoi(e) > 0 && atoi(e) * 1024 < smem) smem = atoi(e) * 1024;
     smem &= ~255;
-    CU(cudaFuncSetAttribute(k_em_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<1>, EM_BLOCK, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<true>, EM_BLOCK, smem));
     if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM (%d bytes of shared memory)", smem); return EMSAR_ERR_CUDA; }
     ctx->em_blocks_per_sm = 1;
     ctx->em_smem_bytes = smem;
@@ -659,7 +703,6 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     p.dmax = (unsigned long long *)(ctx->d_barrier + 4);
     p.iters_done = (int *)(ctx->d_barrier + 8);
     p.final_delta = (double *)(ctx->d_barrier + 10);
-    { const char *e = getenv("EMSAR_EM_MODE"); p.direct = (e && !strcmp(e, "pipe")) ? 0 : 1; }
     p.trace = s->d_trace;
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + (size_t)s->m.B * 128, st));
     const int grid = s->m.B;
@@ -689,7 +732,8 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
-    CU(cudaLaunchKernelEx(&cfg, k_em_persistent<1>, p));
+    if (s->m.direct) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<true>, p));
+    else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<false>, p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     int it = 0; double fd = 0;
@@ -717,12 +761,12 @@ extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long lo
     if (!s || !s->prepared) return EMSAR_ERR_STATE;
     CU(cudaSetDevice(s->ctx->device));
     const int B = s->m.B;
-    TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64));
-    CU(cudaMemset(s->d_trace, 0, (size_t)B * 64 + 512));
+    TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64 + 1600));
+    CU(cudaMemset(s->d_trace, 0, (size_t)B * 64 + 512 + 12800));
     int it = 0; double fd = 0, ms = 0;
     int rc = em_launch(s, iters, 0, &it, &fd, &ms);
     if (rc == EMSAR_OK) {
-        CU(cudaMemcpy(out, s->d_trace, (size_t)B * 64 + 512, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out, s->d_trace, (size_t)B * 64 + 512 + 12800, cudaMemcpyDeviceToHost));
         *n_blocks = B;
     }
     cudaFree(s->d_trace);

@@ -302,17 +302,14 @@ __global__ void k_class_newid(int64_t n_multi, const int32_t *__restrict__ act, 
     newid2[i] = clsbase[cell] + jo - cell_first[cell];
 }
 
-// classes per E tile: small cardinalities are grouped (k=2: 4 sub-tiles of 32, k=3,4: 2) so that a lane keeps ~8 loads in flight
-__device__ __forceinline__ int cls_per_tile(int k) { return k <= KT ? (k == 2 ? 128 : (k <= 4 ? 64 : 32)) : max(1, E_TILE_TARGET / k); }
-
 __global__ void k_cell_sizes(int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ cell_cnt,
                              uint32_t *__restrict__ cell_ints, int32_t *__restrict__ cell_tiles)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_cells) return;
     if (c == n_cells) { cell_ints[c] = 0; cell_tiles[c] = 0; return; }
-    const int k = kseg_k[c % n_kseg], cnt = cell_cnt[c], cpt = cls_per_tile(k);
-    cell_ints[c] = k <= KT ? (uint32_t)((cnt + 31) / 32) * 32u * (uint32_t)k : (uint32_t)cnt * (uint32_t)k;
+    const int k = kseg_k[c % n_kseg], cnt = cell_cnt[c], cpt = e_cls_per_tile(k), cpb = e_cls_per_block(k);
+    cell_ints[c] = (uint32_t)((cnt + cpb - 1) / cpb) * 32u * (uint32_t)e_steps(k);
     cell_tiles[c] = (cnt + cpt - 1) / cpt;
 }
 
@@ -407,19 +404,23 @@ __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int
     const int nres = blk_nres[ob];
     const uint32_t o = cls_off[T + i];
     const uint32_t base = intbase[cell];
+    const int lg = e_lgG(k), G = 1 << lg, steps = e_steps(k), cpb = 32 >> lg;
+    const uint32_t rb = (uint32_t)(jl / cpb), cb = (uint32_t)(jl % cpb);
+    const int zero_enc = (r1 - r0) + blk_nhr[ob];            // the zero-theta slot follows the CTA's own and halo rows
     bool remote = false;
-    for (int jj = lane; jj < k; jj += 32) {
-        const int p = pos[cls_tid[o + jj]];
-        const bool local = p >= r0 && p < r1;
-        remote = remote || !local;
-        const uint32_t dst = (k <= KT) ? base + (uint32_t)(jl >> 5) * 32u * (uint32_t)k + (uint32_t)jj * 32u + (uint32_t)(jl & 31)
-                                       : base + (uint32_t)jl * (uint32_t)k + (uint32_t)jj;
-        int enc = p - r0;
-        if (!local) {
-            const int h = halo_find(uniq_e, blk_hr0[ob], blk_hr0[ob + 1], ((unsigned long long)ob << 32) | (unsigned long long)(uint32_t)p);
-            enc = h < blk_nhr[ob] ? (r1 - r0) + h : ~p;
+    for (int jj = lane; jj < steps * G; jj += 32) {
+        int enc = zero_enc;
+        if (jj < k) {
+            const int p = pos[cls_tid[o + jj]];
+            const bool local = p >= r0 && p < r1;
+            remote = remote || !local;
+            enc = p - r0;
+            if (!local) {
+                const int h = halo_find(uniq_e, blk_hr0[ob], blk_hr0[ob + 1], ((unsigned long long)ob << 32) | (unsigned long long)(uint32_t)p);
+                enc = h < blk_nhr[ob] ? (r1 - r0) + h : ~p;
+            }
         }
-        e_tid[dst] = enc;
+        e_tid[base + rb * 32u * (uint32_t)steps + (uint32_t)(jj >> lg) * 32u + cb * (uint32_t)G + (uint32_t)(jj & (G - 1))] = enc;
     }
     remote = __any_sync(0xffffffffu, remote);
     if (lane == 0) {
@@ -483,12 +484,12 @@ __global__ void k_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__
     if (g >= n_tiles) return;
     int lo = 0, hi = n_cells - 1;      // largest cell with tilebase[cell] <= g (non-empty by construction)
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tilebase[mid] <= g) lo = mid; else hi = mid - 1; }
-    const int c = lo, k = kseg_k[c % n_kseg], cpt = cls_per_tile(k), lt = g - tilebase[c];
+    const int c = lo, k = kseg_k[c % n_kseg], cpt = e_cls_per_tile(k), cpb = e_cls_per_block(k), steps = e_steps(k), lt = g - tilebase[c];
     int4 t;
     t.x = clsbase[c] + lt * cpt;
     t.y = min(cpt, cell_cnt[c] - lt * cpt);
-    t.z = (int)(intbase[c] + (uint32_t)lt * (uint32_t)cpt * (uint32_t)k);
-    t.w = k | ((k <= KT ? 0 : 1) << 16);
+    t.z = (int)(intbase[c] + (uint32_t)lt * (uint32_t)(cpt / cpb) * 32u * (uint32_t)steps);
+    t.w = steps | (e_lgG(k) << 12);
     tiles[g] = t;
 }
 
@@ -714,7 +715,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.theta = s->d_state;
     m.q = (double *)((char *)s->d_state + theta_bytes);
     // ---- arena part 1: everything whose size is known now ----
-    const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)32 * KT * (size_t)KT * (size_t)B + 64;   // tile padding: <= 31*k per (CTA, k<=KT) cell
+    // padding: a class is padded to steps*G members (< 1.25 k + 31), a cell to whole row blocks (< 32*steps ints per (CTA, cardinality) cell)
+    const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)ix->nnz_multi / 4 + 32 * (size_t)nm + (size_t)n_cells * 32 * 64 + 64;
     const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
     const size_t m_items_max = (size_t)P / 32 + 2 * (size_t)B + std::min<size_t>((size_t)P, (size_t)ix->nnz_multi / M_LONG + 1) + 64;   // slices + long rows
     auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
@@ -875,8 +877,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
             int i0 = h_et0[b], cur = 0;
             for (int i = h_et0[b]; i < h_et0[b + 1]; i++) {
                 const int4 t = h_et[(size_t)i];
-                const int k = t.w & 0xffff, mode = t.w >> 16;
-                const int ints = mode == 0 ? ((t.y + 31) / 32) * 32 * k : t.y * k;
+                const int steps = t.w & 0xfff, cpb = 32 >> ((t.w >> 12) & 0xf);
+                const int ints = ((t.y + cpb - 1) / cpb) * 32 * steps;
                 const int cost = ints + t.y;
                 if (cost > lim) {            // oversized tile: its own, unstaged chunk
                     if (i > i0) h_ech.push_back(make_int4(i0 - h_et0[b], i - h_et0[b], h_et[(size_t)i0].z, cur));
@@ -920,18 +922,50 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
                     gent, sent, h_mch0[b + 1] - h_mch0[b], unst_m);
         }
     }
+    const bool direct = !(getenv("EMSAR_EM_MODE") && !strcmp(getenv("EMSAR_EM_MODE"), "pipe"));
+    std::vector<int32_t> h_eres((size_t)n_etiles + 1, -1), h_mres((size_t)n_mitems + 1, -1), h_resints(B + 1, 0);
     for (int b = 0; b < B; b++) {
         // what of a CTA's state gets a shared-memory slot: its rows (always), then halo rows, then its classes, then halo classes
         const int nrows = h_row0[b + 1] - h_row0[b];
-        int left = ctx->em_smem_bytes - em_smem_plan(h_et0[b + 1] - h_et0[b], h_mi0[b + 1] - h_mi0[b], h_ech0[b + 1] - h_ech0[b], h_mch0[b + 1] - h_mch0[b], nrows, 0, 0, 0).total - 64;
+        const int n_et = h_et0[b + 1] - h_et0[b], n_mi = h_mi0[b + 1] - h_mi0[b];
+        const int n_ech = direct ? 0 : h_ech0[b + 1] - h_ech0[b], n_mch = direct ? 0 : h_mch0[b + 1] - h_mch0[b];
+        int left = ctx->em_smem_bytes - em_smem_plan(direct ? 0 : NSTAGE * CH_BYTES, n_et, n_mi, n_ech, n_mch, direct ? n_et + n_mi : 0, nrows, 0, 0, 0).total - 64;
         if (left < 0) { emsar_set_err("a CTA's rows and tables do not fit in shared memory (%d rows)", nrows); return EMSAR_ERR_UNSUPPORTED; }
         int a = std::max(0, std::min(h_hr0[b + 1] - h_hr0[b], left / 12)); left -= a * 12;
         int r = std::max(0, std::min(h_cls0[b + 1] - h_cls0[b], left / 8)); left -= r * 8;
-        int c = std::max(0, std::min(h_hc0[b + 1] - h_hc0[b], left / 12));
+        int c = std::max(0, std::min(h_hc0[b + 1] - h_hc0[b], left / 12)); left -= c * 12;
         h_nhr[b] = a; h_nres[b] = r; h_nhc[b] = c;
+        if (direct && left > 64) {
+            // resident index cache: the index data of the items with the longest dependent chains stays in shared memory for
+            // the whole kernel (it never changes); everything else is read from L2 every iteration
+            struct Cand { int steps, ints, idx; bool e; };
+            std::vector<Cand> cand;
+            for (int i = h_et0[b]; i < h_et0[b + 1]; i++) {
+                const int4 t = h_et[(size_t)i];
+                const int steps = t.w & 0xfff, cpb = 32 >> ((t.w >> 12) & 0xf);
+                const int ints = ((t.y + cpb - 1) / cpb) * 32 * steps + t.y;                    // members + read counts
+                cand.push_back({t.y > 32 ? 2 : steps, ints, i, true});
+            }
+            for (int i = h_mi0[b]; i < h_mi0[b + 1]; i++) {
+                const int4 t = h_mi[(size_t)i];
+                const int len = t.w & 0x3fffffff;
+                if ((t.w >> 30) == 0) cand.push_back({len, 32 * len, i, false});
+                else cand.push_back({t.y * 6 + len / 32, len + t.y, i, false});
+            }
+            std::stable_sort(cand.begin(), cand.end(), [](const Cand &x, const Cand &y) { return x.steps > y.steps; });
+            int used = 0;
+            const int cap_ints = (left - 64) / 4;
+            for (const Cand &cd : cand) {
+                const int need = (cd.ints + 3) & ~3;
+                if (used + need > cap_ints) continue;
+                (cd.e ? h_eres : h_mres)[(size_t)cd.idx] = used;
+                used += need;
+            }
+            h_resints[b] = used;
+        }
     }
     {
-        const size_t nb = (h_ech.size() + h_mch.size() + 2) * 16 + 2 * (size_t)(B + 1) * 4 + 512;
+        const size_t nb = (h_ech.size() + h_mch.size() + 3) * 16 + 4 * (size_t)(B + 1) * 4 + ((size_t)n_etiles + n_mitems + 2) * 4 + 2048;
         if (nb > s->chunk_bytes) {
             if (s->d_chunks) CU(cudaFree(s->d_chunks));
             s->d_chunks = nullptr;
@@ -945,6 +979,13 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         m.m_chunks = arena_take<int4>(cc, h_mch.size() + 1);
         m.blk_ech0 = arena_take<int32_t>(cc, (size_t)B + 1);
         m.blk_mch0 = arena_take<int32_t>(cc, (size_t)B + 1);
+        m.blk_res_ints = arena_take<int32_t>(cc, (size_t)B + 1);
+        m.e_res = arena_take<int32_t>(cc, (size_t)n_etiles + 1);
+        m.m_res = arena_take<int32_t>(cc, (size_t)n_mitems + 1);
+        m.direct = direct ? 1 : 0;
+        CU(cudaMemcpyAsync(m.blk_res_ints, h_resints.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.e_res, h_eres.data(), ((size_t)n_etiles + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m.m_res, h_mres.data(), ((size_t)n_mitems + 1) * 4, cudaMemcpyHostToDevice, st));
         if (!h_ech.empty()) CU(cudaMemcpyAsync(m.e_chunks, h_ech.data(), h_ech.size() * 16, cudaMemcpyHostToDevice, st));
         if (!h_mch.empty()) CU(cudaMemcpyAsync(m.m_chunks, h_mch.data(), h_mch.size() * 16, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(m.blk_ech0, h_ech0.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));

@@ -7,7 +7,7 @@ idx, reads, _ = bench.make_workload("config2_human_se", 1000)
 ctx = Context(0); ix = Index(ctx, idx); s = ix.sample()
 s.count(reads.read_ptr, reads.read_tid, reads.read_fraglen); s.prepare()
 s.em_run(max_iter=50, stop_on_conv=False)
-out = np.zeros(148*8 + 64, dtype=np.uint64); nb = C.c_int(0)
+out = np.zeros(148*8 + 64 + 1600, dtype=np.uint64); nb = C.c_int(0)
 rc = _lib.lib().emsar_debug_em_trace(s._h, 30, out.ctypes.data_as(C.c_void_p), C.byref(nb))
 t = out.reshape(-1,8)[:nb.value,:5].astype(np.int64)
 t0 = t[:,0].min()
@@ -24,3 +24,15 @@ order = np.argsort(-M)
 print("slowest M CTAs:", [(int(i), round(M[i]/1e3,2)) for i in order[:5]], "fastest:", [(int(i), round(M[i]/1e3,2)) for i in order[-3:]])
 order = np.argsort(-E)
 print("slowest E CTAs:", [(int(i), round(E[i]/1e3,2)) for i in order[:5]], "fastest:", [(int(i), round(E[i]/1e3,2)) for i in order[-3:]])
+
+tr = out[nb.value*8+64:nb.value*8+64+1600].astype(np.int64).reshape(-1,4)
+tr = tr[tr[:,0]>0]
+if len(tr):
+    b0 = t[0,0]
+    k = tr[:,2] & 0xffff; mode=(tr[:,2]>>16)&0xff; res=(tr[:,2]>>40)&1; w=(tr[:,2]>>48)
+    dur = (tr[:,1]-tr[:,0])/1e3; st=(tr[:,0]-b0)/1e3
+    print("CTA 0 E tiles:", len(tr), "sum dur", dur.sum().round(1), "us; per warp busy mean", (dur.sum()/32).round(2))
+    for kk in sorted(set(k.tolist())):
+        m = k==kk
+        print(f"  k={kk:3d} mode {mode[m][0]} tiles {m.sum():3d} resident {res[m].sum():3d} dur mean {dur[m].mean():5.2f} max {dur[m].max():5.2f} us  start {st[m].min():5.2f}..{st[m].max():5.2f} cnt {tr[m,3].mean():5.1f}")
+    print("  last tile end", ((tr[:,1]-b0)/1e3).max().round(2))
