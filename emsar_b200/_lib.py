@@ -37,7 +37,7 @@ class DeviceInfo(C.Structure):
 
 class SolveOpts(C.Structure):
     _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_iter", C.c_int32), ("delta", C.c_double),
-                ("eumacut", C.c_double), ("max_ntid_per_sid", C.c_int32), ("in_model", C.c_void_p)]
+                ("eumacut", C.c_double), ("max_ntid_per_sid", C.c_int32), ("in_model", C.c_void_p), ("sharded", C.c_int32)]
 
 
 class SolveOut(C.Structure):
@@ -60,6 +60,7 @@ SYMBOLS = [
     "emsar_sample_begin", "emsar_sample_count", "emsar_sample_count_device", "emsar_sample_counts_set", "emsar_sample_counts_get",
     "emsar_sample_solve", "emsar_sample_segments_get", "emsar_sample_wf_get", "emsar_sample_end", "emsar_sample_prepare",
     "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_finalize",
+    "emsar_comm_unique_id", "emsar_comm_init", "emsar_comm_destroy", "emsar_sample_counts_allreduce", "emsar_shard_ranges",
 ]
 
 

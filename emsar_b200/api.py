@@ -46,8 +46,36 @@ class Context:
     def synchronize(self):
         L.check(L.lib().emsar_cuda_synchronize(self._h), "emsar_cuda_synchronize")
 
+    # -- multi-GPU (one sample sharded over the ranks) ---------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        L.check(L.lib().emsar_comm_unique_id(buf), "emsar_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        L.check(L.lib().emsar_comm_init(self._h, int(rank), int(nranks), buf), "emsar_comm_init")
+
+    def comm_init_torch(self):
+        """Convenience: ship the NCCL unique id through an initialised torch.distributed process group."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def comm_destroy(self):
+        L.lib().emsar_comm_destroy(self._h)
+
     def close(self):
         if self._h:
+            L.lib().emsar_comm_destroy(self._h)
             L.lib().emsar_cuda_close(self._h)
             self._h = C.c_void_p()
 
@@ -117,6 +145,10 @@ class Sample:
         assert len(R) == self.index.C and len(F) == self.index.max_fraglength + 1
         L.check(L.lib().emsar_sample_counts_set(self._h, _ptr(R), _ptr(F)), "emsar_sample_counts_set")
 
+    def counts_allreduce(self):
+        """Every rank counted a different slice of the read groups: sum the integer counts over the ranks."""
+        L.check(L.lib().emsar_sample_counts_allreduce(self._h), "emsar_sample_counts_allreduce")
+
     def counts(self):
         R = np.zeros(self.index.C, dtype=np.int32)
         F = np.zeros(self.index.max_fraglength + 1, dtype=np.int32)
@@ -126,9 +158,9 @@ class Sample:
 
     # -- estimation --------------------------------------------------------------------------------
     @staticmethod
-    def _opts(eps_abs=0.0, eps_rel=0.0, max_iter=0, delta=0.0, eumacut=0.0, max_ntid_per_sid=0, in_model=None):
+    def _opts(eps_abs=0.0, eps_rel=0.0, max_iter=0, delta=0.0, eumacut=0.0, max_ntid_per_sid=0, in_model=None, sharded=False):
         keep = None
-        o = L.SolveOpts(eps_abs, eps_rel, int(max_iter), delta, eumacut, int(max_ntid_per_sid), None)
+        o = L.SolveOpts(eps_abs, eps_rel, int(max_iter), delta, eumacut, int(max_ntid_per_sid), None, int(bool(sharded)))
         if in_model is not None:
             keep = _np(in_model, np.uint8)
             o.in_model = keep.ctypes.data
@@ -197,3 +229,11 @@ class Sample:
         if self._h:
             L.lib().emsar_sample_end(self._h)
             self._h = C.c_void_p()
+
+
+def shard_ranges(weight_prefix, nranks):
+    """Host-only helper: nnz-balanced contiguous ranges (emsar_shard_ranges)."""
+    wp = _np(weight_prefix, np.int64)
+    out = np.zeros(nranks + 1, dtype=np.int64)
+    L.check(L.lib().emsar_shard_ranges(C.c_int64(len(wp) - 1), _ptr(wp), int(nranks), _ptr(out)), "emsar_shard_ranges")
+    return out

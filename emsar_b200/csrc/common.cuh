@@ -70,6 +70,9 @@ struct emsar_ctx {
     size_t scratch_bytes;
     cudaEvent_t ev0, ev1;
     size_t l2_persist_bytes;
+    // multi-GPU (class-sharded samples): NCCL communicator loaded at run time
+    void *nccl_comm;
+    int rank, nranks;
 };
 
 struct emsar_index {
@@ -135,6 +138,7 @@ struct EmModel {
     int4 *m_items;         // {first row slot, rows, entry offset, length | mode<<30}: mode 0 = slice (length = longest row),
                            // 1 = group of long rows (length = all entries; a header of `rows` lengths precedes them)
     double2 *row_RsA;      // [P] {Rs, A}
+    int32_t *row_t;        // [P] transcript of row p (sharded mode: partial sums are exchanged in transcript order)
     int32_t n_mitems;
     int64_t m_ints;        // entries stored (with padding)
     // state (global copies; the shared-memory copies are loaded from / written through to these)
@@ -178,6 +182,8 @@ struct emsar_sample {
     void *d_chunks;        // chunk tables
     size_t chunk_bytes;
     unsigned long long *d_trace;   // tuning aid
+    double *d_qpart;       // sharded mode: [2*T] partial / reduced per-transcript sums
+    bool sharded;
     EmModel m;
     emsar_model_stats stats;
     // solve bookkeeping
@@ -204,6 +210,8 @@ int sample_build_model(emsar_sample *s);
 int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms);
 int em_query_occupancy(emsar_ctx *ctx);
 int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
+int comm_allreduce_f64(emsar_ctx *ctx, const double *in, double *out, size_t n);
+int comm_allreduce_i32(emsar_ctx *ctx, int32_t *inout, size_t n);
 
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -26,6 +26,7 @@ struct EmParams {
     int *iters_done;
     double *final_delta;
     unsigned long long *trace;     // optional [B*8] globaltimer stamps of the last iteration (tuning aid)
+    double *q_out;                 // sharded mode: one E + partial M pass; the row sums go to q_out[transcript] instead of updating theta
 };
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -191,6 +192,7 @@ __device__ __forceinline__ void e_tile(const EmParams &p, const BlockView &v, in
 // ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
 __device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v, int slot, double Q)
 {
+    if (p.q_out) { p.q_out[p.m.row_t[v.row0 + slot]] = Q; return 0.0; }
     const double2 ra = v.sm_rsa[slot];
     const double th = v.sm_theta[slot];
     const double n = ra.x + th * Q;
@@ -326,6 +328,7 @@ __device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int
 
 __device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v, int slot, double Q)
 {
+    if (p.q_out) { p.q_out[p.m.row_t[v.row0 + slot]] = Q; return 0.0; }
     const double2 ra = ((const double2 *)v.base)[v.rsa16 + slot];
     const double th = S64(v)[v.theta8 + slot];
     const double n = ra.x + th * Q;
@@ -549,6 +552,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 dm = fmax(dm, m_item(p, v, itm, p.m.m_cls + (uint32_t)itm.z, lane));
             }
         }
+        if (p.q_out) { it++; break; }            // sharded mode: the all-reduce and the theta update happen outside
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;
@@ -704,6 +708,7 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     p.iters_done = (int *)(ctx->d_barrier + 8);
     p.final_delta = (double *)(ctx->d_barrier + 10);
     p.trace = s->d_trace;
+    p.q_out = s->sharded ? s->d_qpart : nullptr;
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + (size_t)s->m.B * 128, st));
     const int grid = s->m.B;
     cudaLaunchConfig_t cfg;
@@ -774,6 +779,69 @@ extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long lo
     return rc;
 }
 
+// ---- sharded mode: theta update from the all-reduced per-transcript sums (identical on every rank) ----
+__global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_t, const double2 *__restrict__ row_RsA, const double *__restrict__ qsum,
+                                 double *__restrict__ theta, double eps_abs, double eps_rel, unsigned long long *dmax)
+{
+    __shared__ double red[8];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double d = 0;
+    if (p < P) {
+        const double2 ra = row_RsA[p];
+        const double th = theta[p];
+        const double n = ra.x + th * qsum[row_t[p]];
+        const double thn = n / ra.y;
+        theta[p] = thn;
+        d = fabs(thn - th) * ra.y / (eps_abs + eps_rel * n);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) b = fmax(b, red[w]);
+        atomicMax(dmax, (unsigned long long)__double_as_longlong(b));
+    }
+}
+
+static int em_run_sharded(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out)
+{
+    emsar_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int32_t T = s->index->T, P = s->m.P;
+    if (!s->m.direct) { emsar_set_err("sharded samples need the direct EM mode"); return EMSAR_ERR_UNSUPPORTED; }
+    if (!s->d_qpart) { TRY(dev_alloc(&s->d_qpart, 2 * (size_t)T + 2)); }
+    CU(cudaMemsetAsync(s->d_qpart, 0, (2 * (size_t)T + 2) * 8, st));
+    unsigned long long *d_dmax = (unsigned long long *)(s->d_qpart + 2 * (size_t)T);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, st));
+    int it = 0; double d = INFINITY;
+    while (it < max_iter) {
+        int one = 0; double fd = 0;
+        TRY(em_launch(s, 1, 0, &one, &fd, nullptr));                 // E-phase + partial M-phase of this rank's classes
+        TRY(comm_allreduce_f64(ctx, s->d_qpart, s->d_qpart + T, (size_t)T));
+        CU(cudaMemsetAsync(d_dmax, 0, 8, st));
+        if (P > 0) { k_update_sharded<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_t, s->m.row_RsA, s->d_qpart + T, s->m.theta, s->opts.eps_abs, s->opts.eps_rel, d_dmax); LAUNCHED(ctx); }
+        unsigned long long bits = 0;
+        CU(cudaMemcpyAsync(&bits, d_dmax, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memcpy(&d, &bits, 8);
+        it++;
+        if (stop_on_conv && d <= 1.0) break;
+    }
+    CU(cudaEventRecord(e1, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (iters_done) *iters_done = it;
+    if (final_delta) *final_delta = d;
+    if (ms_out) *ms_out = ms;
+    return EMSAR_OK;
+}
+
 extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
                                    int32_t *iters_done, double *final_delta, double *elapsed_ms)
 {
@@ -787,7 +855,8 @@ extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t st
     }
     if (max_iter <= 0) max_iter = s->opts.max_iter;
     int it = 0; double fd = 0, ms = 0;
-    TRY(em_launch(s, max_iter, stop_on_conv, &it, &fd, &ms));
+    if (s->sharded) TRY(em_run_sharded(s, max_iter, stop_on_conv, &it, &fd, &ms));
+    else TRY(em_launch(s, max_iter, stop_on_conv, &it, &fd, &ms));
     s->n_iter += it; s->final_delta = fd; s->em_ms += ms;
     if (iters_done) *iters_done = it;
     if (final_delta) *final_delta = fd;
@@ -1022,7 +1091,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     cudaFree(s->d_rd_ptr); cudaFree(s->d_rd_tid); cudaFree(s->d_rd_fl);
     cudaFree(s->d_Wf); cudaFree(s->d_adj); cudaFree(s->d_amodel); cudaFree(s->d_in_model);
     cudaFree(s->d_A); cudaFree(s->d_Rs); cudaFree(s->d_iE); cudaFree(s->d_lone); cudaFree(s->d_pos);
-    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls); cudaFree(s->d_halo); cudaFree(s->d_chunks);
+    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls); cudaFree(s->d_halo); cudaFree(s->d_chunks); cudaFree(s->d_qpart);
     delete s;
     return EMSAR_OK;
 }

@@ -110,6 +110,26 @@ __global__ void k_row_stats(int32_t T, const uint32_t *__restrict__ txm_off, con
     }
 }
 
+// ---- class-range sharding (one sample over several GPUs): rank r keeps the active classes whose member-count prefix
+// falls into its nnz-balanced range; everything downstream (degrees, ownership, packing) then sees only those classes
+__global__ void k_shard_weights(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ act, uint32_t *__restrict__ w)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_multi) return;
+    w[i] = (i < n_multi && act[i]) ? cls_off[T + i + 1] - cls_off[T + i] : 0u;
+}
+__global__ void k_shard_apply(int64_t n_multi, const uint32_t *__restrict__ wpre, int rank, int nranks, int32_t *__restrict__ act)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi || !act[i]) return;
+    // same rule as emsar_shard_ranges: rank r owns [lower_bound(total*r/R), lower_bound(total*(r+1)/R))
+    const unsigned long long total = wpre[n_multi], me = wpre[i];
+    const unsigned long long lo = total * (unsigned long long)rank / (unsigned long long)nranks;
+    const unsigned long long hi = total * (unsigned long long)(rank + 1) / (unsigned long long)nranks;
+    const bool mine = (rank == 0 || me >= lo) && (rank == nranks - 1 || me < hi);
+    if (!mine) act[i] = 0;
+}
+
 // participating transcripts in natural order: n = rank, with their active row length
 __global__ void k_nat_fill(int32_t T, const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ nat, const int32_t *__restrict__ deg,
                            int32_t *__restrict__ pos, uint32_t *__restrict__ degn, int32_t *__restrict__ tn, int32_t *__restrict__ ecost, int32_t P)
@@ -176,12 +196,13 @@ __global__ void k_sort_keys(int32_t P, int B, const int32_t *__restrict__ row0, 
 
 __global__ void k_apply_perm(int32_t P, const int32_t *__restrict__ perm, const int32_t *__restrict__ tn, const uint32_t *__restrict__ degn,
                              const double *__restrict__ Rs, const double *__restrict__ A, int32_t *__restrict__ pos,
-                             uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA)
+                             uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA, int32_t *__restrict__ row_t)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const int n = perm[p], t = tn[n];
     pos[t] = p;
+    row_t[p] = t;
     degp[p] = degn[n];
     row_RsA[p] = make_double2(Rs[t], A[t]);
 }
@@ -683,6 +704,15 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     const double p10 = pow(10, o.delta);
     k_class_model<<<(unsigned)((C + 1 + 255) / 256), 256, 0, st>>>(C, T, s->d_adj, d_in_model, s->d_R, nscale, p10, s->d_amodel, d_act);
     LAUNCHED(ctx);
+    s->sharded = o.sharded != 0 && ctx->nranks > 1;
+    if (o.sharded && !ctx->nccl_comm) { emsar_set_err("sharded solve without a communicator (emsar_comm_init)"); return EMSAR_ERR_STATE; }
+    if (s->sharded && nm > 0) {
+        uint32_t *d_w = (uint32_t *)d_newid2, *d_wpre = (uint32_t *)d_cellof;      // scratch reuse: both are written later
+        k_shard_weights<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_act, d_w);
+        CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_w, d_wpre, (int)(nm + 1), st));
+        k_shard_apply<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, d_wpre, ctx->rank, ctx->nranks, d_act);
+        ctx->launches += 3;
+    }
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_act, d_newid, (int)(nm + 1), st));
     LAUNCHED(ctx);
     // ---- row statistics and the natural-order numbering of the participating rows ----
@@ -720,7 +750,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
     const size_t m_items_max = (size_t)P / 32 + 2 * (size_t)B + std::min<size_t>((size_t)P, (size_t)ix->nnz_multi / M_LONG + 1) + 64;   // slices + long rows
     auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
-    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd(m_items_max * 16) + 12 * rnd((size_t)(B + 1) * 4);
+    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd((size_t)(P + 1) * 4) + rnd(m_items_max * 16) + 12 * rnd((size_t)(B + 1) * 4);
     if (arena1 > s->pack_bytes) {
         if (s->d_pack) CU(cudaFree(s->d_pack));
         s->d_pack = nullptr;
@@ -734,6 +764,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.e_R = arena_take<uint32_t>(ac, (size_t)C_a + 1);
     m.e_tiles = arena_take<int4>(ac, e_tiles_max);
     m.row_RsA = arena_take<double2>(ac, (size_t)P + 1);
+    m.row_t = arena_take<int32_t>(ac, (size_t)P + 1);
     m.m_items = arena_take<int4>(ac, m_items_max);
     m.blk_row0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_cls0 = arena_take<int32_t>(ac, (size_t)B + 1);
@@ -762,7 +793,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         LAUNCHED(ctx);
         CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_key, d_key2, d_val, d_perm, P, 0, 44, st));
         ctx->launches += 4;
-        k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA);
+        k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA, m.row_t);
         LAUNCHED(ctx);
     }
     k_block_items_count<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, d_nitems, d_ngroups);

@@ -129,6 +129,8 @@ typedef struct {
     double eumacut;        /* in: EUMAcut carried over from the previous sample (emsar.h:94 is never reset) */
     int32_t max_ntid_per_sid; /* <= 0 selects MAX_NTID_PER_SID = 5000 (emsar.h:17) */
     const uint8_t *in_model;  /* optional [C]: caller-supplied set membership (CS[c] != -1); NULL = computed here */
+    int32_t sharded;          /* != 0: the active classes of THIS sample are range-sharded over the ranks of the context's
+                                 communicator (emsar_comm_init); every rank must hold the same counts and make the same calls */
 } emsar_solve_opts;
 
 typedef struct {
@@ -156,6 +158,21 @@ int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, double *expected
 /* [nF]: Wf (normalized.Fragment.length.sampling.prob of .fraglength_effect) */
 int emsar_sample_wf_get(emsar_sample *s, double *Wf);
 int emsar_sample_end(emsar_sample *s);
+
+/* -------- one sample sharded over several GPUs (BASELINE.json configs[2]) ------------------------
+ * One process (or thread) per GPU, each with its own context holding the SAME index. The multi-tid classes that are
+ * active in the sample are cut into nnz-balanced contiguous ranges, one per rank; every EM iteration each rank computes
+ * the per-transcript sums of its classes and an NCCL all-reduce (fp64, T values) over NVLink adds them up; theta stays
+ * replicated and bit-identical on every rank. The reference has no counterpart (single process, emsar_main.c).
+ * The 128-byte id is NCCL's unique id: rank 0 makes it, the caller ships it to the other ranks (bench.py and the tests
+ * use torch.distributed for that), then every rank calls emsar_comm_init. */
+int emsar_comm_unique_id(uint8_t id[128]);
+int emsar_comm_init(emsar_ctx *ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
+int emsar_comm_destroy(emsar_ctx *ctx);
+/* each rank counted a different slice of the read groups: sum ReadCount / FraglengthCounts over the ranks (exact: integers) */
+int emsar_sample_counts_allreduce(emsar_sample *s);
+/* contiguous ranges of equal weight: out[r] .. out[r+1] is rank r's range of the n items (host-only helper, no device needed) */
+int emsar_shard_ranges(int64_t n, const int64_t *weight_prefix, int32_t nranks, int64_t *out);
 
 /* -------- finer-grained steps of emsar_sample_solve (tests, bench.py, profiling) ----------------- */
 typedef struct {

@@ -1,0 +1,90 @@
+"""Multi-GPU paths. On the GPU box with >= 2 devices: one sample class-range sharded over 2 ranks (NCCL all-reduce of the
+per-transcript sums every iteration) must reproduce the single-GPU solve. On the CPU (gloo, world size 2): the host-side
+logic of the same scheme — shard ranges, partial sums, all-reduce, replicated update — against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_class_sharded_sample_two_gpus(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_shard_ranges_balanced(built):
+    from emsar_b200.api import shard_ranges
+    rng = np.random.default_rng(0)
+    w = rng.integers(2, 100, size=5000)
+    wp = np.concatenate([[0], np.cumsum(w)])
+    for R in (1, 2, 3, 8):
+        out = shard_ranges(wp, R)
+        assert out[0] == 0 and out[-1] == len(w) and np.all(np.diff(out) >= 0)
+        parts = [wp[out[r + 1]] - wp[out[r]] for r in range(R)]
+        assert max(parts) - min(parts) <= 2 * w.max()
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, ROOT)
+    from emsar_b200 import synth
+    from emsar_b200.api import shard_ranges
+    from oracle import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = synth.make_index(T=400, n_multi=2500, kmax=20, seed=41, module_cap=60)
+    reads = synth.make_reads(idx, 20000, seed=41)
+    R, F, N = oracle.count(idx, reads)
+    Wf, adj, ps, iE = oracle.prepare(idx, F, N)
+    T, cp, ct = idx.T, idx.class_ptr, idx.class_tid
+    k = np.diff(cp)
+    act = np.nonzero((np.arange(idx.C) >= T) & (R > 0) & (ps > 0))[0]          # active multi-tid classes, cid order
+    wp = np.concatenate([[0], np.cumsum(k[act])])
+    rng_ = shard_ranges(wp, world)
+    mine = act[rng_[rank]:rng_[rank + 1]]                                       # this rank's class range
+    A = np.zeros(T); np.add.at(A, ct, np.repeat(np.where(ps > 0, ps, 0.0), k))
+    Rs = np.where(ps[:T] > 0, R[:T], 0).astype(float)
+    theta = np.where(A > 0, 1.0, 0.0)
+    n_steps = 8
+    _, _, _, steps = oracle.em(idx, R, ps, None, max_iter=n_steps, n_steps=n_steps)
+    err = 0.0
+    for it in range(n_steps):
+        Q = np.zeros(T)
+        for c in mine:                                                          # E-step + partial M-step of the local classes
+            m = ct[cp[c]:cp[c + 1]]
+            s = theta[m].sum()
+            if s > 0:
+                np.add.at(Q, m, R[c] / s)
+        tq = torch.from_numpy(Q)
+        dist.all_reduce(tq)                                                     # the per-iteration all-reduce of the fp64 sums
+        Q = tq.numpy()
+        theta = np.where(A > 0, (Rs + theta * Q) / np.where(A > 0, A, 1.0), 0.0)
+        err = max(err, float(np.max(np.abs(theta - steps[it]) / np.maximum(np.abs(steps[it]), 1e-300))))
+    q.put((rank, err, int(len(mine))))
+    dist.destroy_process_group()
+
+
+def test_class_sharded_logic_gloo_world2(built):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(e <= 1e-12 for _, e, _ in res), res
+    assert all(n > 0 for _, _, n in res)
