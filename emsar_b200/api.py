@@ -70,6 +70,11 @@ class Context:
         dist.broadcast(t, 0)
         self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
 
+    def comm_info(self) -> dict:
+        r, n, pm = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        L.check(L.lib().emsar_comm_info(self._h, C.byref(r), C.byref(n), C.byref(pm)), "emsar_comm_info")
+        return {"rank": r.value, "nranks": n.value, "peer_memory": pm.value}
+
     def comm_destroy(self):
         L.lib().emsar_comm_destroy(self._h)
 

@@ -31,6 +31,33 @@ extern "C" const char *emsar_cuda_strerror(int status)
     }
 }
 
+// the context whose stream / memory pool the allocation helpers of this host thread use (set by every API entry)
+thread_local emsar_ctx *g_cur_ctx = nullptr;
+
+int ctx_use(emsar_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    g_cur_ctx = ctx;
+    return EMSAR_OK;
+}
+
+int dev_alloc_bytes(void **p, size_t bytes)
+{
+    emsar_ctx *ctx = g_cur_ctx;
+    if (bytes == 0) bytes = 1;
+    cudaError_t e = (ctx && ctx->pool) ? cudaMallocFromPoolAsync(p, bytes, (cudaMemPool_t)ctx->pool, ctx->stream) : cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { *p = nullptr; emsar_set_err("device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return EMSAR_ERR_NOMEM; }
+    return EMSAR_OK;
+}
+
+void dev_free(void *p)
+{
+    if (!p) return;
+    emsar_ctx *ctx = g_cur_ctx;
+    if (ctx && ctx->pool) cudaFreeAsync(p, ctx->stream);       // ordered after everything already enqueued on the stream
+    else cudaFree(p);
+}
+
 extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
 {
     CHECK_ARG(out != nullptr, "emsar_cuda_open: ctx is NULL");
@@ -53,6 +80,22 @@ extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
         return EMSAR_ERR_NO_DEVICE;
     }
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // stream-ordered allocations from a pool that never trims: the per-sample arrays of a -M list cost a cudaMalloc once
+        cudaMemPoolProps pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (!getenv("EMSAR_NO_POOL") && cudaMemPoolCreate(&pool, &pp) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            ctx->pool = pool;
+        }
+        cudaGetLastError();
+    }
+    g_cur_ctx = ctx;
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
     // [0..63] scalars of the EM kernel (delta slots, iteration count), then one 128-byte barrier line per CTA
@@ -73,13 +116,15 @@ extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
 extern "C" int emsar_cuda_close(emsar_ctx *ctx)
 {
     if (!ctx) return EMSAR_OK;
-    cudaSetDevice(ctx->device);
+    ctx_use(ctx);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_barrier);
     cudaFree(ctx->d_scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    if (ctx->pool) cudaMemPoolDestroy((cudaMemPool_t)ctx->pool);
     cudaStreamDestroy(ctx->stream);
+    if (g_cur_ctx == ctx) g_cur_ctx = nullptr;
     delete ctx;
     return EMSAR_OK;
 }
@@ -94,7 +139,7 @@ extern "C" int emsar_cuda_launch_count(emsar_ctx *ctx, int64_t *launches)
 extern "C" int emsar_cuda_synchronize(emsar_ctx *ctx)
 {
     CHECK_ARG(ctx, "emsar_cuda_synchronize: NULL ctx");
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     CU(cudaStreamSynchronize(ctx->stream));
     return EMSAR_OK;
 }
@@ -118,7 +163,7 @@ int ctx_scratch(emsar_ctx *ctx, size_t bytes, void **p)
 {
     if (bytes > ctx->scratch_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_scratch) CU(cudaFree(ctx->d_scratch));
+        if (ctx->d_scratch) cudaFree(ctx->d_scratch);
         ctx->d_scratch = nullptr;
         ctx->scratch_bytes = 0;
         size_t want = bytes + (bytes >> 2) + 4096;

@@ -52,6 +52,8 @@ constexpr int CH_INTS = 4096;     // ints per staged chunk of an index stream (i
 constexpr int CH_BYTES = CH_INTS * 4 + 64;
 constexpr int NSTAGE = 4;         // stages of the TMA pipeline (producer warp -> consumer warps)
 
+constexpr int EMSAR_MAX_RANKS = 8;     // one NVSwitch domain
+
 struct KSeg {          // multi-tid classes of one cardinality, contiguous in cid order
     int32_t k;
     int64_t cid0, cid1;
@@ -61,6 +63,7 @@ struct emsar_ctx {
     int device;
     cudaStream_t stream;
     cudaDeviceProp prop;
+    void *pool;               // cudaMemPool_t of the stream-ordered allocations (NULL: plain cudaMalloc / cudaFree)
     int64_t launches;
     int em_blocks_per_sm;
     int em_minb;              // launch-bounds variant of the EM kernel in use
@@ -73,7 +76,16 @@ struct emsar_ctx {
     // multi-GPU (class-sharded samples): NCCL communicator loaded at run time
     void *nccl_comm;
     int rank, nranks;
+    // peer-memory window of the fused class-sharded EM kernel (comm.cu): one cudaMalloc block per rank, mapped into every
+    // other rank with CUDA IPC (or plain peer access inside one process). Layout: [flags | dmax | theta_nat | xbuf].
+    void *win;                 // this rank's window
+    void *peer_win[EMSAR_MAX_RANKS];   // every rank's window as seen from this device (peer_win[rank] == win)
+    bool peer_ipc[EMSAR_MAX_RANKS];    // mapping opened with cudaIpcOpenMemHandle (must be closed)
+    int64_t win_rows;          // capacity: participating rows
+    int win_state;             // 0 = not tried, 1 = usable, -1 = peer memory unavailable (NCCL path only)
 };
+constexpr size_t WIN_HDR_BYTES = 4096;      // flags: rank j's flag at byte 128*j; dmax: rank j's delta at byte 2048 + 8*j
+__host__ __device__ __forceinline__ int64_t win_slice_rows(int64_t rows, int nranks) { return (rows + nranks - 1) / nranks; }
 
 struct emsar_index {
     emsar_ctx *ctx;
@@ -138,7 +150,9 @@ struct EmModel {
     int4 *m_items;         // {first row slot, rows, entry offset, length | mode<<30}: mode 0 = slice (length = longest row),
                            // 1 = group of long rows (length = all entries; a header of `rows` lengths precedes them)
     double2 *row_RsA;      // [P] {Rs, A}
-    int32_t *row_t;        // [P] transcript of row p (sharded mode: partial sums are exchanged in transcript order)
+    int32_t *row_n;        // [P] natural index (rank among the participating transcripts) of row p: the row order differs
+                           // from rank to rank in sharded mode, the natural order does not, so sums are exchanged in it
+    double2 *rsa_nat;      // [P] {Rs, A} in natural order (sharded mode: the owner of a slice updates theta from it)
     int32_t n_mitems;
     int64_t m_ints;        // entries stored (with padding)
     // state (global copies; the shared-memory copies are loaded from / written through to these)
@@ -182,7 +196,7 @@ struct emsar_sample {
     void *d_chunks;        // chunk tables
     size_t chunk_bytes;
     unsigned long long *d_trace;   // tuning aid
-    double *d_qpart;       // sharded mode: [2*T] partial / reduced per-transcript sums
+    double *d_qpart;       // sharded mode, NCCL path: [2*P] partial / reduced per-row sums in natural order
     bool sharded;
     EmModel m;
     emsar_model_stats stats;
@@ -195,23 +209,30 @@ struct emsar_sample {
 
 // ---- helpers implemented across the .cu files ---------------------------------------------------
 int ctx_scratch(emsar_ctx *ctx, size_t bytes, void **p);
+// Device memory of the current context (ctx_use): stream-ordered (cudaMallocFromPoolAsync / cudaFreeAsync on the context's
+// stream) from a pool that keeps what it is given back, so the second sample of a run allocates nothing from the driver.
+int ctx_use(emsar_ctx *ctx);
+int dev_alloc_bytes(void **p, size_t bytes);
+void dev_free(void *p);
 template <class T> static inline int dev_alloc(T **p, size_t n)
 {
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
-    if (e != cudaSuccess) { emsar_set_err("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); return EMSAR_ERR_NOMEM; }
+    int rc = dev_alloc_bytes(&q, (n ? n : 1) * sizeof(T));
     *p = (T *)q;
-    return EMSAR_OK;
+    return rc;
 }
 #define LAUNCHED(ctx) ((ctx)->launches++)
 
 int index_build_hash(emsar_index *ix, const std::vector<uint8_t> &insertable);
 int sample_build_model(emsar_sample *s);
-int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms);
+int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms, bool fused = false);
 int em_query_occupancy(emsar_ctx *ctx);
 int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
 int comm_allreduce_f64(emsar_ctx *ctx, const double *in, double *out, size_t n);
 int comm_allreduce_i32(emsar_ctx *ctx, int32_t *inout, size_t n);
+int comm_barrier(emsar_ctx *ctx);
+int comm_window_ensure(emsar_ctx *ctx, int64_t rows);      // collective; leaves ctx->win_state at 1 (peer memory) or -1
+void comm_window_release(emsar_ctx *ctx);
 
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__

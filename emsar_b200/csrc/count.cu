@@ -198,12 +198,11 @@ static int launch_count(emsar_sample *s, int64_t n_reads, const int64_t *d_ptr, 
 static int grow(void **p, size_t *cap, size_t bytes, emsar_ctx *ctx)
 {
     if (bytes <= *cap) return EMSAR_OK;
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (*p) CU(cudaFree(*p));
+    (void)ctx;
+    if (*p) dev_free(*p);
     *p = nullptr; *cap = 0;
     size_t want = bytes + (bytes >> 3) + 256;
-    cudaError_t e = cudaMalloc(p, want);
-    if (e != cudaSuccess) { emsar_set_err("read staging cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); return EMSAR_ERR_NOMEM; }
+    TRY(dev_alloc_bytes(p, want));
     *cap = want;
     return EMSAR_OK;
 }
@@ -215,7 +214,7 @@ extern "C" int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_
     if (n_reads == 0) { s->have_counts = true; return EMSAR_OK; }   // an empty alignment file is still a sample
     CHECK_ARG(read_ptr && read_tid && read_fraglen, "emsar_sample_count: NULL read arrays");
     emsar_ctx *ctx = s->ctx;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     const int64_t base = read_ptr[0];
     const int64_t ntid = read_ptr[n_reads] - base;
     CHECK_ARG(ntid >= 0, "emsar_sample_count: read_ptr not monotone");
@@ -235,7 +234,7 @@ extern "C" int emsar_sample_count_device(emsar_sample *s, int64_t n_reads, const
     CHECK_ARG(s && n_reads >= 0, "emsar_sample_count_device: bad argument");
     if (n_reads == 0) { s->have_counts = true; return EMSAR_OK; }
     CHECK_ARG(d_read_ptr && d_read_tid && d_read_fraglen, "emsar_sample_count_device: NULL read arrays");
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     return launch_count(s, n_reads, (const int64_t *)d_read_ptr, (const int32_t *)d_read_tid, (const int32_t *)d_read_fraglen);
 }
 
@@ -244,7 +243,7 @@ extern "C" int emsar_sample_begin(emsar_index *ix, emsar_sample **out)
     CHECK_ARG(ix && out, "emsar_sample_begin: NULL argument");
     *out = nullptr;
     emsar_ctx *ctx = ix->ctx;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     emsar_sample *s = new emsar_sample();
     s->index = ix; s->ctx = ctx;
     int rc;
@@ -273,7 +272,7 @@ extern "C" int emsar_sample_counts_set(emsar_sample *s, const int32_t *ReadCount
 {
     CHECK_ARG(s && ReadCount && FraglengthCounts, "emsar_sample_counts_set: NULL argument");
     emsar_index *ix = s->index;
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     CU(cudaMemcpyAsync(s->d_R, ReadCount, (size_t)ix->C * 4, cudaMemcpyHostToDevice, s->ctx->stream));
     CU(cudaMemcpyAsync(s->d_hist, FraglengthCounts, ((size_t)ix->max_fl + 1) * 4, cudaMemcpyHostToDevice, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream));
@@ -285,7 +284,7 @@ extern "C" int emsar_sample_counts_get(emsar_sample *s, int32_t *ReadCount, int3
 {
     CHECK_ARG(s, "emsar_sample_counts_get: NULL sample");
     emsar_index *ix = s->index;
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     TRY(check_flags(s));
     std::vector<int32_t> hist((size_t)ix->max_fl + 1);
     CU(cudaMemcpyAsync(hist.data(), s->d_hist, hist.size() * 4, cudaMemcpyDeviceToHost, s->ctx->stream));

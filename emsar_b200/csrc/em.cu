@@ -26,7 +26,17 @@ struct EmParams {
     int *iters_done;
     double *final_delta;
     unsigned long long *trace;     // optional [B*8] globaltimer stamps of the last iteration (tuning aid)
-    double *q_out;                 // sharded mode: one E + partial M pass; the row sums go to q_out[transcript] instead of updating theta
+    // class-sharded sample (k_em_persistent<2> only): this rank holds a class range; per-row sums are exchanged in natural order
+    struct Shard {
+        int rank, nranks;          // nranks == 0: not sharded
+        int S;                     // rows per owner slice: rank r updates the natural rows [r*S, min(P, (r+1)*S))
+        int fused;                 // 1: all-reduce inside the kernel over peer memory; 0: one pass, sums to q_out (NCCL path)
+        unsigned char *win[EMSAR_MAX_RANKS];   // every rank's window (comm.cu): flags | dmax | theta_nat | xbuf
+        long long theta_off, xbuf_off;         // byte offsets inside a window
+        unsigned long long *dloc;  // this rank's delta of the slice it owns (reduced over its CTAs)
+        unsigned *xbar;            // arrival flag per CTA for the cross-GPU barriers, 128 bytes apart
+        double *q_out;             // NCCL path: [P] partial row sums in natural order
+    } sh;
 };
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -55,12 +65,18 @@ struct BlockView {
     const double2 *sm_rsa;     // {Rs, A} of the rows this CTA owns
     const int4 *sm_etiles;     // this CTA's E tile descriptors
     const int4 *sm_mitems;     // this CTA's M items
+    double *sm_stage;          // sharded mode: partial row sums of this CTA in natural order (reuses the {Rs,A} area)
+    const int *sm_noff;        // sharded mode: natural offset (inside the CTA's range) of every row slot
+    const double *g_theta;     // fused sharded mode: theta in natural order (this rank's window) ...
+    const int *g_rown;         // ... and the permuted row -> natural index table (NULL otherwise)
     int row0, nrows, cls0, nres, nhr, nhc;
 };
 
 // branch-free: one generic load from either the CTA's shared slice or the global copy (overflow only)
+template <bool SH>
 __device__ __forceinline__ double load_theta(const EmParams &p, const BlockView &v, int enc)
 {
+    if (SH && enc < 0 && v.g_rown) return __ldcg(v.g_theta + v.g_rown[~enc]);   // fused sharded mode: the live copy is in natural order
     const double *ptr = enc >= 0 ? v.sm_theta + enc : p.m.theta + ~enc;
     return *ptr;
 }
@@ -137,7 +153,7 @@ __device__ __forceinline__ int next_item(int *counter, int lane)
 
 // ---- E-phase: q_c = R_c / sum of theta over the class members --------------------------------------------------
 // tids / rfl point at the tile's member indices / read counts (shared memory when staged, global otherwise)
-template <int K, int G>
+template <bool SH, int K, int G>
 __device__ __forceinline__ void etile_small(const EmParams &p, const BlockView &v, int4 tile, const int *tids, const uint32_t *rfl, int lane)
 {
     int t[K * G];
@@ -148,7 +164,7 @@ __device__ __forceinline__ void etile_small(const EmParams &p, const BlockView &
     for (int g = 0; g < G; g++) rf[g] = (g * 32 + lane < tile.y) ? rfl[g * 32 + lane] : 0u;
     double x[K * G];
 #pragma unroll
-    for (int u = 0; u < K * G; u++) x[u] = load_theta(p, v, t[u]);
+    for (int u = 0; u < K * G; u++) x[u] = load_theta<SH>(p, v, t[u]);
 #pragma unroll
     for (int g = 0; g < G; g++) {
         double s = 0;
@@ -158,13 +174,14 @@ __device__ __forceinline__ void etile_small(const EmParams &p, const BlockView &
     }
 }
 
+template <bool SH>
 __device__ __forceinline__ void e_tile(const EmParams &p, const BlockView &v, int4 tile, const int *tids, const uint32_t *rfl, int lane)
 {
     const int steps = tile.w & 0xfff, lg = (tile.w >> 12) & 0xf;
     if (lg == 0) {
-        if (steps == 2) { etile_small<2, 4>(p, v, tile, tids, rfl, lane); return; }
-        if (steps == 3) { etile_small<3, 2>(p, v, tile, tids, rfl, lane); return; }
-        if (steps == 4) { etile_small<4, 2>(p, v, tile, tids, rfl, lane); return; }
+        if (steps == 2) { etile_small<SH, 2, 4>(p, v, tile, tids, rfl, lane); return; }
+        if (steps == 3) { etile_small<SH, 3, 2>(p, v, tile, tids, rfl, lane); return; }
+        if (steps == 4) { etile_small<SH, 4, 2>(p, v, tile, tids, rfl, lane); return; }
     }
     // G = 1 << lg lanes per class; step j of all 32 lanes is one 128-byte line
     const int cls = lane >> lg, G = 1 << lg;
@@ -180,19 +197,20 @@ __device__ __forceinline__ void e_tile(const EmParams &p, const BlockView &v, in
         for (int u = 0; u < 4; u++) t[u] = tids[(j + u) * 32];
         double x[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) x[u] = load_theta(p, v, t[u]);
+        for (int u = 0; u < 4; u++) x[u] = load_theta<SH>(p, v, t[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) s += x[u];
     }
-    for (; j < steps; j++) s += load_theta(p, v, tids[j * 32]);
+    for (; j < steps; j++) s += load_theta<SH>(p, v, tids[j * 32]);
     for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (head) store_q(p, v, tile.x + cls, rf, s);
 }
 
 // ---- M-phase: theta_t' = (Rs_t + theta_t * sum of q over the row) / A_t, fused convergence measure --------------
+template <bool SH>
 __device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v, int slot, double Q)
 {
-    if (p.q_out) { p.q_out[p.m.row_t[v.row0 + slot]] = Q; return 0.0; }
+    if (SH) { v.sm_stage[v.sm_noff[slot]] = Q; return 0.0; }     // sharded: stage the partial sum in natural order
     const double2 ra = v.sm_rsa[slot];
     const double th = v.sm_theta[slot];
     const double n = ra.x + th * Q;
@@ -202,6 +220,7 @@ __device__ __forceinline__ double m_update(const EmParams &p, const BlockView &v
     return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
 }
 
+template <bool SH>
 __device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, int4 it, const int *ent, int lane)
 {
     const int len = it.w & 0x3fffffff;
@@ -222,7 +241,7 @@ __device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, 
             for (int u = 0; u < 4; u++) Q += x[u];       // ascending class order
         }
         for (; j < len; j++) Q += load_q(p, v, ent[j * 32]);
-        if (lane < it.y) d = m_update(p, v, it.x + lane, Q);
+        if (lane < it.y) d = m_update<SH>(p, v, it.x + lane, Q);
     } else {
         // a group of long rows: header = the rows' lengths, then their entries; the warp reduces one row at a time with a
         // fixed shuffle tree, lane r keeps row r's sum, then all rows are updated together
@@ -242,7 +261,7 @@ __device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, 
             for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
             if (lane == r) mine = s;
         }
-        if (lane < n) d = m_update(p, v, it.x + lane, mine);
+        if (lane < n) d = m_update<SH>(p, v, it.x + lane, mine);
     }
     return d;
 }
@@ -252,6 +271,7 @@ __device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, 
 struct SmView {
     unsigned char *base;   // sm_dyn
     int theta8, q8, rsa16; // element offsets of theta / q / {Rs,A} inside sm_dyn
+    int noff4;             // sharded mode: int offset of the slot -> natural offset table (second half of the {Rs,A} area)
     int row0, cls0, nres;
 };
 #define S32(v) ((const int *)(v).base)
@@ -326,9 +346,10 @@ __device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int
     if (head) f_store_q(p, v, tile.x + cls, rf, s);
 }
 
+template <bool SH>
 __device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v, int slot, double Q)
 {
-    if (p.q_out) { p.q_out[p.m.row_t[v.row0 + slot]] = Q; return 0.0; }
+    if (SH) { S64(v)[v.rsa16 * 2 + ((const int *)v.base)[v.noff4 + slot]] = Q; return 0.0; }   // stage = the {Rs,A} area (unused when sharded)
     const double2 ra = ((const double2 *)v.base)[v.rsa16 + slot];
     const double th = S64(v)[v.theta8 + slot];
     const double n = ra.x + th * Q;
@@ -338,7 +359,7 @@ __device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v,
     return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
 }
 
-template <class IT>
+template <bool SH, class IT>
 __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, int4 it, IT T_, int ei, int lane)
 {
     const int len = it.w & 0x3fffffff;
@@ -363,7 +384,7 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
             Q += x0; Q += x1; Q += x2; Q += x3;          // ascending class order
         }
         for (; j < len; j++) Q += S64(v)[v.q8 + T_(ei + j * 32)];
-        if (lane < it.y) d = f_m_update(p, v, it.x + lane, Q);
+        if (lane < it.y) d = f_m_update<SH>(p, v, it.x + lane, Q);
     } else {
         const int n = it.y;
         const int mylen = lane < n ? T_(ei + lane) : 0;
@@ -381,14 +402,58 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
             for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
             if (lane == r) mine = s;
         }
-        if (lane < n) d = f_m_update(p, v, it.x + lane, mine);
+        if (lane < n) d = f_m_update<SH>(p, v, it.x + lane, mine);
     }
     return d;
 }
 
-template <bool DIRECT>
+// ---- cross-GPU barrier of the fused sharded kernel ---------------------------------------------------------------
+// Every CTA of every rank arrives; nobody leaves before all have. Two levels: (1) the CTAs of a rank publish their
+// arrival in local flags (release.gpu, after a system-scope fence that covers the CTA's remote stores); (2) CTA 0 collects
+// them and then stores the generation into flag[rank] of EVERY rank's window (its own included) over NVLink; (3) every
+// CTA polls the nranks flags of its OWN window (local memory, acquire.sys). Remote stores issued before the barrier are
+// therefore visible in the target's memory to everything the target does after it. `send_delta`: CTA 0 also forwards the
+// rank's reduced convergence measure (dloc) to slot `rank` of every window's dmax array, ahead of the flag.
+__device__ __forceinline__ void xbarrier(const EmParams::Shard &sh, unsigned nblocks, unsigned gen, bool send_delta)
+{
+    __shared__ unsigned long long s_dl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(sh.xbar + blockIdx.x * 32), "r"(gen) : "memory");
+    }
+    if (blockIdx.x == 0) {
+        for (unsigned i = threadIdx.x; i < nblocks; i += blockDim.x) {
+            unsigned cur;
+            do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(sh.xbar + i * 32) : "memory"); } while ((int)(cur - gen) < 0);
+        }
+        __syncthreads();
+        if (send_delta && threadIdx.x == 0) {
+            s_dl = *((volatile unsigned long long *)sh.dloc);
+            *((volatile unsigned long long *)sh.dloc) = 0ULL;          // next use: after every CTA has left this barrier
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < sh.nranks) {
+            unsigned char *w = sh.win[threadIdx.x];
+            if (send_delta) *((volatile unsigned long long *)(w + 2048) + sh.rank) = s_dl;
+            __threadfence_system();
+            asm volatile("st.release.sys.u32 [%0], %1;" ::"l"((unsigned *)(w + 128 * sh.rank)), "r"(gen) : "memory");
+        }
+    }
+    if ((int)threadIdx.x < sh.nranks) {
+        const unsigned *f = (const unsigned *)(sh.win[sh.rank] + 128 * threadIdx.x);
+        unsigned cur;
+        do { asm volatile("ld.acquire.sys.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory"); } while ((int)(cur - gen) < 0);
+    }
+    __syncthreads();
+}
+
+// MODE 0: TMA-pipelined index streams; 1: direct (resident index cache + L2); 2: direct, class-sharded over several GPUs
+template <int MODE>
 __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
 {
+    constexpr bool DIRECT = MODE != 0;
+    constexpr bool SHARDED = MODE == 2;
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     __shared__ double sm_red[EM_WARPS];
     __shared__ int sm_ctr[NSTAGE];     // work-queue tickets, one counter per pipeline stage
@@ -418,6 +483,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
     v.sm_theta = (double *)(sm_dyn + pl.off_theta);
     v.sm_q = (double *)(sm_dyn + pl.off_q);
     v.sm_etiles = s_et; v.sm_mitems = s_mi; v.sm_rsa = s_rsa;
+    v.sm_stage = nullptr; v.sm_noff = nullptr; v.g_theta = nullptr; v.g_rown = nullptr;
     SmView f;
     f.base = sm_dyn; f.theta8 = pl.off_theta / 8; f.q8 = pl.off_q / 8; f.rsa16 = pl.off_rsa / 16;
     f.row0 = v.row0; f.cls0 = v.cls0; f.nres = v.nres;
@@ -506,7 +572,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
     };
 
     const int res4 = pl.off_res / 4;
-    while (it < p.max_iter && direct) {
+    while (it < p.max_iter && MODE == 1) {
         // ---- direct mode: one work queue per phase, all 32 warps, indices straight from global memory (L2) ----
         TRACE(0);
         for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + s_hrl[i]);
@@ -530,7 +596,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         } else {
             for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
                 const int4 tile = s_et[n_et - 1 - tk];
-                e_tile(p, v, tile, p.m.e_tid + (uint32_t)tile.z, p.m.e_R + tile.x, lane);
+                e_tile<false>(p, v, tile, p.m.e_tid + (uint32_t)tile.z, p.m.e_R + tile.x, lane);
             }
         }
         TRACE(1);
@@ -543,16 +609,15 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
                 const int4 itm = s_mi[tk];
                 const int ro = s_mres[tk];
-                if (ro >= 0) dm = fmax(dm, f_m_item(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
-                else dm = fmax(dm, f_m_item(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
+                if (ro >= 0) dm = fmax(dm, f_m_item<false>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
+                else dm = fmax(dm, f_m_item<false>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
             }
         } else {
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
                 const int4 itm = s_mi[tk];
-                dm = fmax(dm, m_item(p, v, itm, p.m.m_cls + (uint32_t)itm.z, lane));
+                dm = fmax(dm, m_item<false>(p, v, itm, p.m.m_cls + (uint32_t)itm.z, lane));
             }
         }
-        if (p.q_out) { it++; break; }            // sharded mode: the all-reduce and the theta update happen outside
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;
@@ -570,7 +635,113 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         it++;
         if (p.stop_on_conv && d <= 1.0) break;
     }
-    while (it < p.max_iter && !direct) {
+    if (SHARDED) {
+        // ---- class-sharded sample: this rank's classes only. Per iteration: E-phase -> grid barrier -> partial row sums,
+        // pushed (coalesced, natural order) into the xbuf of the rank that owns the row -> cross-GPU barrier -> the owner adds
+        // the nranks partials in rank order, updates theta of its slice and stores it into EVERY rank's theta_nat ->
+        // cross-GPU barrier (carries the convergence measure). theta is bit-identical on all ranks by construction.
+        const EmParams::Shard &sh = p.sh;
+        const int R = sh.nranks, S = sh.S, me = sh.rank;
+        const double *th_nat = (const double *)(sh.win[me] + sh.theta_off);       // local copy of the full theta, natural order
+        const double *xb = (const double *)(sh.win[me] + sh.xbuf_off);           // partials pushed to me: xb[src * S + i]
+        const int n0 = v.row0;                                                   // the CTA's rows are a contiguous natural range
+        int *s_noff = (int *)(s_rsa + 0) + 2 * v.nrows;                          // second half of the {Rs,A} area
+        double *s_stage = (double *)s_rsa;
+        v.sm_stage = s_stage; v.sm_noff = s_noff;
+        v.g_theta = th_nat; v.g_rown = sh.fused ? p.m.row_n : nullptr;
+        f.noff4 = pl.off_rsa / 4 + 2 * v.nrows;
+        for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) s_noff[i] = p.m.row_n[v.row0 + i] - n0;
+        for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) s_hrl[i] = p.m.row_n[s_hrl[i]];        // halo rows: natural index
+        __syncthreads();
+        // the slice this rank owns, cut over the CTAs
+        const int own0 = me * S, own1 = min(p.m.P, own0 + S);
+        const int per = (max(own1 - own0, 0) + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int u0 = min(own1, own0 + b * per), u1 = min(own1, u0 + per);
+        while (it < p.max_iter) {
+            if (sh.fused) {
+                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = __ldcg(th_nat + n0 + s_noff[i]);
+                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(th_nat + s_hrl[i]);
+            } else {
+                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + p.m.halo_rows[hr0 + i]);
+            }
+            if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
+            __syncthreads();
+            if (all_local) {
+                for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                    const int ti = n_et - 1 - tk;
+                    const int4 tile = s_et[ti];
+                    const int ro = s_eres[ti];
+                    if (ro >= 0) {
+                        const int cpb = 32 >> ((tile.w >> 12) & 0xf), ints = ((tile.y + cpb - 1) / cpb) * 32 * (tile.w & 0xfff);
+                        f_e_tile(p, f, tile, IdxS{sm_dyn}, IdxS{sm_dyn}, res4 + ro, res4 + ro + ints, lane);
+                    } else f_e_tile(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+                }
+            } else {
+                for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                    const int4 tile = s_et[n_et - 1 - tk];
+                    e_tile<true>(p, v, tile, p.m.e_tid + (uint32_t)tile.z, p.m.e_R + tile.x, lane);
+                }
+            }
+            grid_barrier(p.bar, gridDim.x, it + 1);
+            for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
+            __syncthreads();
+            if (all_local) {
+                for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                    const int4 itm = s_mi[tk];
+                    const int ro = s_mres[tk];
+                    if (ro >= 0) f_m_item<true>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane);
+                    else f_m_item<true>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane);
+                }
+            } else {
+                for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                    const int4 itm = s_mi[tk];
+                    m_item<true>(p, v, itm, p.m.m_cls + (uint32_t)itm.z, lane);
+                }
+            }
+            __syncthreads();
+            if (!sh.fused) {
+                // NCCL path: one pass; the host all-reduces q_out and runs the update kernel
+                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) sh.q_out[n0 + i] = s_stage[i];
+                it++;
+                break;
+            }
+            // push: natural row n goes to rank n / S, slot me * S + (n - owner * S)
+            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) {
+                const int n = n0 + i, o = n / S;
+                ((double *)(sh.win[o] + sh.xbuf_off))[(size_t)me * S + (n - o * S)] = s_stage[i];
+            }
+            xbarrier(sh, gridDim.x, 2 * it + 1, false);
+            // owner update of this CTA's share of the slice
+            double dm = 0;
+            for (int n = u0 + threadIdx.x; n < u1; n += EM_BLOCK) {
+                double Q = 0;
+                for (int r = 0; r < R; r++) Q += __ldcg(xb + (size_t)r * S + (n - own0));      // rank order: deterministic
+                const double2 ra = p.m.rsa_nat[n];
+                const double th = __ldcg(th_nat + n);
+                const double nn = ra.x + th * Q;
+                const double thn = nn / ra.y;
+                dm = fmax(dm, fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * nn));
+                for (int r = 0; r < R; r++) ((double *)(sh.win[r] + sh.theta_off))[n] = thn;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            if (lane == 0) sm_red[warp] = dm;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double bm = 0;
+                for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
+                atomicMax(sh.dloc, (unsigned long long)__double_as_longlong(bm));
+            }
+            xbarrier(sh, gridDim.x, 2 * it + 2, true);
+            d = 0;
+            for (int r = 0; r < R; r++) d = fmax(d, __longlong_as_double((long long)*((volatile unsigned long long *)(sh.win[me] + 2048) + r)));
+            it++;
+            if (p.stop_on_conv && d <= 1.0) break;
+        }
+        if (sh.fused)        // the permuted copy the output kernels read
+            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = __ldcg(th_nat + n0 + s_noff[i]);
+    }
+    while (it < p.max_iter && MODE == 0) {
         TRACE(0);
         double dm = 0;
         if (producer) {
@@ -611,7 +782,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                         const int4 tile = s_et[c.y - 1 - tk];
                         const int *tids = staged ? buf + sh + (tile.z - c.z) : p.m.e_tid + (uint32_t)tile.z;
                         const uint32_t *rfl = staged ? (const uint32_t *)(buf + ro + sr + (tile.x - jbase)) : p.m.e_R + tile.x;
-                        e_tile(p, v, tile, tids, rfl, lane);
+                        e_tile<false>(p, v, tile, tids, rfl, lane);
                     }
                 }
                 __syncwarp();
@@ -642,14 +813,14 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                     const int ebase = sg * (CH_BYTES / 4) + sh - c.z;
                     for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
                         const int4 itm = s_mi[c.x + tk];
-                        dm = fmax(dm, f_m_item(p, f, itm, IdxS{sm_dyn}, ebase + itm.z, lane));
+                        dm = fmax(dm, f_m_item<false>(p, f, itm, IdxS{sm_dyn}, ebase + itm.z, lane));
                     }
                 } else {
                     int *buf = (int *)(sm_dyn + sg * CH_BYTES);
                     for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
                         const int4 itm = s_mi[c.x + tk];
                         const int *ent = staged ? buf + sh + (itm.z - c.z) : p.m.m_cls + (uint32_t)itm.z;
-                        dm = fmax(dm, m_item(p, v, itm, ent, lane));
+                        dm = fmax(dm, m_item<false>(p, v, itm, ent, lane));
                     }
                 }
                 __syncwarp();
@@ -685,17 +856,20 @@ int em_query_occupancy(emsar_ctx *ctx)
     const char *e = getenv("EMSAR_EM_SMEM_KB");
     if (e && atoi(e) > 0 && atoi(e) * 1024 < smem) smem = atoi(e) * 1024;
     smem &= ~255;
-    CU(cudaFuncSetAttribute(k_em_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(k_em_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<true>, EM_BLOCK, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int nb = 0, nb2 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<1>, EM_BLOCK, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_em_persistent<2>, EM_BLOCK, smem));
+    if (nb2 < nb) nb = nb2;
     if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM (%d bytes of shared memory)", smem); return EMSAR_ERR_CUDA; }
     ctx->em_blocks_per_sm = 1;
     ctx->em_smem_bytes = smem;
     return EMSAR_OK;
 }
 
-int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out)
+int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out, bool fused)
 {
     emsar_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -708,8 +882,22 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     p.iters_done = (int *)(ctx->d_barrier + 8);
     p.final_delta = (double *)(ctx->d_barrier + 10);
     p.trace = s->d_trace;
-    p.q_out = s->sharded ? s->d_qpart : nullptr;
-    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + (size_t)s->m.B * 128, st));
+    memset(&p.sh, 0, sizeof(p.sh));
+    if (s->sharded) {
+        if (!s->m.direct) { emsar_set_err("sharded samples need the direct EM mode"); return EMSAR_ERR_UNSUPPORTED; }
+        p.sh.rank = ctx->rank; p.sh.nranks = ctx->nranks;
+        p.sh.S = (int)win_slice_rows(s->m.P > 0 ? s->m.P : 1, ctx->nranks);
+        p.sh.fused = fused ? 1 : 0;
+        p.sh.q_out = s->d_qpart;
+        p.sh.dloc = (unsigned long long *)(ctx->d_barrier + 12);
+        p.sh.xbar = ctx->d_barrier + 64 + (size_t)s->m.B * 32;
+        if (fused) {
+            for (int r = 0; r < ctx->nranks; r++) p.sh.win[r] = (unsigned char *)ctx->peer_win[r];
+            p.sh.theta_off = (long long)WIN_HDR_BYTES;
+            p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 8 * (size_t)ctx->win_rows);
+        }
+    }
+    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)s->m.B * 128, st));
     const int grid = s->m.B;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -737,8 +925,9 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
-    if (s->m.direct) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<true>, p));
-    else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<false>, p));
+    if (s->sharded) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<2>, p));
+    else if (s->m.direct) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<1>, p));
+    else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<0>, p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     int it = 0; double fd = 0;
@@ -764,23 +953,23 @@ __global__ void k_fill_double2(double *p, int64_t n, double v)
 extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long long *out, int *n_blocks)
 {
     if (!s || !s->prepared) return EMSAR_ERR_STATE;
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     const int B = s->m.B;
     TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64 + 1600));
     CU(cudaMemset(s->d_trace, 0, (size_t)B * 64 + 512 + 12800));
     int it = 0; double fd = 0, ms = 0;
-    int rc = em_launch(s, iters, 0, &it, &fd, &ms);
+    int rc = em_launch(s, iters, 0, &it, &fd, &ms, false);
     if (rc == EMSAR_OK) {
         CU(cudaMemcpy(out, s->d_trace, (size_t)B * 64 + 512 + 12800, cudaMemcpyDeviceToHost));
         *n_blocks = B;
     }
-    cudaFree(s->d_trace);
+    dev_free(s->d_trace);
     s->d_trace = nullptr;
     return rc;
 }
 
-// ---- sharded mode: theta update from the all-reduced per-transcript sums (identical on every rank) ----
-__global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_t, const double2 *__restrict__ row_RsA, const double *__restrict__ qsum,
+// ---- sharded mode, NCCL path: theta update from the all-reduced per-row sums (identical on every rank) ----
+__global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_n, const double2 *__restrict__ row_RsA, const double *__restrict__ qsum,
                                  double *__restrict__ theta, double eps_abs, double eps_rel, unsigned long long *dmax)
 {
     __shared__ double red[8];
@@ -789,7 +978,7 @@ __global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_t, c
     if (p < P) {
         const double2 ra = row_RsA[p];
         const double th = theta[p];
-        const double n = ra.x + th * qsum[row_t[p]];
+        const double n = ra.x + th * qsum[row_n[p]];
         const double thn = n / ra.y;
         theta[p] = thn;
         d = fabs(thn - th) * ra.y / (eps_abs + eps_rel * n);
@@ -805,33 +994,56 @@ __global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_t, c
     }
 }
 
+// fused path: theta in natural order into this rank's window before the kernel starts
+__global__ void k_theta_to_nat(int32_t P, const int32_t *__restrict__ row_n, const double *__restrict__ theta, double *__restrict__ th_nat)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) th_nat[row_n[p]] = theta[p];
+}
+
+// One sample whose active classes are range-sharded over the ranks (BASELINE.json configs[2]).
+//  * fused path (default): ONE persistent kernel per rank; the per-iteration all-reduce of the per-row sums runs inside it
+//    over NVLink peer memory (reduce-scatter by pushes, owner update, all-gather by pushes; two cross-GPU barriers).
+//  * NCCL path (EMSAR_SHARD_MODE=nccl, or when peer memory cannot be mapped): one kernel pass, ncclAllReduce of the fp64
+//    sums, update kernel, host check of the convergence measure - per iteration.
 static int em_run_sharded(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out)
 {
     emsar_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    const int32_t T = s->index->T, P = s->m.P;
+    const int32_t P = s->m.P;
     if (!s->m.direct) { emsar_set_err("sharded samples need the direct EM mode"); return EMSAR_ERR_UNSUPPORTED; }
-    if (!s->d_qpart) { TRY(dev_alloc(&s->d_qpart, 2 * (size_t)T + 2)); }
-    CU(cudaMemsetAsync(s->d_qpart, 0, (2 * (size_t)T + 2) * 8, st));
-    unsigned long long *d_dmax = (unsigned long long *)(s->d_qpart + 2 * (size_t)T);
+    TRY(comm_window_ensure(ctx, P));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, st));
     int it = 0; double d = INFINITY;
-    while (it < max_iter) {
-        int one = 0; double fd = 0;
-        TRY(em_launch(s, 1, 0, &one, &fd, nullptr));                 // E-phase + partial M-phase of this rank's classes
-        TRY(comm_allreduce_f64(ctx, s->d_qpart, s->d_qpart + T, (size_t)T));
-        CU(cudaMemsetAsync(d_dmax, 0, 8, st));
-        if (P > 0) { k_update_sharded<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_t, s->m.row_RsA, s->d_qpart + T, s->m.theta, s->opts.eps_abs, s->opts.eps_rel, d_dmax); LAUNCHED(ctx); }
-        unsigned long long bits = 0;
-        CU(cudaMemcpyAsync(&bits, d_dmax, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        memcpy(&d, &bits, 8);
-        it++;
-        if (stop_on_conv && d <= 1.0) break;
+    if (ctx->win_state == 1) {
+        CU(cudaMemsetAsync(ctx->win, 0, WIN_HDR_BYTES, st));
+        if (P > 0) { k_theta_to_nat<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_n, s->m.theta, (double *)((char *)ctx->win + WIN_HDR_BYTES)); LAUNCHED(ctx); }
+        TRY(comm_barrier(ctx));                  // every window is reset before any rank's kernel can write into it
+        CU(cudaEventRecord(e0, st));
+        TRY(em_launch(s, max_iter, stop_on_conv, &it, &d, nullptr, true));
+        CU(cudaEventRecord(e1, st));
+    } else {
+        if (!s->d_qpart) { TRY(dev_alloc(&s->d_qpart, 2 * (size_t)s->index->T + 2)); }
+        CU(cudaMemsetAsync(s->d_qpart, 0, (2 * (size_t)s->index->T + 2) * 8, st));
+        double *d_sum = s->d_qpart + s->index->T;
+        unsigned long long *d_dmax = (unsigned long long *)(s->d_qpart + 2 * (size_t)s->index->T);
+        CU(cudaEventRecord(e0, st));
+        while (it < max_iter) {
+            int one = 0; double fd = 0;
+            TRY(em_launch(s, 1, 0, &one, &fd, nullptr, false));          // E-phase + partial M-phase of this rank's classes
+            TRY(comm_allreduce_f64(ctx, s->d_qpart, d_sum, (size_t)(P > 0 ? P : 1)));
+            CU(cudaMemsetAsync(d_dmax, 0, 8, st));
+            if (P > 0) { k_update_sharded<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_n, s->m.row_RsA, d_sum, s->m.theta, s->opts.eps_abs, s->opts.eps_rel, d_dmax); LAUNCHED(ctx); }
+            unsigned long long bits = 0;
+            CU(cudaMemcpyAsync(&bits, d_dmax, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            memcpy(&d, &bits, 8);
+            it++;
+            if (stop_on_conv && d <= 1.0) break;
+        }
+        CU(cudaEventRecord(e1, st));
     }
-    CU(cudaEventRecord(e1, st));
     CU(cudaStreamSynchronize(st));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
@@ -847,7 +1059,7 @@ extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t st
 {
     CHECK_ARG(s, "emsar_sample_em_run: NULL sample");
     if (!s->prepared) { emsar_set_err("emsar_sample_em_run: call emsar_sample_prepare first"); return EMSAR_ERR_STATE; }
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     const int P = s->m.P;
     if (reset_theta) {
         if (P > 0) { k_fill_double2<<<(unsigned)((P + 255) / 256), 256, 0, s->ctx->stream>>>(s->m.theta, P, 1.0); LAUNCHED(s->ctx); }
@@ -856,7 +1068,7 @@ extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t st
     if (max_iter <= 0) max_iter = s->opts.max_iter;
     int it = 0; double fd = 0, ms = 0;
     if (s->sharded) TRY(em_run_sharded(s, max_iter, stop_on_conv, &it, &fd, &ms));
-    else TRY(em_launch(s, max_iter, stop_on_conv, &it, &fd, &ms));
+    else TRY(em_launch(s, max_iter, stop_on_conv, &it, &fd, &ms, false));
     s->n_iter += it; s->final_delta = fd; s->em_ms += ms;
     if (iters_done) *iters_done = it;
     if (final_delta) *final_delta = fd;
@@ -978,7 +1190,7 @@ static int class_eval(emsar_sample *s, const double *d_fpkm, double *d_expected,
     CU(cudaMemcpyAsync(&ll, d_out, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(d_part);
+    dev_free(d_part);
     if (bad || ll < NEAR_LOWEST) ll = NEAR_LOWEST;
     if (loglik) *loglik = ll;
     return EMSAR_OK;
@@ -989,7 +1201,7 @@ extern "C" int emsar_sample_finalize(emsar_sample *s, emsar_solve_out *out)
     CHECK_ARG(s && out, "emsar_sample_finalize: NULL argument");
     if (!s->prepared) { emsar_set_err("emsar_sample_finalize: sample not prepared"); return EMSAR_ERR_STATE; }
     emsar_index *ix = s->index; emsar_ctx *ctx = s->ctx; cudaStream_t st = ctx->stream;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     const int32_t T = ix->T;
     const int nb = (T + FIN_BLOCK - 1) / FIN_BLOCK;
     char *buf = nullptr;
@@ -1020,7 +1232,7 @@ extern "C" int emsar_sample_finalize(emsar_sample *s, emsar_solve_out *out)
     CU(cudaMemcpyAsync(&toti, d_toti, 8, cudaMemcpyDeviceToHost, st));
     double ll = 0;
     int rc = class_eval(s, d_fpkm, nullptr, &ll);      // synchronizes the stream
-    cudaFree(buf);
+    dev_free(buf);
     if (rc != EMSAR_OK) return rc;
     out->n_iter = s->n_iter; out->final_delta = s->final_delta; out->loglik = ll;
     out->total_ireadcount = toti; out->total_readcount = s->N; out->eumacut = s->eumacut; out->max_sid = s->max_sid;
@@ -1042,7 +1254,7 @@ extern "C" int emsar_sample_theta_get(emsar_sample *s, double *theta)
     CHECK_ARG(s && theta, "emsar_sample_theta_get: NULL argument");
     if (!s->prepared) { emsar_set_err("emsar_sample_theta_get: sample not prepared"); return EMSAR_ERR_STATE; }
     emsar_index *ix = s->index; emsar_ctx *ctx = s->ctx; cudaStream_t st = ctx->stream;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     double *d_fpkm = nullptr;
     TRY(dev_alloc(&d_fpkm, (size_t)ix->T));
     const double nscale = (double)s->N / 1E6, p10 = pow(10, s->delta);
@@ -1050,7 +1262,7 @@ extern "C" int emsar_sample_theta_get(emsar_sample *s, double *theta)
     LAUNCHED(ctx);
     CU(cudaMemcpyAsync(theta, d_fpkm, (size_t)ix->T * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(d_fpkm);
+    dev_free(d_fpkm);
     return EMSAR_OK;
 }
 
@@ -1059,7 +1271,7 @@ extern "C" int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, doubl
     CHECK_ARG(s, "emsar_sample_segments_get: NULL sample");
     if (!s->prepared) { emsar_set_err("emsar_sample_segments_get: sample not prepared"); return EMSAR_ERR_STATE; }
     emsar_index *ix = s->index; emsar_ctx *ctx = s->ctx; cudaStream_t st = ctx->stream;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     if (adjEUMA) CU(cudaMemcpyAsync(adjEUMA, s->d_adj, (size_t)ix->C * 8, cudaMemcpyDeviceToHost, st));
     if (expected) {
         double *d_fpkm = nullptr, *d_ex = nullptr;
@@ -1072,7 +1284,7 @@ extern "C" int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, doubl
         if (rc != EMSAR_OK) return rc;
         CU(cudaMemcpyAsync(expected, d_ex, (size_t)ix->C * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        cudaFree(d_fpkm); cudaFree(d_ex);
+        dev_free(d_fpkm); dev_free(d_ex);
     }
     CU(cudaStreamSynchronize(st));
     if (set_id) {
@@ -1085,13 +1297,13 @@ extern "C" int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, doubl
 extern "C" int emsar_sample_end(emsar_sample *s)
 {
     if (!s) return EMSAR_OK;
-    cudaSetDevice(s->ctx->device);
+    ctx_use(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->d_R); cudaFree(s->d_hist); cudaFree(s->d_flags);
-    cudaFree(s->d_rd_ptr); cudaFree(s->d_rd_tid); cudaFree(s->d_rd_fl);
-    cudaFree(s->d_Wf); cudaFree(s->d_adj); cudaFree(s->d_amodel); cudaFree(s->d_in_model);
-    cudaFree(s->d_A); cudaFree(s->d_Rs); cudaFree(s->d_iE); cudaFree(s->d_lone); cudaFree(s->d_pos);
-    cudaFree(s->d_state); cudaFree(s->d_pack); cudaFree(s->d_mcls); cudaFree(s->d_halo); cudaFree(s->d_chunks); cudaFree(s->d_qpart);
+    dev_free(s->d_R); dev_free(s->d_hist); dev_free(s->d_flags);
+    dev_free(s->d_rd_ptr); dev_free(s->d_rd_tid); dev_free(s->d_rd_fl);
+    dev_free(s->d_Wf); dev_free(s->d_adj); dev_free(s->d_amodel); dev_free(s->d_in_model);
+    dev_free(s->d_A); dev_free(s->d_Rs); dev_free(s->d_iE); dev_free(s->d_lone); dev_free(s->d_pos);
+    dev_free(s->d_state); dev_free(s->d_pack); dev_free(s->d_mcls); dev_free(s->d_halo); dev_free(s->d_chunks); dev_free(s->d_qpart);
     delete s;
     return EMSAR_OK;
 }

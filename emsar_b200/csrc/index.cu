@@ -58,8 +58,8 @@ int index_build_hash(emsar_index *ix, const std::vector<uint8_t> &insertable)
     CU(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ix->hash_inserted = (int64_t)cnt;
-    cudaFree(d_ins);
-    cudaFree(d_cnt);
+    dev_free(d_ins);
+    dev_free(d_cnt);
     return EMSAR_OK;
 }
 
@@ -134,7 +134,7 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
     }
     ix->kseg = kseg;
     ix->device_bytes = 0;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     // ---- host copies (32-bit) ----
     ix->h_cls_off.resize((size_t)C + 1);
     for (int64_t c = 0; c <= C; c++) ix->h_cls_off[(size_t)c] = (uint32_t)d->class_ptr[c];
@@ -207,10 +207,10 @@ extern "C" int emsar_index_info_get(const emsar_index *ix, emsar_index_info *inf
 extern "C" int emsar_index_destroy(emsar_index *ix)
 {
     if (!ix) return EMSAR_OK;
-    cudaSetDevice(ix->ctx->device);
+    ctx_use(ix->ctx);
     cudaStreamSynchronize(ix->ctx->stream);
-    cudaFree(ix->d_cls_off); cudaFree(ix->d_cls_tid); cudaFree(ix->d_euma); cudaFree(ix->d_has_node);
-    cudaFree(ix->d_txm_off); cudaFree(ix->d_txm_cid); cudaFree(ix->d_hash); cudaFree(ix->d_kseg_cid0); cudaFree(ix->d_kseg_k);
+    dev_free(ix->d_cls_off); dev_free(ix->d_cls_tid); dev_free(ix->d_euma); dev_free(ix->d_has_node);
+    dev_free(ix->d_txm_off); dev_free(ix->d_txm_cid); dev_free(ix->d_hash); dev_free(ix->d_kseg_cid0); dev_free(ix->d_kseg_k);
     delete ix;
     return EMSAR_OK;
 }

@@ -196,13 +196,14 @@ __global__ void k_sort_keys(int32_t P, int B, const int32_t *__restrict__ row0, 
 
 __global__ void k_apply_perm(int32_t P, const int32_t *__restrict__ perm, const int32_t *__restrict__ tn, const uint32_t *__restrict__ degn,
                              const double *__restrict__ Rs, const double *__restrict__ A, int32_t *__restrict__ pos,
-                             uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA, int32_t *__restrict__ row_t)
+                             uint32_t *__restrict__ degp, double2 *__restrict__ row_RsA, int32_t *__restrict__ row_n, double2 *__restrict__ rsa_nat)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const int n = perm[p], t = tn[n];
     pos[t] = p;
-    row_t[p] = t;
+    row_n[p] = n;
+    rsa_nat[n] = make_double2(Rs[t], A[t]);
     degp[p] = degn[n];
     row_RsA[p] = make_double2(Rs[t], A[t]);
 }
@@ -582,7 +583,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     emsar_index *ix = s->index;
     emsar_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    CU(cudaSetDevice(ctx->device));
+    TRY(ctx_use(ctx));
     emsar_solve_opts o;
     memset(&o, 0, sizeof(o));
     if (opts_in) o = *opts_in;
@@ -732,7 +733,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     size_t theta_bytes = (((size_t)(P > 0 ? P : 1) * 8 + 255) / 256) * 256;
     size_t q_bytes = (((size_t)(C_a > 0 ? C_a : 1) * 8 + 255) / 256) * 256;
     if (theta_bytes + q_bytes > s->state_bytes) {
-        if (s->d_state) CU(cudaFree(s->d_state));
+        if (s->d_state) dev_free(s->d_state);
         s->d_state = nullptr;
         double *p = nullptr;
         TRY(dev_alloc(&p, (theta_bytes + q_bytes) / 8));
@@ -750,9 +751,9 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     const size_t e_tiles_max = (size_t)C_a + (size_t)n_cells + 1;
     const size_t m_items_max = (size_t)P / 32 + 2 * (size_t)B + std::min<size_t>((size_t)P, (size_t)ix->nnz_multi / M_LONG + 1) + 64;   // slices + long rows
     auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
-    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + rnd((size_t)(P + 1) * 16) + rnd((size_t)(P + 1) * 4) + rnd(m_items_max * 16) + 12 * rnd((size_t)(B + 1) * 4);
+    size_t arena1 = rnd(e_ints_max * 4) + rnd((size_t)(C_a + 1) * 4) + rnd(e_tiles_max * 16) + 2 * rnd((size_t)(P + 1) * 16) + rnd((size_t)(P + 1) * 4) + rnd(m_items_max * 16) + 12 * rnd((size_t)(B + 1) * 4);
     if (arena1 > s->pack_bytes) {
-        if (s->d_pack) CU(cudaFree(s->d_pack));
+        if (s->d_pack) dev_free(s->d_pack);
         s->d_pack = nullptr;
         char *p = nullptr;
         TRY(dev_alloc(&p, arena1));
@@ -764,7 +765,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.e_R = arena_take<uint32_t>(ac, (size_t)C_a + 1);
     m.e_tiles = arena_take<int4>(ac, e_tiles_max);
     m.row_RsA = arena_take<double2>(ac, (size_t)P + 1);
-    m.row_t = arena_take<int32_t>(ac, (size_t)P + 1);
+    m.row_n = arena_take<int32_t>(ac, (size_t)P + 1);
+    m.rsa_nat = arena_take<double2>(ac, (size_t)P + 1);
     m.m_items = arena_take<int4>(ac, m_items_max);
     m.blk_row0 = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_cls0 = arena_take<int32_t>(ac, (size_t)B + 1);
@@ -793,7 +795,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         LAUNCHED(ctx);
         CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_key, d_key2, d_val, d_perm, P, 0, 44, st));
         ctx->launches += 4;
-        k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA, m.row_t);
+        k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, d_pos, d_degp, m.row_RsA, m.row_n, m.rsa_nat);
         LAUNCHED(ctx);
     }
     k_block_items_count<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, m.blk_row0, d_degp, d_nlong, d_nitems, d_ngroups);
@@ -855,7 +857,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     const unsigned int n_ue = h_cnt[0] ? h_cnt[1] : 0, n_um = h_cnt[2] ? h_cnt[3] : 0;
     if ((size_t)(n_ue + n_um + 2) * 4 > s->halo_bytes) {
-        if (s->d_halo) CU(cudaFree(s->d_halo));
+        if (s->d_halo) dev_free(s->d_halo);
         s->d_halo = nullptr;
         int32_t *p = nullptr;
         TRY(dev_alloc(&p, (size_t)n_ue + n_um + 64));
@@ -998,7 +1000,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     {
         const size_t nb = (h_ech.size() + h_mch.size() + 3) * 16 + 4 * (size_t)(B + 1) * 4 + ((size_t)n_etiles + n_mitems + 2) * 4 + 2048;
         if (nb > s->chunk_bytes) {
-            if (s->d_chunks) CU(cudaFree(s->d_chunks));
+            if (s->d_chunks) dev_free(s->d_chunks);
             s->d_chunks = nullptr;
             char *p = nullptr;
             TRY(dev_alloc(&p, nb + (nb >> 2)));
@@ -1027,7 +1029,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         CU(cudaStreamSynchronize(st));     // the host vectors go out of scope below
     }
     if ((size_t)(m_ints + 1) * 4 > s->mcls_bytes) {
-        if (s->d_mcls) CU(cudaFree(s->d_mcls));
+        if (s->d_mcls) dev_free(s->d_mcls);
         s->d_mcls = nullptr;
         int32_t *p = nullptr;
         TRY(dev_alloc(&p, (size_t)m_ints + (m_ints >> 3) + 64));
@@ -1089,7 +1091,7 @@ extern "C" int emsar_sample_wf_get(emsar_sample *s, double *Wf)
 {
     CHECK_ARG(s && Wf, "emsar_sample_wf_get: NULL argument");
     if (!s->prepared) { emsar_set_err("emsar_sample_wf_get: sample not prepared"); return EMSAR_ERR_STATE; }
-    CU(cudaSetDevice(s->ctx->device));
+    TRY(ctx_use(s->ctx));
     CU(cudaMemcpyAsync(Wf, s->d_Wf, (size_t)s->index->nF * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream));
     return EMSAR_OK;

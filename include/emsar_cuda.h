@@ -162,13 +162,20 @@ int emsar_sample_end(emsar_sample *s);
 /* -------- one sample sharded over several GPUs (BASELINE.json configs[2]) ------------------------
  * One process (or thread) per GPU, each with its own context holding the SAME index. The multi-tid classes that are
  * active in the sample are cut into nnz-balanced contiguous ranges, one per rank; every EM iteration each rank computes
- * the per-transcript sums of its classes and an NCCL all-reduce (fp64, T values) over NVLink adds them up; theta stays
- * replicated and bit-identical on every rank. The reference has no counterpart (single process, emsar_main.c).
+ * the per-transcript sums of its classes and an all-reduce (fp64, one value per participating transcript) over NVLink adds
+ * them up; theta stays replicated and bit-identical on every rank. The all-reduce runs INSIDE the persistent EM kernel over
+ * peer memory (pushes to the owner of a transcript slice, owner update, pushes of the new theta; two cross-GPU barriers per
+ * iteration, no host involvement), or, where peer memory cannot be mapped, as one ncclAllReduce per iteration.
+ * The reference has no counterpart (single process, emsar_main.c).
  * The 128-byte id is NCCL's unique id: rank 0 makes it, the caller ships it to the other ranks (bench.py and the tests
  * use torch.distributed for that), then every rank calls emsar_comm_init. */
 int emsar_comm_unique_id(uint8_t id[128]);
 int emsar_comm_init(emsar_ctx *ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
 int emsar_comm_destroy(emsar_ctx *ctx);
+/* peer_memory: 1 = the fused kernel exchanges the sums over NVLink peer memory (CUDA IPC between processes, peer access inside
+ * one process), -1 = peer memory could not be mapped (or EMSAR_SHARD_MODE=nccl): ncclAllReduce per iteration, 0 = not decided
+ * yet (decided collectively at the first sharded solve) */
+int emsar_comm_info(emsar_ctx *ctx, int32_t *rank, int32_t *nranks, int32_t *peer_memory);
 /* each rank counted a different slice of the read groups: sum ReadCount / FraglengthCounts over the ranks (exact: integers) */
 int emsar_sample_counts_allreduce(emsar_sample *s);
 /* contiguous ranges of equal weight: out[r] .. out[r+1] is rank r's range of the n items (host-only helper, no device needed) */

@@ -15,6 +15,7 @@ from emsar_b200.api import Context, Index  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    mode = sys.argv[1] if len(sys.argv) > 1 else "fused"
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     idx = synth.make_index(T=3000, n_multi=20000, alpha=1.8, kmax=120, seed=31, module_cap=400)
@@ -34,6 +35,9 @@ def main():
     s.close()
     ok = True
     msg = ""
+    pm = ctx.comm_info()["peer_memory"]
+    if pm != (-1 if mode == "nccl" else 1):
+        ok, msg = False, f"expected the {mode} path, peer_memory={pm}"
     # reference: the whole sample on one GPU (every rank does it: also checks that all ranks hold the same answer)
     s1 = ix.sample()
     s1.count(reads.read_ptr, reads.read_tid, reads.read_fraglen)
@@ -62,7 +66,7 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MGPU {'OK' if flag.item() == 1.0 else 'FAIL'} world={world} iters={r['n_iter']}/{r1['n_iter']} em_ms={r['em_ms']:.1f}/{r1['em_ms']:.1f} "
+        print(f"MGPU {'OK' if flag.item() == 1.0 else 'FAIL'} mode={mode} peer_memory={pm} world={world} iters={r['n_iter']}/{r1['n_iter']} em_ms={r['em_ms']:.1f}/{r1['em_ms']:.1f} "
               f"max_rel={float(rel.max()):.2e} nnz_a/rank={st['nnz_a']} {msg}", flush=True)
     ix.close(); ctx.close()
     dist.destroy_process_group()

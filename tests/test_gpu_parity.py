@@ -161,3 +161,37 @@ def test_unsupported_and_bad_inputs(ctx):
     if not np.array_equal(bad.class_tid, idx.class_tid):
         with pytest.raises(EmsarError):
             Index(ctx, bad)
+
+
+# The EM kernel has three data paths: everything of a CTA resident in shared memory (the usual case at test sizes), the
+# overflow path (halo rows / classes and q that did not get a slot are read from the L2-resident global copies) and the
+# TMA-pipelined index streams. The two rarer ones are forced here with the tuning knobs the library reads from the environment.
+VARIANTS = {
+    "overflow_12k": {"EMSAR_EM_SMEM_KB": "12"},
+    "overflow_24k": {"EMSAR_EM_SMEM_KB": "24"},
+    "pipelined": {"EMSAR_EM_MODE": "pipe"},
+    "pipelined_small": {"EMSAR_EM_MODE": "pipe", "EMSAR_EM_SMEM_KB": "80"},
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("name", ["se_longk", "hubs"])
+def test_solve_kernel_variants(built, monkeypatch, variant, name):
+    from emsar_b200.api import Context
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    idx, reads = _make(name)
+    o = _oracle().quantify(idx, reads)
+    c = Context(0)
+    try:
+        ix = Index(c, idx)
+        s = ix.sample()
+        s.count(reads.read_ptr, reads.read_tid, reads.read_fraglen)
+        r = s.solve()
+        s.close(); ix.close()
+    finally:
+        c.close()
+    assert abs(r["n_iter"] - o["n_iter"]) <= 1, (r["n_iter"], o["n_iter"])
+    rel = np.abs(r["fpkm"] - o["fpkm"]) / np.maximum(np.abs(o["fpkm"]), 1e-300)
+    reads_abs = np.abs(r["ireadcount"] - o["ireadcount"])
+    assert np.all((rel <= 1e-9) | (reads_abs <= 1e-9)), (rel.max(), reads_abs.max())

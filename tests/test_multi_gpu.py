@@ -12,13 +12,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_class_sharded_sample_two_gpus(built):
+@pytest.mark.parametrize("mode", ["fused", "fused_overflow", "nccl"])
+def test_class_sharded_sample_two_gpus(built, mode):
+    """fused: the all-reduce runs inside the persistent kernel over peer memory; nccl: ncclAllReduce per iteration."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
-           os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    n = min(4, torch.cuda.device_count()) if mode == "fused" else 2
+    env = dict(os.environ)
+    if mode == "nccl":
+        env["EMSAR_SHARD_MODE"] = "nccl"
+    if mode == "fused_overflow":
+        env["EMSAR_EM_SMEM_KB"] = "12"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
