@@ -123,6 +123,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converge", action="store_true", help="skip the one-off run to convergence (samples/min)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg (e2e is then null)")
+    ap.add_argument("--shard", default="samples", choices=["samples", "classes"],
+                    help="N>1: independent samples per GPU (-M list, weak scaling, the default) or ONE sample whose classes are "
+                         "range-sharded over the GPUs with the per-iteration all-reduce (BASELINE.json configs[2], strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -139,8 +142,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from emsar_b200.api import Context, Index
 
-    idx, reads, gen_s = make_workload(args.workload, seed=1000 + rank)
+    by_class = args.shard == "classes" and world > 1
+    idx, reads, gen_s = make_workload(args.workload, seed=1000 if by_class else 1000 + rank)
     ctx = Context(local)
+    if by_class:
+        ctx.comm_init_torch()
+        n_all = len(reads.read_fraglen)                      # every rank counts its slice of the read groups
+        lo, hi = n_all * rank // world, n_all * (rank + 1) // world
+        base = int(reads.read_ptr[lo])
+        reads.read_tid = reads.read_tid[base:int(reads.read_ptr[hi])]
+        reads.read_ptr = reads.read_ptr[lo:hi + 1] - base
+        reads.read_fraglen = reads.read_fraglen[lo:hi]
     ix = Index(ctx, idx)
     # pinned host copies of this rank's read lists (the e2e leg copies them every step)
     h_ptr = torch.from_numpy(reads.read_ptr).pin_memory()
@@ -148,9 +160,14 @@ def main():
     h_fl = torch.from_numpy(reads.read_fraglen).pin_memory()
     h2d_bytes = h_ptr.numel() * 8 + h_tid.numel() * 4 + h_fl.numel() * 4
     # resident sample for the device-timed leg
+    def load(s_):
+        s_.count(h_ptr, h_tid, h_fl)
+        if by_class:
+            s_.counts_allreduce()
+        s_.prepare(sharded=by_class)
+
     smp = ix.sample()
-    smp.count(h_ptr, h_tid, h_fl)
-    smp.prepare()
+    load(smp)
     st = smp.model_stats()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -189,8 +206,7 @@ def main():
     # ---- e2e leg: host buffers through the C ABI ----
     def step_e2e():
         s = ix.sample()
-        s.count(h_ptr, h_tid, h_fl)
-        s.prepare()
+        load(s)
         it, fd, ms = s.em_run(max_iter=args.em_iters, stop_on_conv=False)
         r = s.finalize()
         s.close()
@@ -220,7 +236,9 @@ def main():
         c0 = time.perf_counter()
         s = ix.sample()
         s.count(h_ptr, h_tid, h_fl)
-        r = s.solve()
+        if by_class:
+            s.counts_allreduce()
+        r = s.solve(sharded=by_class)
         s.close()
         c1 = time.perf_counter()
         conv = {"seconds": c1 - c0, "n_iter": int(r["n_iter"]), "final_delta": float(r["final_delta"]), "em_ms": float(r["em_ms"]),
@@ -231,15 +249,21 @@ def main():
         tt = torch.tensor([wall, e_wall, t_em], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         wall, e_wall, t_em = tt.tolist()
-        ww = torch.tensor([iters_done, e_iters, launches], dtype=torch.float64, device="cuda")
+        ww = torch.tensor([iters_done, e_iters, launches, st["bytes_per_iter"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        iters_tot, e_iters_tot, launches_tot = ww.tolist()
+        iters_tot, e_iters_tot, launches_tot, bytes_all = ww.tolist()
+        if by_class:                       # one sample: the ranks iterate together
+            iters_tot, e_iters_tot = iters_done, e_iters
     else:
-        iters_tot, e_iters_tot, launches_tot = iters_done, e_iters, launches
+        iters_tot, e_iters_tot, launches_tot, bytes_all = iters_done, e_iters, launches, st["bytes_per_iter"]
 
     if rank == 0:
         peak, peak_src = peaks()
         achieved = st["bytes_per_iter"] * iters_done / t_em / 1e9 if t_em > 0 else 0.0
+        if by_class:                       # the whole sample's bytes per iteration against the N GPUs' bandwidth
+            achieved = bytes_all * iters_done / t_em / 1e9 if t_em > 0 else 0.0
+            peak *= world
+            st = dict(st, bytes_per_iter=int(bytes_all), rank0_bytes_per_iter=st["bytes_per_iter"])
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import oracle
@@ -255,10 +279,12 @@ def main():
         line = {
             "metric": "em_iterations_per_sec", "value": iters_tot / wall, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "T": idx.T, "C": idx.C, "reads_per_sample": int(len(reads.read_fraglen)),
-                       "C_a": st["C_a"], "nnz_a": st["nnz_a"], "em_iters_per_step": args.em_iters, "samples": world,
-                       "parallelism": f"sample-sharded x{world} (-M), no collective",
+            "scaling": "strong" if by_class else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "T": idx.T, "C": idx.C, "reads_per_sample": int(len(reads.read_fraglen)) * (world if by_class else 1),
+                       "C_a": st["C_a"], "nnz_a": st["nnz_a"], "em_iters_per_step": args.em_iters, "samples": 1 if by_class else world,
+                       "parallelism": (f"one sample, classes range-sharded x{world}, per-iteration fp64 all-reduce over NVLink "
+                                       f"({'inside the EM kernel, peer memory' if ctx.comm_info()['peer_memory'] == 1 else 'ncclAllReduce'})")
+                       if by_class else f"sample-sharded x{world} (-M), no collective",
                        "l2": "flushed between steps (256 MiB memset); iterations inside a step reuse L2 as the production loop does"},
             "e2e": None if args.no_e2e else {"value": e_iters_tot / e_wall, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * e_wall / args.steps},

@@ -134,7 +134,7 @@ void comm_window_release(emsar_ctx *ctx)
         ctx->peer_win[r] = nullptr; ctx->peer_ipc[r] = false;
     }
     if (ctx->win) cudaFree(ctx->win);
-    ctx->win = nullptr; ctx->win_rows = 0; ctx->win_state = 0;
+    ctx->win = nullptr; ctx->win_rows = 0; ctx->win_state = 0; ctx->win_bytes = 0;
     cudaGetLastError();
 }
 
@@ -152,7 +152,8 @@ int comm_window_ensure(emsar_ctx *ctx, int64_t rows)
     CU(cudaStreamSynchronize(st));
     comm_window_release(ctx);
     const int64_t cap = rows + (rows >> 3) + 1024;
-    const size_t bytes = WIN_HDR_BYTES + 8 * (size_t)cap + 8 * (size_t)(win_slice_rows(cap, R) * R + 64);
+    const size_t bytes = WIN_HDR_BYTES + 16 * (size_t)cap + 16 * (size_t)(win_slice_rows(cap, R) * R + 64);
+    ctx->win_bytes = bytes;
     WinInfo mine;
     memset(&mine, 0, sizeof(mine));
     mine.pid = (long long)getpid(); mine.device = ctx->device;

@@ -82,9 +82,14 @@ struct emsar_ctx {
     void *peer_win[EMSAR_MAX_RANKS];   // every rank's window as seen from this device (peer_win[rank] == win)
     bool peer_ipc[EMSAR_MAX_RANKS];    // mapping opened with cudaIpcOpenMemHandle (must be closed)
     int64_t win_rows;          // capacity: participating rows
+    size_t win_bytes;
     int win_state;             // 0 = not tried, 1 = usable, -1 = peer memory unavailable (NCCL path only)
 };
-constexpr size_t WIN_HDR_BYTES = 4096;      // flags: rank j's flag at byte 128*j; dmax: rank j's delta at byte 2048 + 8*j
+// Window layout (bytes): [dm: 2 parities x nranks x WIN_MAX_CTAS slots][theta: win_rows slots][xbuf: nranks x S slots].
+// A slot is 16 bytes: two 64-bit words {low half of the double | tag << 32}, {high half | tag << 32}. Each word is written
+// with one 8-byte store, so a reader that polls until both tags match has the value - no fence, no separate flag.
+constexpr int WIN_MAX_CTAS = 256;
+constexpr size_t WIN_HDR_BYTES = 2 * (size_t)EMSAR_MAX_RANKS * WIN_MAX_CTAS * 16;
 __host__ __device__ __forceinline__ int64_t win_slice_rows(int64_t rows, int nranks) { return (rows + nranks - 1) / nranks; }
 
 struct emsar_index {
@@ -133,6 +138,7 @@ struct EmModel {
     int32_t *e_res, *m_res;        // per E tile / M item: int offset of its resident copy in the CTA's shared-memory index cache, -1 = none
     int32_t *blk_res_ints;         // [B] ints of the CTA's resident index cache
     int32_t direct;                // 1: direct mode (index cache, no staging pipeline)
+    int32_t all_local;             // 1: every halo row / class and every q of every CTA has a shared-memory slot
     int32_t *blk_nres;     // [B]   classes of the CTA whose q lives in shared memory (slot nres holds 0.0: padding target)
     // halo: distinct remote rows / classes a CTA references; copied into its shared memory at the start of each phase
     int32_t *blk_hr0, *blk_hc0;   // [B+1] ranges in halo_rows / halo_cls

@@ -31,10 +31,10 @@ struct EmParams {
         int rank, nranks;          // nranks == 0: not sharded
         int S;                     // rows per owner slice: rank r updates the natural rows [r*S, min(P, (r+1)*S))
         int fused;                 // 1: all-reduce inside the kernel over peer memory; 0: one pass, sums to q_out (NCCL path)
-        unsigned char *win[EMSAR_MAX_RANKS];   // every rank's window (comm.cu): flags | dmax | theta_nat | xbuf
+        unsigned char *win[EMSAR_MAX_RANKS];   // every rank's window (comm.cu): dm | theta | xbuf, 16-byte tagged slots
         long long theta_off, xbuf_off;         // byte offsets inside a window
-        unsigned long long *dloc;  // this rank's delta of the slice it owns (reduced over its CTAs)
-        unsigned *xbar;            // arrival flag per CTA for the cross-GPU barriers, 128 bytes apart
+        unsigned tag0;             // tags of this launch start above tag0 (windows are zeroed before every launch)
+        int *abort_flag;           // set when a wait ran out of patience (a peer died): every wait then falls through
         double *q_out;             // NCCL path: [P] partial row sums in natural order
     } sh;
 };
@@ -67,8 +67,6 @@ struct BlockView {
     const int4 *sm_mitems;     // this CTA's M items
     double *sm_stage;          // sharded mode: partial row sums of this CTA in natural order (reuses the {Rs,A} area)
     const int *sm_noff;        // sharded mode: natural offset (inside the CTA's range) of every row slot
-    const double *g_theta;     // fused sharded mode: theta in natural order (this rank's window) ...
-    const int *g_rown;         // ... and the permuted row -> natural index table (NULL otherwise)
     int row0, nrows, cls0, nres, nhr, nhc;
 };
 
@@ -76,7 +74,7 @@ struct BlockView {
 template <bool SH>
 __device__ __forceinline__ double load_theta(const EmParams &p, const BlockView &v, int enc)
 {
-    if (SH && enc < 0 && v.g_rown) return __ldcg(v.g_theta + v.g_rown[~enc]);   // fused sharded mode: the live copy is in natural order
+    if (SH && enc < 0) return __ldcg(p.m.theta + ~enc);      // sharded overflow path: the permuted global copy is rewritten every iteration
     const double *ptr = enc >= 0 ? v.sm_theta + enc : p.m.theta + ~enc;
     return *ptr;
 }
@@ -407,45 +405,28 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
     return d;
 }
 
-// ---- cross-GPU barrier of the fused sharded kernel ---------------------------------------------------------------
-// Every CTA of every rank arrives; nobody leaves before all have. Two levels: (1) the CTAs of a rank publish their
-// arrival in local flags (release.gpu, after a system-scope fence that covers the CTA's remote stores); (2) CTA 0 collects
-// them and then stores the generation into flag[rank] of EVERY rank's window (its own included) over NVLink; (3) every
-// CTA polls the nranks flags of its OWN window (local memory, acquire.sys). Remote stores issued before the barrier are
-// therefore visible in the target's memory to everything the target does after it. `send_delta`: CTA 0 also forwards the
-// rank's reduced convergence measure (dloc) to slot `rank` of every window's dmax array, ahead of the flag.
-__device__ __forceinline__ void xbarrier(const EmParams::Shard &sh, unsigned nblocks, unsigned gen, bool send_delta)
+// ---- tagged 16-byte slots: the exchange primitive of the fused sharded kernel ----------------------------------------
+// (the LL idea of NCCL applied to fp64): the writer splits the double into two 32-bit halves and stores each together with
+// the tag of the iteration in ONE aligned 8-byte word; the reader polls the two words until both carry the tag it expects.
+// A value and its "ready" signal therefore travel in the same store: no system-scope fence, no barrier, and no assumption
+// about the order in which different stores cross NVLink.
+constexpr unsigned LL_PATIENCE = 1u << 22;      // polls (~ seconds) before a wait gives up and raises the abort flag
+__device__ __forceinline__ void ll_store(unsigned char *slot, double v, unsigned tag)
 {
-    __shared__ unsigned long long s_dl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(sh.xbar + blockIdx.x * 32), "r"(gen) : "memory");
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffULL) | t, w1 = (b >> 32) | t;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned char *slot, unsigned tag, int *abort_flag)
+{
+    unsigned long long w0, w1;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if ((++spins & 1023u) == 0 && (*((volatile int *)abort_flag) != 0 || spins >= LL_PATIENCE)) { *((volatile int *)abort_flag) = 1; break; }
     }
-    if (blockIdx.x == 0) {
-        for (unsigned i = threadIdx.x; i < nblocks; i += blockDim.x) {
-            unsigned cur;
-            do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(sh.xbar + i * 32) : "memory"); } while ((int)(cur - gen) < 0);
-        }
-        __syncthreads();
-        if (send_delta && threadIdx.x == 0) {
-            s_dl = *((volatile unsigned long long *)sh.dloc);
-            *((volatile unsigned long long *)sh.dloc) = 0ULL;          // next use: after every CTA has left this barrier
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < sh.nranks) {
-            unsigned char *w = sh.win[threadIdx.x];
-            if (send_delta) *((volatile unsigned long long *)(w + 2048) + sh.rank) = s_dl;
-            __threadfence_system();
-            asm volatile("st.release.sys.u32 [%0], %1;" ::"l"((unsigned *)(w + 128 * sh.rank)), "r"(gen) : "memory");
-        }
-    }
-    if ((int)threadIdx.x < sh.nranks) {
-        const unsigned *f = (const unsigned *)(sh.win[sh.rank] + 128 * threadIdx.x);
-        unsigned cur;
-        do { asm volatile("ld.acquire.sys.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory"); } while ((int)(cur - gen) < 0);
-    }
-    __syncthreads();
+    return __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
 }
 
 // MODE 0: TMA-pipelined index streams; 1: direct (resident index cache + L2); 2: direct, class-sharded over several GPUs
@@ -483,7 +464,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
     v.sm_theta = (double *)(sm_dyn + pl.off_theta);
     v.sm_q = (double *)(sm_dyn + pl.off_q);
     v.sm_etiles = s_et; v.sm_mitems = s_mi; v.sm_rsa = s_rsa;
-    v.sm_stage = nullptr; v.sm_noff = nullptr; v.g_theta = nullptr; v.g_rown = nullptr;
+    v.sm_stage = nullptr; v.sm_noff = nullptr;
     SmView f;
     f.base = sm_dyn; f.theta8 = pl.off_theta / 8; f.q8 = pl.off_q / 8; f.rsa16 = pl.off_rsa / 16;
     f.row0 = v.row0; f.cls0 = v.cls0; f.nres = v.nres;
@@ -636,36 +617,66 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         if (p.stop_on_conv && d <= 1.0) break;
     }
     if (SHARDED) {
-        // ---- class-sharded sample: this rank's classes only. Per iteration: E-phase -> grid barrier -> partial row sums,
-        // pushed (coalesced, natural order) into the xbuf of the rank that owns the row -> cross-GPU barrier -> the owner adds
-        // the nranks partials in rank order, updates theta of its slice and stores it into EVERY rank's theta_nat ->
-        // cross-GPU barrier (carries the convergence measure). theta is bit-identical on all ranks by construction.
+        // ---- class-sharded sample: this rank's classes only. Per iteration: [theta of my rows + halo rows from my window] ->
+        // E-phase -> grid barrier -> partial row sums, pushed (coalesced, natural order, tagged slots) into the xbuf of the rank
+        // that owns the row -> the owner adds the nranks partials in rank order as they arrive, updates theta of its slice and
+        // pushes it into EVERY rank's theta window -> every owner CTA pushes its convergence measure to every rank; all CTAs
+        // read all of them (the only all-to-all wait of the iteration). theta is bit-identical on all ranks by construction.
+        // Hazards: a slot is rewritten one iteration later; by then its readers are done because (a) a CTA pushes partials of
+        // iteration i+1 only after the wait at the end of iteration i, which every owner CTA joins after reading its xbuf
+        // slots, and (b) an owner rewrites theta only after partials of iteration i+1 arrived from every rank, i.e. after that
+        // rank's E -> M grid barrier, which every reader of theta(i) has passed. The dm slots alternate by parity.
         const EmParams::Shard &sh = p.sh;
         const int R = sh.nranks, S = sh.S, me = sh.rank;
-        const double *th_nat = (const double *)(sh.win[me] + sh.theta_off);       // local copy of the full theta, natural order
-        const double *xb = (const double *)(sh.win[me] + sh.xbuf_off);           // partials pushed to me: xb[src * S + i]
+        const unsigned char *my_theta = sh.win[me] + sh.theta_off;
+        const unsigned char *my_xbuf = sh.win[me] + sh.xbuf_off;
         const int n0 = v.row0;                                                   // the CTA's rows are a contiguous natural range
         int *s_noff = (int *)(s_rsa + 0) + 2 * v.nrows;                          // second half of the {Rs,A} area
         double *s_stage = (double *)s_rsa;
         v.sm_stage = s_stage; v.sm_noff = s_noff;
-        v.g_theta = th_nat; v.g_rown = sh.fused ? p.m.row_n : nullptr;
+       
         f.noff4 = pl.off_rsa / 4 + 2 * v.nrows;
         for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) s_noff[i] = p.m.row_n[v.row0 + i] - n0;
-        for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) s_hrl[i] = p.m.row_n[s_hrl[i]];        // halo rows: natural index
+        if (sh.fused)
+            for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) s_hrl[i] = p.m.row_n[s_hrl[i]];    // halo rows: natural index
         __syncthreads();
         // the slice this rank owns, cut over the CTAs
         const int own0 = me * S, own1 = min(p.m.P, own0 + S);
         const int per = (max(own1 - own0, 0) + (int)gridDim.x - 1) / (int)gridDim.x;
         const int u0 = min(own1, own0 + b * per), u1 = min(own1, u0 + per);
+        // the convergence measure of iteration j: the maximum over every owner CTA of every rank (slots alternate by parity)
+        auto read_dm = [&](int j) -> double {
+            const unsigned tg = sh.tag0 + (unsigned)j + 1u;
+            double x = 0;
+            for (int i = threadIdx.x; i < R * (int)gridDim.x; i += EM_BLOCK) {
+                const int r = i / (int)gridDim.x, c = i - r * (int)gridDim.x;
+                x = fmax(x, ll_load(sh.win[me] + 16 * ((size_t)((j & 1) * R + r) * WIN_MAX_CTAS + c), tg, sh.abort_flag));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+            __syncthreads();
+            if (lane == 0) sm_red[warp] = x;
+            __syncthreads();
+            x = 0;
+            for (int w = 0; w < EM_WARPS; w++) x = fmax(x, sm_red[w]);
+            __syncthreads();
+            return x;
+        };
+        bool stopped = false;
         while (it < p.max_iter) {
+            const unsigned tag = sh.tag0 + (unsigned)it + 1u;             // theta(it) and partials / dm of iteration it carry it
+            TRACE(0);
             if (sh.fused) {
-                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = __ldcg(th_nat + n0 + s_noff[i]);
-                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(th_nat + s_hrl[i]);
+                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = ll_load(my_theta + 16 * (size_t)(n0 + s_noff[i]), tag, sh.abort_flag);
+                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = ll_load(my_theta + 16 * (size_t)s_hrl[i], tag, sh.abort_flag);
+                if (!p.m.all_local)    // overflow path (some CTA): halo rows without a slot are read from the permuted global copy during the E-phase
+                    for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = v.sm_theta[i];
             } else {
-                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + p.m.halo_rows[hr0 + i]);
+                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = __ldcg(p.m.theta + s_hrl[i]);
             }
             if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
-            __syncthreads();
+            if (sh.fused && !p.m.all_local) grid_barrier(p.bar, gridDim.x, 2 * it + 1);  // the global copy is complete before anybody gathers from it
+            else __syncthreads();
             if (all_local) {
                 for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
                     const int ti = n_et - 1 - tk;
@@ -682,7 +693,23 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                     e_tile<true>(p, v, tile, p.m.e_tid + (uint32_t)tile.z, p.m.e_R + tile.x, lane);
                 }
             }
-            grid_barrier(p.bar, gridDim.x, it + 1);
+            TRACE(1);
+            if (sh.fused && it > 0) {
+                // The delta of the PREVIOUS iteration is read here, not at its end: by now the values have arrived, so the only
+                // all-to-all dependency of an iteration costs nothing. theta has not changed since (this E-phase only wrote q),
+                // so stopping here leaves exactly the state of the iteration that met the rule. Every CTA of every rank takes
+                // the same decision from the same numbers.
+                d = read_dm(it - 1);
+                if (*((volatile int *)sh.abort_flag) != 0) {
+                    // leaving early: park this CTA's barrier flag at the last generation so that no CTA still running waits for it
+                    if (threadIdx.x == 0) asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(p.bar + blockIdx.x * 32), "r"(0x7fffffffu) : "memory");
+                    stopped = true;
+                    break;
+                }
+                if (p.stop_on_conv && d <= 1.0) { stopped = true; break; }
+            }
+            grid_barrier(p.bar, gridDim.x, 2 * it + 2);
+            TRACE(2);
             for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
             __syncthreads();
             if (all_local) {
@@ -708,38 +735,40 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             // push: natural row n goes to rank n / S, slot me * S + (n - owner * S)
             for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) {
                 const int n = n0 + i, o = n / S;
-                ((double *)(sh.win[o] + sh.xbuf_off))[(size_t)me * S + (n - o * S)] = s_stage[i];
+                ll_store(sh.win[o] + sh.xbuf_off + 16 * ((size_t)me * S + (n - o * S)), s_stage[i], tag);
             }
-            xbarrier(sh, gridDim.x, 2 * it + 1, false);
-            // owner update of this CTA's share of the slice
+            TRACE(3);
+            // owner update of this CTA's share of the slice, as the partials arrive
             double dm = 0;
             for (int n = u0 + threadIdx.x; n < u1; n += EM_BLOCK) {
                 double Q = 0;
-                for (int r = 0; r < R; r++) Q += __ldcg(xb + (size_t)r * S + (n - own0));      // rank order: deterministic
+                for (int r = 0; r < R; r++) Q += ll_load(my_xbuf + 16 * ((size_t)r * S + (n - own0)), tag, sh.abort_flag);   // rank order: deterministic
                 const double2 ra = p.m.rsa_nat[n];
-                const double th = __ldcg(th_nat + n);
+                const double th = ll_load(my_theta + 16 * (size_t)n, tag, sh.abort_flag);
                 const double nn = ra.x + th * Q;
                 const double thn = nn / ra.y;
                 dm = fmax(dm, fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * nn));
-                for (int r = 0; r < R; r++) ((double *)(sh.win[r] + sh.theta_off))[n] = thn;
+                for (int r = 0; r < R; r++) ll_store(sh.win[r] + sh.theta_off + 16 * (size_t)n, thn, tag + 1);
             }
+            TRACE(4);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
             if (lane == 0) sm_red[warp] = dm;
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if ((int)threadIdx.x < R) {
                 double bm = 0;
                 for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
-                atomicMax(sh.dloc, (unsigned long long)__double_as_longlong(bm));
+                ll_store(sh.win[threadIdx.x] + 16 * ((size_t)((it & 1) * R + me) * WIN_MAX_CTAS + b), bm, tag);
             }
-            xbarrier(sh, gridDim.x, 2 * it + 2, true);
-            d = 0;
-            for (int r = 0; r < R; r++) d = fmax(d, __longlong_as_double((long long)*((volatile unsigned long long *)(sh.win[me] + 2048) + r)));
+            TRACE(5);
             it++;
-            if (p.stop_on_conv && d <= 1.0) break;
         }
-        if (sh.fused)        // the permuted copy the output kernels read
-            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = __ldcg(th_nat + n0 + s_noff[i]);
+        if (sh.fused && it > 0 && !stopped) d = read_dm(it - 1);         // ran out of iterations: the last delta is still in flight
+        if (sh.fused && *((volatile int *)sh.abort_flag) != 0) d = INFINITY;
+        if (sh.fused) {      // the permuted copy the output kernels read
+            const unsigned tag = sh.tag0 + (unsigned)it + 1u;
+            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = ll_load(my_theta + 16 * (size_t)(n0 + s_noff[i]), tag, sh.abort_flag);
+        }
     }
     while (it < p.max_iter && MODE == 0) {
         TRACE(0);
@@ -889,12 +918,13 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
         p.sh.S = (int)win_slice_rows(s->m.P > 0 ? s->m.P : 1, ctx->nranks);
         p.sh.fused = fused ? 1 : 0;
         p.sh.q_out = s->d_qpart;
-        p.sh.dloc = (unsigned long long *)(ctx->d_barrier + 12);
-        p.sh.xbar = ctx->d_barrier + 64 + (size_t)s->m.B * 32;
+        p.sh.abort_flag = (int *)(ctx->d_barrier + 14);
+        p.sh.tag0 = 0;
         if (fused) {
+            if (s->m.B > WIN_MAX_CTAS) { emsar_set_err("sharded EM: more than %d CTAs", WIN_MAX_CTAS); return EMSAR_ERR_UNSUPPORTED; }
             for (int r = 0; r < ctx->nranks; r++) p.sh.win[r] = (unsigned char *)ctx->peer_win[r];
             p.sh.theta_off = (long long)WIN_HDR_BYTES;
-            p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 8 * (size_t)ctx->win_rows);
+            p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 16 * (size_t)ctx->win_rows);
         }
     }
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)s->m.B * 128, st));
@@ -931,9 +961,12 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     int it = 0; double fd = 0;
+    int aborted = 0;
     CU(cudaMemcpyAsync(&it, p.iters_done, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&fd, p.final_delta, 8, cudaMemcpyDeviceToHost, st));
+    if (s->sharded) CU(cudaMemcpyAsync(&aborted, p.sh.abort_flag, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (aborted) { emsar_set_err("sharded EM: a wait on peer memory timed out (a rank died or the ranks disagree on the call sequence)"); return EMSAR_ERR_COMM; }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (iters_done) *iters_done = it;
@@ -950,15 +983,17 @@ __global__ void k_fill_double2(double *p, int64_t n, double v)
 
 // tuning aid (not part of include/emsar_cuda.h): run `iters` iterations and return, per CTA, the globaltimer stamps (ns) of
 // the last iteration: [0] E start, [1] E end, [2] after barrier 1, [3] M end, [4] after barrier 2
+extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
+                                   int32_t *iters_done, double *final_delta, double *elapsed_ms);
 extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long long *out, int *n_blocks)
 {
     if (!s || !s->prepared) return EMSAR_ERR_STATE;
     TRY(ctx_use(s->ctx));
     const int B = s->m.B;
     TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64 + 1600));
-    CU(cudaMemset(s->d_trace, 0, (size_t)B * 64 + 512 + 12800));
+    CU(cudaMemsetAsync(s->d_trace, 0, (size_t)B * 64 + 512 + 12800, s->ctx->stream));
     int it = 0; double fd = 0, ms = 0;
-    int rc = em_launch(s, iters, 0, &it, &fd, &ms, false);
+    int rc = emsar_sample_em_run(s, iters, 0, 0, &it, &fd, &ms);       // the sharded runner when the sample is sharded
     if (rc == EMSAR_OK) {
         CU(cudaMemcpy(out, s->d_trace, (size_t)B * 64 + 512 + 12800, cudaMemcpyDeviceToHost));
         *n_blocks = B;
@@ -995,10 +1030,10 @@ __global__ void k_update_sharded(int32_t P, const int32_t *__restrict__ row_n, c
 }
 
 // fused path: theta in natural order into this rank's window before the kernel starts
-__global__ void k_theta_to_nat(int32_t P, const int32_t *__restrict__ row_n, const double *__restrict__ theta, double *__restrict__ th_nat)
+__global__ void k_theta_to_nat(int32_t P, const int32_t *__restrict__ row_n, const double *__restrict__ theta, unsigned char *__restrict__ th_slots, unsigned tag)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < P) th_nat[row_n[p]] = theta[p];
+    if (p < P) ll_store(th_slots + 16 * (size_t)row_n[p], theta[p], tag);
 }
 
 // One sample whose active classes are range-sharded over the ranks (BASELINE.json configs[2]).
@@ -1017,8 +1052,8 @@ static int em_run_sharded(emsar_sample *s, int max_iter, int stop_on_conv, int *
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     int it = 0; double d = INFINITY;
     if (ctx->win_state == 1) {
-        CU(cudaMemsetAsync(ctx->win, 0, WIN_HDR_BYTES, st));
-        if (P > 0) { k_theta_to_nat<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_n, s->m.theta, (double *)((char *)ctx->win + WIN_HDR_BYTES)); LAUNCHED(ctx); }
+        CU(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, st));          // every tag back to 0: the tags of a launch start at 1
+        if (P > 0) { k_theta_to_nat<<<(P + 255) / 256, 256, 0, st>>>(P, s->m.row_n, s->m.theta, (unsigned char *)ctx->win + WIN_HDR_BYTES, 1u); LAUNCHED(ctx); }
         TRY(comm_barrier(ctx));                  // every window is reset before any rank's kernel can write into it
         CU(cudaEventRecord(e0, st));
         TRY(em_launch(s, max_iter, stop_on_conv, &it, &d, nullptr, true));

@@ -957,6 +957,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     }
     const bool direct = !(getenv("EMSAR_EM_MODE") && !strcmp(getenv("EMSAR_EM_MODE"), "pipe"));
     std::vector<int32_t> h_eres((size_t)n_etiles + 1, -1), h_mres((size_t)n_mitems + 1, -1), h_resints(B + 1, 0);
+    int32_t grid_all_local = 1;
     for (int b = 0; b < B; b++) {
         // what of a CTA's state gets a shared-memory slot: its rows (always), then halo rows, then its classes, then halo classes
         const int nrows = h_row0[b + 1] - h_row0[b];
@@ -968,6 +969,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         int r = std::max(0, std::min(h_cls0[b + 1] - h_cls0[b], left / 8)); left -= r * 8;
         int c = std::max(0, std::min(h_hc0[b + 1] - h_hc0[b], left / 12)); left -= c * 12;
         h_nhr[b] = a; h_nres[b] = r; h_nhc[b] = c;
+        if (a != h_hr0[b + 1] - h_hr0[b] || r != h_cls0[b + 1] - h_cls0[b] || c != h_hc0[b + 1] - h_hc0[b]) grid_all_local = 0;
         if (direct && left > 64) {
             // resident index cache: the index data of the items with the longest dependent chains stays in shared memory for
             // the whole kernel (it never changes); everything else is read from L2 every iteration
@@ -1016,6 +1018,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         m.e_res = arena_take<int32_t>(cc, (size_t)n_etiles + 1);
         m.m_res = arena_take<int32_t>(cc, (size_t)n_mitems + 1);
         m.direct = direct ? 1 : 0;
+        m.all_local = grid_all_local;
         CU(cudaMemcpyAsync(m.blk_res_ints, h_resints.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(m.e_res, h_eres.data(), ((size_t)n_etiles + 1) * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(m.m_res, h_mres.data(), ((size_t)n_mitems + 1) * 4, cudaMemcpyHostToDevice, st));
