@@ -45,6 +45,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, em_iters):
+    """DRAM bytes of one k_em_persistent launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t.get("workload") != workload:
+            return None
+        return int(t["dram_bytes_per_launch"] + t.get("dram_bytes_per_extra_iteration", 0) * em_iters)
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -289,7 +300,11 @@ def main():
             "e2e": None if args.no_e2e else {"value": e_iters_tot / e_wall, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * e_wall / args.steps},
             "gpu_launches": int(launches_tot),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None if world > 1 else measured_traffic(args.workload, args.em_iters),
+                         "traffic_note": "DRAM bytes per launch (ncu, profiles/traffic.json); algorithmic bytes per launch = bytes_per_iter x "
+                                         "em_iters_per_step: the packed model is L2-resident after the first iteration",
+                         "algorithmic_bytes_per_launch": int(st["bytes_per_iter"]) * int(args.em_iters),
                          "peak_source": peak_src, "kernel": "k_em_persistent", "bytes_per_iter": st["bytes_per_iter"],
                          "us_per_iter": 1e6 * t_em / max(iters_done, 1)},
             "cpu_baseline": cpu,
