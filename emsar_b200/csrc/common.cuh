@@ -202,6 +202,9 @@ struct emsar_sample {
     void *d_chunks;        // chunk tables
     size_t chunk_bytes;
     unsigned long long *d_trace;   // tuning aid
+    void *d_slots;         // barrier-free EM kernel: tagged 16-byte slots of theta [P+1] and q [C_a+1]
+    size_t slots_bytes;
+    unsigned slot_tag;     // tags handed out so far (every launch takes a fresh range, so the slots are never cleared)
     double *d_qpart;       // sharded mode, NCCL path: [2*P] partial / reduced per-row sums in natural order
     bool sharded;
     EmModel m;

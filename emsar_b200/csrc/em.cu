@@ -26,6 +26,10 @@ struct EmParams {
     int *iters_done;
     double *final_delta;
     unsigned long long *trace;     // optional [B*8] globaltimer stamps of the last iteration (tuning aid)
+    // barrier-free single-GPU kernel (k_em_persistent<3>): halo theta / q travel through tagged slots instead of grid barriers
+    unsigned char *th_slots, *q_slots, *dm_slots;    // [P], [C_a], [2 * B] 16-byte tagged slots
+    unsigned df_tag0;
+    int *df_abort;
     // class-sharded sample (k_em_persistent<2> only): this rank holds a class range; per-row sums are exchanged in natural order
     struct Shard {
         int rank, nranks;          // nranks == 0: not sharded
@@ -264,12 +268,37 @@ __device__ __forceinline__ double m_item(const EmParams &p, const BlockView &v, 
     return d;
 }
 
+// ---- tagged 16-byte slots: the exchange primitive of the fused sharded kernel ----------------------------------------
+// (the LL idea of NCCL applied to fp64): the writer splits the double into two 32-bit halves and stores each together with
+// the tag of the iteration in ONE aligned 8-byte word; the reader polls the two words until both carry the tag it expects.
+// A value and its "ready" signal therefore travel in the same store: no system-scope fence, no barrier, and no assumption
+// about the order in which different stores cross NVLink.
+constexpr unsigned LL_PATIENCE = 1u << 22;      // polls (~ seconds) before a wait gives up and raises the abort flag
+__device__ __forceinline__ void ll_store(unsigned char *slot, double v, unsigned tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffULL) | t, w1 = (b >> 32) | t;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned char *slot, unsigned tag, int *abort_flag)
+{
+    unsigned long long w0, w1;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if ((++spins & 1023u) == 0 && (*((volatile int *)abort_flag) != 0 || spins >= LL_PATIENCE)) { *((volatile int *)abort_flag) = 1; break; }
+    }
+    return __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
+}
+
 // ---- fast path: the chunk is staged and every index of this CTA is a shared-memory slot. All addresses are 32-bit
 // offsets from the CTA's dynamic shared memory, so the loops are LDS + LDS.64 + DADD with almost no address arithmetic.
 struct SmView {
     unsigned char *base;   // sm_dyn
     int theta8, q8, rsa16; // element offsets of theta / q / {Rs,A} inside sm_dyn
     int noff4;             // sharded mode: int offset of the slot -> natural offset table (second half of the {Rs,A} area)
+    unsigned tag;          // data-flow mode: tag of the current iteration
     int row0, cls0, nres;
 };
 #define S32(v) ((const int *)(v).base)
@@ -278,15 +307,19 @@ struct SmView {
 struct IdxS { const unsigned char *base; __device__ __forceinline__ int operator()(int i) const { return ((const int *)base)[i]; } };
 struct IdxG { const int32_t *g; __device__ __forceinline__ int operator()(int i) const { return __ldg(g + i); } };
 
+template <int DF>
 __device__ __forceinline__ void f_store_q(const EmParams &p, const SmView &v, int j, uint32_t rflag, double s)
 {
     const double r = (double)(rflag & 0x7fffffffu);
     const double val = s > 0 ? r / s : 0.0;
     S64(v)[v.q8 + (j - v.cls0)] = val;              // fast path: every owned class is resident
-    if (rflag & 0x80000000u) p.m.q[j] = val;        // a row of another CTA reads it
+    if (rflag & 0x80000000u) {                      // a row of another CTA reads it
+        if (DF) ll_store(p.q_slots + 16 * (size_t)j, val, v.tag);
+        else p.m.q[j] = val;
+    }
 }
 
-template <int K, int G, class IT, class IR>
+template <int K, int G, int DF, class IT, class IR>
 __device__ __forceinline__ void f_etile_small(const EmParams &p, const SmView &v, int4 tile, IT T_, IR R_, int ti, int ri, int lane)
 {
     int t[K * G];
@@ -303,18 +336,18 @@ __device__ __forceinline__ void f_etile_small(const EmParams &p, const SmView &v
         double s = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) s += x[g * K + j];       // sequential member order
-        if (g * 32 + lane < tile.y) f_store_q(p, v, tile.x + g * 32 + lane, rf[g], s);
+        if (g * 32 + lane < tile.y) f_store_q<DF>(p, v, tile.x + g * 32 + lane, rf[g], s);
     }
 }
 
-template <class IT, class IR>
+template <int DF = 0, class IT, class IR>
 __device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int4 tile, IT T_, IR R_, int ti, int ri, int lane)
 {
     const int steps = tile.w & 0xfff, lg = (tile.w >> 12) & 0xf;
     if (lg == 0) {
-        if (steps == 2) { f_etile_small<2, 4>(p, v, tile, T_, R_, ti, ri, lane); return; }
-        if (steps == 3) { f_etile_small<3, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
-        if (steps == 4) { f_etile_small<4, 2>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (steps == 2) { f_etile_small<2, 4, DF>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (steps == 3) { f_etile_small<3, 2, DF>(p, v, tile, T_, R_, ti, ri, lane); return; }
+        if (steps == 4) { f_etile_small<4, 2, DF>(p, v, tile, T_, R_, ti, ri, lane); return; }
     }
     // G = 1 << lg lanes per class; step j of all 32 lanes is one 128-byte line
     const int cls = lane >> lg, G = 1 << lg;
@@ -341,23 +374,24 @@ __device__ __forceinline__ void f_e_tile(const EmParams &p, const SmView &v, int
     }
     for (; j < steps; j++) s += S64(v)[v.theta8 + T_(ti + j * 32)];
     for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (head) f_store_q(p, v, tile.x + cls, rf, s);
+    if (head) f_store_q<DF>(p, v, tile.x + cls, rf, s);
 }
 
-template <bool SH>
+template <int MD>
 __device__ __forceinline__ double f_m_update(const EmParams &p, const SmView &v, int slot, double Q)
 {
-    if (SH) { S64(v)[v.rsa16 * 2 + ((const int *)v.base)[v.noff4 + slot]] = Q; return 0.0; }   // stage = the {Rs,A} area (unused when sharded)
+    if (MD == 1) { S64(v)[v.rsa16 * 2 + ((const int *)v.base)[v.noff4 + slot]] = Q; return 0.0; }   // stage = the {Rs,A} area (unused when sharded)
     const double2 ra = ((const double2 *)v.base)[v.rsa16 + slot];
     const double th = S64(v)[v.theta8 + slot];
     const double n = ra.x + th * Q;
     const double thn = n / ra.y;
     S64(v)[v.theta8 + slot] = thn;
-    p.m.theta[v.row0 + slot] = thn;                 // write-through: halo readers and the final result
+    if (MD == 2) ll_store(p.th_slots + 16 * (size_t)(v.row0 + slot), thn, v.tag + 1);   // halo readers of the next iteration
+    else p.m.theta[v.row0 + slot] = thn;            // write-through: halo readers and the final result
     return fabs(thn - th) * ra.y / (p.eps_abs + p.eps_rel * n);
 }
 
-template <bool SH, class IT>
+template <int MD, class IT>
 __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, int4 it, IT T_, int ei, int lane)
 {
     const int len = it.w & 0x3fffffff;
@@ -382,7 +416,7 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
             Q += x0; Q += x1; Q += x2; Q += x3;          // ascending class order
         }
         for (; j < len; j++) Q += S64(v)[v.q8 + T_(ei + j * 32)];
-        if (lane < it.y) d = f_m_update<SH>(p, v, it.x + lane, Q);
+        if (lane < it.y) d = f_m_update<MD>(p, v, it.x + lane, Q);
     } else {
         const int n = it.y;
         const int mylen = lane < n ? T_(ei + lane) : 0;
@@ -400,36 +434,13 @@ __device__ __forceinline__ double f_m_item(const EmParams &p, const SmView &v, i
             for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
             if (lane == r) mine = s;
         }
-        if (lane < n) d = f_m_update<SH>(p, v, it.x + lane, mine);
+        if (lane < n) d = f_m_update<MD>(p, v, it.x + lane, mine);
     }
     return d;
 }
 
-// ---- tagged 16-byte slots: the exchange primitive of the fused sharded kernel ----------------------------------------
-// (the LL idea of NCCL applied to fp64): the writer splits the double into two 32-bit halves and stores each together with
-// the tag of the iteration in ONE aligned 8-byte word; the reader polls the two words until both carry the tag it expects.
-// A value and its "ready" signal therefore travel in the same store: no system-scope fence, no barrier, and no assumption
-// about the order in which different stores cross NVLink.
-constexpr unsigned LL_PATIENCE = 1u << 22;      // polls (~ seconds) before a wait gives up and raises the abort flag
-__device__ __forceinline__ void ll_store(unsigned char *slot, double v, unsigned tag)
-{
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
-    const unsigned long long w0 = (b & 0xffffffffULL) | t, w1 = (b >> 32) | t;
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
-}
-__device__ __forceinline__ double ll_load(const unsigned char *slot, unsigned tag, int *abort_flag)
-{
-    unsigned long long w0, w1;
-    unsigned spins = 0;
-    for (;;) {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
-        if ((++spins & 1023u) == 0 && (*((volatile int *)abort_flag) != 0 || spins >= LL_PATIENCE)) { *((volatile int *)abort_flag) = 1; break; }
-    }
-    return __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
-}
-
-// MODE 0: TMA-pipelined index streams; 1: direct (resident index cache + L2); 2: direct, class-sharded over several GPUs
+// MODE 0: TMA-pipelined index streams; 1: direct (resident index cache + L2); 2: direct, class-sharded over several GPUs;
+// 3: direct without grid barriers (halo theta / q and the convergence measure travel through tagged slots)
 template <int MODE>
 __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
 {
@@ -590,8 +601,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
                 const int4 itm = s_mi[tk];
                 const int ro = s_mres[tk];
-                if (ro >= 0) dm = fmax(dm, f_m_item<false>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
-                else dm = fmax(dm, f_m_item<false>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
+                if (ro >= 0) dm = fmax(dm, f_m_item<0>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
+                else dm = fmax(dm, f_m_item<0>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
             }
         } else {
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
@@ -615,6 +626,81 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         if (blockIdx.x == 0 && threadIdx.x == 0) p.dmax[(it + 1) & 1] = 0ULL;
         it++;
         if (p.stop_on_conv && d <= 1.0) break;
+    }
+    if (MODE == 3) {
+        // ---- barrier-free iteration (needs every halo row / class of every CTA in a shared-memory slot) --------------------
+        // A CTA depends only on the CTAs it shares classes with, so nothing here waits for the whole grid: the owner of a row /
+        // class publishes theta / q in a tagged 16-byte slot (ll_store) and the readers poll exactly the slots they need
+        // (ll_load) at the start of a phase. A slot is rewritten one iteration later; its readers are done by then because the
+        // dependency is symmetric: the owner b of class c needs theta of every member row of c before it can recompute q_c, and
+        // the owner n of such a row publishes that theta only after it has read q_c (and the same the other way round).
+        // The convergence measure of iteration i is read after the E-phase of iteration i+1 (theta has not changed by then, so
+        // stopping there leaves exactly the state of iteration i); that read is the only all-to-all dependency and bounds the
+        // drift between CTAs to one iteration, which is what lets the delta slots alternate by parity.
+        auto read_dm = [&](int j) -> double {
+            const unsigned tg = p.df_tag0 + (unsigned)j + 1u;
+            double x = 0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += EM_BLOCK)
+                x = fmax(x, ll_load(p.dm_slots + 16 * (size_t)((j & 1) * (int)gridDim.x + i), tg, p.df_abort));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+            __syncthreads();
+            if (lane == 0) sm_red[warp] = x;
+            __syncthreads();
+            x = 0;
+            for (int w = 0; w < EM_WARPS; w++) x = fmax(x, sm_red[w]);
+            __syncthreads();
+            return x;
+        };
+        bool stopped = false;
+        while (it < p.max_iter) {
+            const unsigned tag = p.df_tag0 + (unsigned)it + 1u;
+            f.tag = tag;
+            TRACE(0);
+            for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = ll_load(p.th_slots + 16 * (size_t)s_hrl[i], tag, p.df_abort);
+            if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
+            __syncthreads();
+            for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                const int ti = n_et - 1 - tk;
+                const int4 tile = s_et[ti];
+                const int ro = s_eres[ti];
+                if (ro >= 0) {
+                    const int cpb = 32 >> ((tile.w >> 12) & 0xf), ints = ((tile.y + cpb - 1) / cpb) * 32 * (tile.w & 0xfff);
+                    f_e_tile<1>(p, f, tile, IdxS{sm_dyn}, IdxS{sm_dyn}, res4 + ro, res4 + ro + ints, lane);
+                } else f_e_tile<1>(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+            }
+            TRACE(1);
+            if (it > 0) {
+                d = read_dm(it - 1);
+                if (*((volatile int *)p.df_abort) != 0 || (p.stop_on_conv && d <= 1.0)) { stopped = true; break; }
+            }
+            for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = ll_load(p.q_slots + 16 * (size_t)s_hcl[i], tag, p.df_abort);
+            __syncthreads();                       // the CTA's E-phase is complete and the halo q are in place
+            TRACE(2);
+            double dm = 0;
+            for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                const int4 itm = s_mi[tk];
+                const int ro = s_mres[tk];
+                if (ro >= 0) dm = fmax(dm, f_m_item<2>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane));
+                else dm = fmax(dm, f_m_item<2>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            if (lane == 0) sm_red[warp] = dm;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double bm = 0;
+                for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
+                ll_store(p.dm_slots + 16 * (size_t)((it & 1) * (int)gridDim.x + b), bm, tag);
+            }
+            TRACE(3);
+            TRACE(4);
+            it++;
+        }
+        if (it > 0 && !stopped) d = read_dm(it - 1);
+        if (*((volatile int *)p.df_abort) != 0) d = INFINITY;
+        __syncthreads();
+        for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = v.sm_theta[i];      // the copy the output kernels read
     }
     if (SHARDED) {
         // ---- class-sharded sample: this rank's classes only. Per iteration: [theta of my rows + halo rows from my window] ->
@@ -716,8 +802,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
                     const int4 itm = s_mi[tk];
                     const int ro = s_mres[tk];
-                    if (ro >= 0) f_m_item<true>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane);
-                    else f_m_item<true>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane);
+                    if (ro >= 0) f_m_item<1>(p, f, itm, IdxS{sm_dyn}, res4 + ro, lane);
+                    else f_m_item<1>(p, f, itm, IdxG{p.m.m_cls}, itm.z, lane);
                 }
             } else {
                 for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
@@ -842,7 +928,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                     const int ebase = sg * (CH_BYTES / 4) + sh - c.z;
                     for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
                         const int4 itm = s_mi[c.x + tk];
-                        dm = fmax(dm, f_m_item<false>(p, f, itm, IdxS{sm_dyn}, ebase + itm.z, lane));
+                        dm = fmax(dm, f_m_item<0>(p, f, itm, IdxS{sm_dyn}, ebase + itm.z, lane));
                     }
                 } else {
                     int *buf = (int *)(sm_dyn + sg * CH_BYTES);
@@ -888,14 +974,23 @@ int em_query_occupancy(emsar_ctx *ctx)
     CU(cudaFuncSetAttribute(k_em_persistent<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_em_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_em_persistent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_em_persistent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int nb = 0, nb2 = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_persistent<1>, EM_BLOCK, smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_em_persistent<2>, EM_BLOCK, smem));
+    if (nb2 < nb) nb = nb2;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_em_persistent<3>, EM_BLOCK, smem));
     if (nb2 < nb) nb = nb2;
     if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM (%d bytes of shared memory)", smem); return EMSAR_ERR_CUDA; }
     ctx->em_blocks_per_sm = 1;
     ctx->em_smem_bytes = smem;
     return EMSAR_OK;
+}
+
+__global__ void k_theta_to_slots(int32_t P, const double *__restrict__ theta, unsigned char *__restrict__ th_slots, unsigned tag)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) ll_store(th_slots + 16 * (size_t)p, theta[p], tag);
 }
 
 int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out, bool fused)
@@ -928,6 +1023,22 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
         }
     }
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)s->m.B * 128, st));
+    // barrier-free variant: whenever every CTA holds its whole halo in shared memory (EMSAR_EM_MODE=barrier keeps the grid barriers)
+    const char *em_mode = getenv("EMSAR_EM_MODE");
+    const bool dataflow = !s->sharded && s->m.direct && s->m.all_local && s->d_slots && !(em_mode && !strcmp(em_mode, "barrier"));
+    p.th_slots = p.q_slots = p.dm_slots = nullptr; p.df_tag0 = 0; p.df_abort = (int *)(ctx->d_barrier + 14);
+    if (dataflow) {
+        p.th_slots = (unsigned char *)s->d_slots;
+        p.q_slots = p.th_slots + 16 * (size_t)(s->m.P + 1);
+        p.dm_slots = (unsigned char *)ctx->d_barrier + 256 + 2 * (size_t)ctx->prop.multiProcessorCount * 128;     // behind the two flag arrays
+        if ((unsigned)(s->slot_tag + (unsigned)max_iter + 4u) < s->slot_tag) {         // tag wrap: start over from clean slots
+            CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
+            s->slot_tag = 0;
+        }
+        p.df_tag0 = s->slot_tag;
+        s->slot_tag += (unsigned)max_iter + 2u;
+        if (s->m.P > 0) { k_theta_to_slots<<<(s->m.P + 255) / 256, 256, 0, st>>>(s->m.P, s->m.theta, p.th_slots, p.df_tag0 + 1u); LAUNCHED(ctx); }
+    }
     const int grid = s->m.B;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -956,6 +1067,7 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
     if (s->sharded) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<2>, p));
+    else if (dataflow) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<3>, p));
     else if (s->m.direct) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<1>, p));
     else CU(cudaLaunchKernelEx(&cfg, k_em_persistent<0>, p));
     LAUNCHED(ctx);
@@ -964,8 +1076,9 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     int aborted = 0;
     CU(cudaMemcpyAsync(&it, p.iters_done, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&fd, p.final_delta, 8, cudaMemcpyDeviceToHost, st));
-    if (s->sharded) CU(cudaMemcpyAsync(&aborted, p.sh.abort_flag, 4, cudaMemcpyDeviceToHost, st));
+    if (s->sharded || dataflow) CU(cudaMemcpyAsync(&aborted, p.df_abort, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (aborted && dataflow) { emsar_set_err("EM kernel: a wait on a tagged slot timed out (internal error)"); return EMSAR_ERR_STATE; }
     if (aborted) { emsar_set_err("sharded EM: a wait on peer memory timed out (a rank died or the ranks disagree on the call sequence)"); return EMSAR_ERR_COMM; }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1338,7 +1451,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     dev_free(s->d_rd_ptr); dev_free(s->d_rd_tid); dev_free(s->d_rd_fl);
     dev_free(s->d_Wf); dev_free(s->d_adj); dev_free(s->d_amodel); dev_free(s->d_in_model);
     dev_free(s->d_A); dev_free(s->d_Rs); dev_free(s->d_iE); dev_free(s->d_lone); dev_free(s->d_pos);
-    dev_free(s->d_state); dev_free(s->d_pack); dev_free(s->d_mcls); dev_free(s->d_halo); dev_free(s->d_chunks); dev_free(s->d_qpart);
+    dev_free(s->d_state); dev_free(s->d_pack); dev_free(s->d_mcls); dev_free(s->d_halo); dev_free(s->d_chunks); dev_free(s->d_qpart); dev_free(s->d_slots);
     delete s;
     return EMSAR_OK;
 }

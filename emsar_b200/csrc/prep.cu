@@ -740,6 +740,19 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         s->d_state = p;
         s->state_bytes = theta_bytes + q_bytes;
     }
+    {   // tagged slots of the barrier-free kernel
+        const size_t need = 16 * ((size_t)P + 1 + (size_t)C_a + 1);
+        if (need > s->slots_bytes) {
+            if (s->d_slots) dev_free(s->d_slots);
+            s->d_slots = nullptr;
+            char *ps = nullptr;
+            TRY(dev_alloc(&ps, need + (need >> 3)));
+            s->d_slots = ps;
+            s->slots_bytes = need + (need >> 3);
+            CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
+            s->slot_tag = 0;
+        }
+    }
     EmModel &m = s->m;
     memset(&m, 0, sizeof(m));
     m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.smem_bytes = ctx->em_smem_bytes;
