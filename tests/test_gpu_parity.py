@@ -163,12 +163,13 @@ def test_unsupported_and_bad_inputs(ctx):
             Index(ctx, bad)
 
 
-# The EM kernel has three data paths: everything of a CTA resident in shared memory (the usual case at test sizes), the
-# overflow path (halo rows / classes and q that did not get a slot are read from the L2-resident global copies) and the
+# The EM kernel has four variants: the barrier-free one (everything of every CTA resident in shared memory: the usual case
+# at test sizes and at config #2), the same with grid barriers, the overflow path (halo rows / classes and q that did not get a slot are read from the L2-resident global copies) and the
 # TMA-pipelined index streams. The two rarer ones are forced here with the tuning knobs the library reads from the environment.
 VARIANTS = {
     "overflow_12k": {"EMSAR_EM_SMEM_KB": "12"},
     "overflow_24k": {"EMSAR_EM_SMEM_KB": "24"},
+    "grid_barriers": {"EMSAR_EM_MODE": "barrier"},          # the default at these sizes is the barrier-free kernel
     "pipelined": {"EMSAR_EM_MODE": "pipe"},
     "pipelined_small": {"EMSAR_EM_MODE": "pipe", "EMSAR_EM_SMEM_KB": "80"},
 }
