@@ -177,6 +177,8 @@ struct emsar_sample {
     // staging for host read batches (grow-only)
     void *d_rd_ptr, *d_rd_tid, *d_rd_fl;
     size_t cap_rd_ptr, cap_rd_tid, cap_rd_fl;
+    cudaEvent_t count_ev[4];   // "host arrays of batch k are free again" (emsar_sample_count_wait)
+    unsigned count_seq;
     // model
     bool prepared;
     int64_t N;

@@ -224,8 +224,39 @@ extern "C" int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_
     CU(cudaMemcpyAsync(s->d_rd_ptr, read_ptr, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (ntid > 0) CU(cudaMemcpyAsync(s->d_rd_tid, read_tid + base, (size_t)ntid * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(s->d_rd_fl, read_fraglen, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // the host arrays are free again once these copies are done (matters for page-locked arrays: the copies are asynchronous)
+    if (!s->count_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&s->count_ev[i], cudaEventDisableTiming));
+    CU(cudaEventRecord(s->count_ev[s->count_seq & 3], ctx->stream));
+    s->count_seq++;
     // offsets stay absolute: shift the tid base pointer instead of rewriting read_ptr
     return launch_count(s, n_reads, (const int64_t *)s->d_rd_ptr, (const int32_t *)s->d_rd_tid - base, (const int32_t *)s->d_rd_fl);
+}
+
+extern "C" int emsar_sample_count_wait(emsar_sample *s, int32_t lag)
+{
+    CHECK_ARG(s && lag >= 0 && lag < 4, "emsar_sample_count_wait: lag must be 0..3");
+    if ((int64_t)s->count_seq - 1 - lag < 0) return EMSAR_OK;
+    TRY(ctx_use(s->ctx));
+    CU(cudaEventSynchronize(s->count_ev[(s->count_seq - 1 - (unsigned)lag) & 3]));
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_host_alloc(emsar_ctx *ctx, size_t bytes, void **p)
+{
+    CHECK_ARG(ctx && p, "emsar_host_alloc: NULL argument");
+    TRY(ctx_use(ctx));
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *p = nullptr; emsar_set_err("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return EMSAR_ERR_NOMEM; }
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_host_free(emsar_ctx *ctx, void *p)
+{
+    CHECK_ARG(ctx, "emsar_host_free: NULL context");
+    if (!p) return EMSAR_OK;
+    TRY(ctx_use(ctx));
+    CU(cudaFreeHost(p));
+    return EMSAR_OK;
 }
 
 extern "C" int emsar_sample_count_device(emsar_sample *s, int64_t n_reads, const void *d_read_ptr, const void *d_read_tid,

@@ -26,7 +26,8 @@ class _Rsh(C.Structure):
 
 
 class _ReaderOpts(C.Structure):
-    _fields_ = [("pe", C.c_int), ("strand", C.c_char), ("max_repeat", C.c_int), ("format", C.c_char), ("batch_reads", C.c_int64)]
+    _fields_ = [("pe", C.c_int), ("strand", C.c_char), ("max_repeat", C.c_int), ("format", C.c_char), ("batch_reads", C.c_int64),
+                ("io_threads", C.c_int), ("nbuf", C.c_int), ("buf_alloc", C.c_void_p), ("buf_free", C.c_void_p), ("hook_user", C.c_void_p)]
 
 
 _BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32))
@@ -81,12 +82,12 @@ class Rsh:
             self._p = C.POINTER(_Rsh)()
 
 
-def read_alignments(rsh: Rsh, path, pe=False, strand="ns", max_repeat=100, fmt="bowtie", batch_reads=0):
+def read_alignments(rsh: Rsh, path, pe=False, strand="ns", max_repeat=100, fmt="bowtie", batch_reads=0, io_threads=0, nbuf=1):
     """Runs the C reader over an alignment file and returns the concatenated read groups
     (read_ptr int64[n+1], read_tid int32[], read_fraglen int32[n]) plus the PE read length seen."""
     st = {"ns": b"\0", "ssf": b"+", "ssr": b"-", "ssfr": b"+", "ssrf": b"-"}[strand]
     f = {"bowtie": b"\0", "sam": b"s", "bam": b"b"}[fmt]
-    o = _ReaderOpts(int(bool(pe)), st, int(max_repeat), f, int(batch_reads))
+    o = _ReaderOpts(int(bool(pe)), st, int(max_repeat), f, int(batch_reads), int(io_threads), int(nbuf), None, None, None)
     ptrs, tids, fls = [np.zeros(1, dtype=np.int64)], [], []
     base = [0]
 

@@ -47,6 +47,13 @@ typedef struct {
     int max_repeat;    /* -k MAX_REPEAT */
     char format;       /* 0 = default bowtie output, 's' = SAM, 'b' = BAM (bamflag) */
     int64_t batch_reads; /* read groups per batch handed to the callback (0 = 1<<20) */
+    /* ingestion pipeline; all optional, zero = the plain single-threaded reader */
+    int io_threads;      /* BAM: BGZF blocks are inflated by this many worker threads ahead of the parser (0: zlib gz* inline) */
+    int nbuf;            /* 2: two batch buffer sets used in turn. The callback may then return while the device is still
+                            copying the batch; it must only make sure that the PREVIOUS batch has been consumed */
+    void *(*buf_alloc)(void *hook_user, size_t bytes);   /* batch buffers from here (e.g. pinned host memory) instead of malloc */
+    void (*buf_free)(void *hook_user, void *p);
+    void *hook_user;
 } emsar_reader_opts;
 
 /* A batch of read groups that passed the reader-side filters (add_alignment_to_list alignment.c:29-60, size <=

@@ -70,23 +70,35 @@ static void usage(const char *p)
             "  -g           also write prefix.i.segments            -R  write the rsh index to outdir/prefix.rsh\n"
             "  -i n         max EM iterations (default 200000)      -e/-r  absolute (reads) / relative EM tolerance\n"
             "  -d n         delta (lambda scaled by 10^n)           -q / -v  quiet / verbose\n"
-            "  -p -n -b -t -h -F -f are accepted for compatibility; -F/-f are overwritten by the rsh header.\n",
+            "  -p n         BGZF inflate threads for BAM input (default 4)\n"
+            "  -n -b -t -h -F -f are accepted for compatibility; -F/-f are overwritten by the rsh header.\n",
             p);
 }
 
-typedef struct { emsar_sample *s; int rc; } count_ctx;
+/* Ingestion pipeline: BGZF blocks are inflated by -p worker threads, the parser fills one of two page-locked batch buffers
+ * while the device still copies / counts the other one (emsar_sample_count is asynchronous on page-locked arrays). */
+typedef struct { emsar_sample *s; emsar_ctx *ctx; int rc; int64_t batches, groups; } count_ctx;
 static int on_batch(void *user, int64_t n, const int64_t *ptr, const int32_t *tid, const int32_t *fl)
 {
     count_ctx *c = (count_ctx *)user;
     c->rc = emsar_sample_count(c->s, n, ptr, tid, fl);
+    if (!c->rc) c->rc = emsar_sample_count_wait(c->s, 1);      /* the other buffer set (batch k-1) is free again */
+    c->batches++; c->groups += n;
     return c->rc;
 }
+static void *pinned_alloc(void *user, size_t bytes)
+{
+    void *p = NULL;
+    if (emsar_host_alloc((emsar_ctx *)user, bytes, &p)) die("%s", emsar_cuda_last_error());
+    return p;
+}
+static void pinned_free(void *user, void *p) { emsar_host_free((emsar_ctx *)user, p); }
 
 typedef struct {
     const options *o; const emsar_rsh *rsh; int device, worker, nworker; int rc;
 } worker_arg;
 
-static int run_file(const options *o, const emsar_rsh *rsh, emsar_index *ix, int i, double *eumacut)
+static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsar_index *ix, int i, double *eumacut)
 {
     char err[EMSAR_HOST_ERRLEN] = "";
     emsar_sample *s = NULL;
@@ -95,12 +107,23 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_index *ix, int
     fprintf(stdout, "alnfile[%d]=%s\n", i, o->aln[i]);
     emsar_reader_opts ro;
     memset(&ro, 0, sizeof ro);
-    ro.pe = o->pe; ro.strand = o->strand; ro.max_repeat = o->max_repeat; ro.format = o->bamflag; ro.batch_reads = 1 << 21;
+    ro.pe = o->pe; ro.strand = o->strand; ro.max_repeat = o->max_repeat; ro.format = o->bamflag; ro.batch_reads = 1 << 20;
+    ro.io_threads = o->nthread > 0 ? o->nthread : 4;            /* -p: BGZF inflate threads (the reference's -p sizes its MLE thread team) */
+    ro.nbuf = 2; ro.buf_alloc = pinned_alloc; ro.buf_free = pinned_free; ro.hook_user = ctx;
     int readlength = rsh->readlength;
-    count_ctx cc = {s, 0};
+    count_ctx cc = {s, ctx, 0, 0, 0};
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     if (emsar_read_alignments(rsh, o->aln[i], &ro, &readlength, on_batch, &cc, err)) {
         if (cc.rc) die("%s: %s", emsar_cuda_strerror(cc.rc), emsar_cuda_last_error());
         die("%s", err);
+    }
+    if ((rc = emsar_sample_count_wait(s, 0))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (o->verbose > 0) {
+        const double sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        fprintf(stdout, "alignments read: %lld read groups in %lld batches, %.2f s (%.2f M groups/s, %d inflate threads)\n", (long long)cc.groups,
+                (long long)cc.batches, sec, sec > 0 ? 1e-6 * (double)cc.groups / sec : 0.0, ro.io_threads);
     }
     stamp(o, "\nscanning rsh array and constructing EUMA, ReadCount and CT array...");
     emsar_solve_opts so;
@@ -165,7 +188,7 @@ static void *worker(void *p)
     rc = emsar_index_create(ctx, &d, &ix);
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
     double eumacut = 0;
-    for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ix, i, &eumacut);
+    for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ctx, ix, i, &eumacut);
     emsar_index_destroy(ix);
     emsar_cuda_close(ctx);
     return NULL;
@@ -189,7 +212,7 @@ int main(int argc, char *argv[])
         {"no_verbose", no_argument, 0, 'q'}, {0, 0, 0, 0}};
     /* defaults (emsar_main.c:64-91) */
     strcpy(o.strand_str, "ns");
-    o.max_fl = 400; o.min_fl = 1; o.max_repeat = 100; o.verbose = 1; o.nthread = 1; o.num_round = 4;
+    o.max_fl = 400; o.min_fl = 1; o.max_repeat = 100; o.verbose = 1; o.nthread = 0; o.num_round = 4;
     int c, oi;
     while ((c = getopt_long(argc, argv, "vqPs:b:p:h:t:F:f:n:e:r:p:d:gm:MHBSW:w:k:i:l:TRI:x:", long_options, &oi)) != -1) {
         switch (c) {

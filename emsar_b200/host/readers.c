@@ -5,9 +5,11 @@
  * Output: batches of read groups (tids of the kept alignments + the first fragment length) for the device counter.
  * SAM text and BGZF/BAM are decoded here directly over zlib (the reference vendors samtools 0.1.19 for this). */
 #define _GNU_SOURCE
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "emsar_host.h"
@@ -83,11 +85,16 @@ typedef struct {
     int *tid, *pos, *fl;
     int size, cap, cur_min;
     char *prev_id; size_t prev_cap; int have_prev;
-    /* output batch */
+    /* output batch: `nbuf` buffer sets used in turn (2 = the parser fills one while the device still copies the other) */
     int64_t *rptr; int32_t *rtid; int32_t *rfl;
     int64_t nr, ntid, cap_r, cap_t;
+    struct { int64_t *rptr; int32_t *rtid; int32_t *rfl; int64_t cap_t; } set[2];
+    int nbuf, cur_set;
     int rc;
 } grouper;
+
+static void *g_alloc(grouper *g, size_t bytes) { return g->o->buf_alloc ? g->o->buf_alloc(g->o->hook_user, bytes) : malloc(bytes); }
+static void g_free(grouper *g, void *p) { if (!p) return; if (g->o->buf_free) g->o->buf_free(g->o->hook_user, p); else free(p); }
 
 static void g_init(grouper *g, const emsar_reader_opts *o, emsar_batch_fn fn, void *user)
 {
@@ -95,16 +102,29 @@ static void g_init(grouper *g, const emsar_reader_opts *o, emsar_batch_fn fn, vo
     g->o = o; g->fn = fn; g->user = user;
     g->batch = o->batch_reads > 0 ? o->batch_reads : (1 << 20);
     g->cur_min = 10000;
-    g->cap_r = g->batch + 1; g->cap_t = g->batch * 4;
-    g->rptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(g->cap_r + 1));
-    g->rfl = (int32_t *)malloc(sizeof(int32_t) * (size_t)g->cap_r);
-    g->rtid = (int32_t *)malloc(sizeof(int32_t) * (size_t)g->cap_t);
+    g->cap_r = g->batch + 1;
+    g->nbuf = (o->nbuf == 2) ? 2 : 1;
+    for (int b = 0; b < g->nbuf; b++) {
+        g->set[b].cap_t = g->batch * 4;
+        g->set[b].rptr = (int64_t *)g_alloc(g, sizeof(int64_t) * (size_t)(g->cap_r + 1));
+        g->set[b].rfl = (int32_t *)g_alloc(g, sizeof(int32_t) * (size_t)g->cap_r);
+        g->set[b].rtid = (int32_t *)g_alloc(g, sizeof(int32_t) * (size_t)g->set[b].cap_t);
+    }
+    g->cur_set = 0;
+    g->rptr = g->set[0].rptr; g->rfl = g->set[0].rfl; g->rtid = g->set[0].rtid; g->cap_t = g->set[0].cap_t;
     g->rptr[0] = 0;
 }
 
 static void g_emit_batch(grouper *g)
 {
-    if (g->nr > 0 && !g->rc) g->rc = g->fn(g->user, g->nr, g->rptr, g->rtid, g->rfl);
+    if (g->nr > 0 && !g->rc) {
+        g->rc = g->fn(g->user, g->nr, g->rptr, g->rtid, g->rfl);
+        if (g->nbuf == 2) {        /* the callback may still be copying this set: go on in the other one */
+            g->set[g->cur_set].rtid = g->rtid; g->set[g->cur_set].cap_t = g->cap_t;
+            g->cur_set ^= 1;
+            g->rptr = g->set[g->cur_set].rptr; g->rfl = g->set[g->cur_set].rfl; g->rtid = g->set[g->cur_set].rtid; g->cap_t = g->set[g->cur_set].cap_t;
+        }
+    }
     g->nr = 0; g->ntid = 0; g->rptr[0] = 0;
 }
 
@@ -115,7 +135,13 @@ static void g_flush_group(grouper *g)
         int ok = 1;
         if (g->o->pe) for (int j = 1; j < g->size; j++) if (g->fl[j] != g->fl[0]) { ok = 0; break; }
         if (ok) {
-            if (g->ntid + g->size > g->cap_t) { while (g->ntid + g->size > g->cap_t) g->cap_t *= 2; g->rtid = (int32_t *)realloc(g->rtid, sizeof(int32_t) * (size_t)g->cap_t); }
+            if (g->ntid + g->size > g->cap_t) {
+                while (g->ntid + g->size > g->cap_t) g->cap_t *= 2;
+                int32_t *nt = (int32_t *)g_alloc(g, sizeof(int32_t) * (size_t)g->cap_t);
+                memcpy(nt, g->rtid, sizeof(int32_t) * (size_t)g->ntid);
+                g_free(g, g->rtid);
+                g->rtid = nt;
+            }
             for (int j = 0; j < g->size; j++) g->rtid[g->ntid + j] = g->tid[j];
             g->ntid += g->size;
             g->rfl[g->nr] = g->fl[0];
@@ -164,7 +190,9 @@ static int g_finish(grouper *g)
     g_flush_group(g);      /* the last group is flushed after EOF (:761) */
     g_emit_batch(g);
     int rc = g->rc;
-    free(g->tid); free(g->pos); free(g->fl); free(g->prev_id); free(g->rptr); free(g->rtid); free(g->rfl);
+    g->set[g->cur_set].rtid = g->rtid;
+    free(g->tid); free(g->pos); free(g->fl); free(g->prev_id);
+    for (int b = 0; b < g->nbuf; b++) { g_free(g, g->set[b].rptr); g_free(g, g->set[b].rtid); g_free(g, g->set[b].rfl); }
     return rc;
 }
 
@@ -249,6 +277,164 @@ static int read_bowtie(const emsar_rsh *r, FILE *fp, const emsar_reader_opts *o,
     return rc;
 }
 
+
+/* ---- BGZF with a pool of inflate threads ------------------------------------------------------
+ * A BAM file is a sequence of independent gzip members of <= 64 KB (BGZF); the reference inflates them one at a time on
+ * the thread that also parses (samtools 0.1.19 bgzf.c). Here the parsing thread only reads the compressed blocks ahead
+ * (the block length is in the `BC` extra field) into a ring of jobs; `nthr` workers inflate them out of order and the
+ * parser consumes them in file order. CRC32 and ISIZE of every block are checked. */
+typedef struct { unsigned char *c, *u; int clen, ulen, isize, state, err; unsigned crc; } bgzf_job;   /* state: 0 free, 1 queued, 2 running, 3 done */
+typedef struct {
+    FILE *fp;
+    int nthr, njobs;
+    pthread_t *thr;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    bgzf_job *jobs;
+    unsigned long long n_read, n_taken, n_consumed;     /* counters; slot = counter % njobs */
+    int eof, stop, failed, have_cur;
+    const unsigned char *cur; int cur_len, cur_off;
+    unsigned char first[18]; int first_len;             /* bytes consumed by the format probe */
+} bgzf_mt;
+
+static void *bgzf_worker(void *arg)
+{
+    bgzf_mt *h = (bgzf_mt *)arg;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    inflateInit2(&zs, -15);
+    pthread_mutex_lock(&h->mu);
+    for (;;) {
+        while (!h->stop && h->n_taken == h->n_read) pthread_cond_wait(&h->cv_work, &h->mu);
+        if (h->stop) break;
+        bgzf_job *j = &h->jobs[h->n_taken % (unsigned long long)h->njobs];
+        h->n_taken++;
+        j->state = 2;
+        pthread_mutex_unlock(&h->mu);
+        inflateReset(&zs);
+        zs.next_in = j->c; zs.avail_in = (uInt)j->clen;
+        zs.next_out = j->u; zs.avail_out = 65536;
+        int rc = inflate(&zs, Z_FINISH);
+        j->ulen = (int)(65536 - zs.avail_out);
+        j->err = !(rc == Z_STREAM_END && j->ulen == j->isize && (unsigned)crc32(crc32(0L, Z_NULL, 0), j->u, (uInt)j->ulen) == j->crc);
+        pthread_mutex_lock(&h->mu);
+        j->state = 3;
+        pthread_cond_broadcast(&h->cv_done);
+    }
+    pthread_mutex_unlock(&h->mu);
+    inflateEnd(&zs);
+    return NULL;
+}
+
+/* reads the next compressed block into job slot j; returns 1 = block, 0 = clean EOF, -1 = malformed */
+static int bgzf_fetch(bgzf_mt *h, bgzf_job *j)
+{
+    unsigned char hd[18];
+    size_t got;
+    if (h->first_len) { memcpy(hd, h->first, (size_t)h->first_len); got = (size_t)h->first_len; h->first_len = 0; }
+    else got = fread(hd, 1, 12, h->fp);
+    if (got == 0) return 0;
+    if (got < 12) { got += fread(hd + got, 1, 12 - got, h->fp); }
+    if (got < 12 || hd[0] != 31 || hd[1] != 139 || hd[2] != 8 || !(hd[3] & 4)) return -1;
+    int xlen = hd[10] | (hd[11] << 8), bsize = -1;       /* 10 fixed bytes, then XLEN */
+    unsigned char extra[256];
+    if (xlen > (int)sizeof extra || fread(extra, 1, (size_t)xlen, h->fp) != (size_t)xlen) return -1;
+    for (int o = 0; o + 4 <= xlen;) {
+        int slen = extra[o + 2] | (extra[o + 3] << 8);
+        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
+        o += 4 + slen;
+    }
+    if (bsize < 0) return -1;
+    int clen = bsize + 1 - 12 - xlen - 8;
+    if (clen < 0 || clen > 65536) return -1;
+    unsigned char tail[8];
+    if (fread(j->c, 1, (size_t)clen, h->fp) != (size_t)clen || fread(tail, 1, 8, h->fp) != 8) return -1;
+    j->clen = clen;
+    j->crc = (unsigned)tail[0] | ((unsigned)tail[1] << 8) | ((unsigned)tail[2] << 16) | ((unsigned)tail[3] << 24);
+    j->isize = (int)((unsigned)tail[4] | ((unsigned)tail[5] << 8) | ((unsigned)tail[6] << 16) | ((unsigned)tail[7] << 24));
+    if (j->isize < 0 || j->isize > 65536) return -1;
+    return 1;
+}
+
+static void bgzf_mt_close(bgzf_mt *h)
+{
+    if (!h) return;
+    pthread_mutex_lock(&h->mu);
+    h->stop = 1;
+    pthread_cond_broadcast(&h->cv_work);
+    pthread_mutex_unlock(&h->mu);
+    for (int i = 0; i < h->nthr; i++) pthread_join(h->thr[i], NULL);
+    for (int i = 0; i < h->njobs; i++) { free(h->jobs[i].c); free(h->jobs[i].u); }
+    free(h->jobs); free(h->thr);
+    if (h->fp && h->fp != stdin) fclose(h->fp);
+    pthread_mutex_destroy(&h->mu); pthread_cond_destroy(&h->cv_work); pthread_cond_destroy(&h->cv_done);
+    free(h);
+}
+
+/* NULL when the file cannot be opened or does not start with a BGZF block (plain gzip: the caller falls back to zlib's gz*) */
+static bgzf_mt *bgzf_mt_open(const char *path, int nthr)
+{
+    FILE *fp = (path[0] == 0 || strcmp(path, "-") == 0) ? stdin : fopen(path, "rb");
+    if (!fp) return NULL;
+    if (fp == stdin) return NULL;                 /* stdin cannot be rewound for the fallback: leave it to gzdopen */
+    unsigned char hd[12];
+    if (fread(hd, 1, 12, fp) != 12 || hd[0] != 31 || hd[1] != 139 || hd[2] != 8 || !(hd[3] & 4)) { fclose(fp); return NULL; }
+    bgzf_mt *h = (bgzf_mt *)calloc(1, sizeof *h);
+    memcpy(h->first, hd, 12); h->first_len = 12;
+    h->fp = fp;
+    h->nthr = nthr < 1 ? 1 : (nthr > 64 ? 64 : nthr);
+    h->njobs = 8 * h->nthr + 8;
+    h->jobs = (bgzf_job *)calloc((size_t)h->njobs, sizeof(bgzf_job));
+    for (int i = 0; i < h->njobs; i++) { h->jobs[i].c = (unsigned char *)malloc(65536); h->jobs[i].u = (unsigned char *)malloc(65536); }
+    pthread_mutex_init(&h->mu, NULL); pthread_cond_init(&h->cv_work, NULL); pthread_cond_init(&h->cv_done, NULL);
+    h->thr = (pthread_t *)calloc((size_t)h->nthr, sizeof(pthread_t));
+    for (int i = 0; i < h->nthr; i++) pthread_create(&h->thr[i], NULL, bgzf_worker, h);
+    return h;
+}
+
+/* like gzread: up to n bytes, fewer only at the end of the file; -1 on a malformed / corrupt block */
+static int bgzf_mt_read(bgzf_mt *h, void *buf, unsigned n)
+{
+    unsigned done = 0;
+    while (done < n) {
+        if (h->have_cur && h->cur_off < h->cur_len) {
+            unsigned take = (unsigned)(h->cur_len - h->cur_off);
+            if (take > n - done) take = n - done;
+            memcpy((char *)buf + done, h->cur + h->cur_off, take);
+            h->cur_off += (int)take; done += take;
+            continue;
+        }
+        if (h->failed) return -1;
+        if (h->have_cur) {                        /* release the block just finished */
+            pthread_mutex_lock(&h->mu);
+            h->jobs[h->n_consumed % (unsigned long long)h->njobs].state = 0;
+            h->n_consumed++;
+            pthread_mutex_unlock(&h->mu);
+            h->have_cur = 0;
+        }
+        /* keep the ring full: only this thread touches the file and n_read */
+        while (!h->eof && h->n_read - h->n_consumed < (unsigned long long)h->njobs) {
+            bgzf_job *j = &h->jobs[h->n_read % (unsigned long long)h->njobs];
+            int st = bgzf_fetch(h, j);
+            if (st == 0) { h->eof = 1; break; }
+            if (st < 0) { h->failed = 1; h->eof = 1; break; }
+            pthread_mutex_lock(&h->mu);
+            j->state = 1;
+            h->n_read++;
+            pthread_cond_signal(&h->cv_work);
+            pthread_mutex_unlock(&h->mu);
+        }
+        if (h->n_consumed == h->n_read) { if (h->failed) return -1; break; }      /* end of file */
+        bgzf_job *j = &h->jobs[h->n_consumed % (unsigned long long)h->njobs];
+        pthread_mutex_lock(&h->mu);
+        while (j->state != 3) pthread_cond_wait(&h->cv_done, &h->mu);
+        pthread_mutex_unlock(&h->mu);
+        if (j->err) { h->failed = 1; return -1; }
+        h->cur = j->u; h->cur_len = j->ulen; h->cur_off = 0; h->have_cur = 1;
+    }
+    return (int)done;
+}
+
 /* ---- SAM / BAM records ----------------------------------------------------------------------------------- */
 typedef struct { char *qname; int flag; int ref; int pos; int l_qseq; const char *md; } samrec;   /* md NULL = no MD tag */
 
@@ -260,6 +446,7 @@ typedef struct {
     FILE *fp; char *line; size_t cap;
     /* BAM */
     gzFile gz; int is_bam;
+    bgzf_mt *mt;        /* threaded BGZF reader (NULL: zlib's gz* on a plain gzip stream or stdin) */
     unsigned char *blk; size_t blk_cap;
     char *md_buf; size_t md_cap;
     char *qbuf; size_t qcap;
@@ -310,29 +497,37 @@ static int sam_ref_index(samfile *s, const char *name)
     }
 }
 
-static int sam_open(samfile *s, const char *path, char fmt, char *err)
+static int bam_read(samfile *s, void *buf, unsigned n)
+{
+    return s->mt ? bgzf_mt_read(s->mt, buf, n) : gzread(s->gz, buf, n);
+}
+
+static int sam_open(samfile *s, const char *path, char fmt, int io_threads, char *err)
 {
     memset(s, 0, sizeof(*s));
     s->is_bam = (fmt == 'b');
     if (s->is_bam) {
-        s->gz = (path[0] == 0 || strcmp(path, "-") == 0) ? gzdopen(0, "rb") : gzopen(path, "rb");   /* BGZF is a valid multi-member gzip stream */
-        if (!s->gz) return fail(err, "can't open BAM file.");
-        gzbuffer(s->gz, 1 << 20);
+        if (io_threads > 0) s->mt = bgzf_mt_open(path, io_threads);
+        if (!s->mt) {
+            s->gz = (path[0] == 0 || strcmp(path, "-") == 0) ? gzdopen(0, "rb") : gzopen(path, "rb");   /* BGZF is a valid multi-member gzip stream */
+            if (!s->gz) return fail(err, "can't open BAM file.");
+            gzbuffer(s->gz, 1 << 20);
+        }
         char magic[4];
         int32_t l_text, n_ref;
-        if (gzread(s->gz, magic, 4) != 4 || memcmp(magic, "BAM\1", 4) != 0) return fail(err, "can't open BAM file.");
-        if (gzread(s->gz, &l_text, 4) != 4) return fail(err, "truncated BAM header");
+        if (bam_read(s, magic, 4) != 4 || memcmp(magic, "BAM\1", 4) != 0) return fail(err, "can't open BAM file.");
+        if (bam_read(s, &l_text, 4) != 4) return fail(err, "truncated BAM header");
         char *text = (char *)malloc((size_t)l_text + 1);
-        if (gzread(s->gz, text, (unsigned)l_text) != l_text) { free(text); return fail(err, "truncated BAM header"); }
+        if (bam_read(s, text, (unsigned)l_text) != l_text) { free(text); return fail(err, "truncated BAM header"); }
         free(text);
-        if (gzread(s->gz, &n_ref, 4) != 4) return fail(err, "truncated BAM header");
+        if (bam_read(s, &n_ref, 4) != 4) return fail(err, "truncated BAM header");
         for (int i = 0; i < n_ref; i++) {
             int32_t l_name, l_ref;
-            if (gzread(s->gz, &l_name, 4) != 4) return fail(err, "truncated BAM header");
+            if (bam_read(s, &l_name, 4) != 4) return fail(err, "truncated BAM header");
             char *nm = (char *)malloc((size_t)l_name + 1);
-            if (gzread(s->gz, nm, (unsigned)l_name) != l_name) { free(nm); return fail(err, "truncated BAM header"); }
+            if (bam_read(s, nm, (unsigned)l_name) != l_name) { free(nm); return fail(err, "truncated BAM header"); }
             nm[l_name] = 0;
-            if (gzread(s->gz, &l_ref, 4) != 4) { free(nm); return fail(err, "truncated BAM header"); }
+            if (bam_read(s, &l_ref, 4) != 4) { free(nm); return fail(err, "truncated BAM header"); }
             sam_add_ref(s, nm);
             free(nm);
         }
@@ -362,6 +557,7 @@ static int sam_open(samfile *s, const char *path, char fmt, char *err)
 static void sam_close(samfile *s)
 {
     if (s->gz) gzclose(s->gz);
+    if (s->mt) bgzf_mt_close(s->mt);
     if (s->fp && s->fp != stdin) fclose(s->fp);
     for (int i = 0; i < s->n_ref; i++) free(s->ref_names[i]);
     free(s->ref_names); free(s->ref_tid); free(s->ref_slots); free(s->line); free(s->blk); free(s->md_buf); free(s->qbuf);
@@ -372,11 +568,11 @@ static int sam_next(samfile *s, samrec *r, char *err)
 {
     if (s->is_bam) {
         int32_t bs;
-        int got = gzread(s->gz, &bs, 4);
+        int got = bam_read(s, &bs, 4);
         if (got == 0) return 0;
         if (got != 4 || bs < 32) { fail(err, "truncated BAM record"); return -1; }
         if ((size_t)bs + 1 > s->blk_cap) { s->blk_cap = (size_t)bs * 2 + 64; s->blk = (unsigned char *)realloc(s->blk, s->blk_cap); }
-        if (gzread(s->gz, s->blk, (unsigned)bs) != bs) { fail(err, "truncated BAM record"); return -1; }
+        if (bam_read(s, s->blk, (unsigned)bs) != bs) { fail(err, "truncated BAM record"); return -1; }
         const unsigned char *b = s->blk;
         int32_t refID, pos, l_seq;
         uint8_t l_read_name; uint16_t n_cigar, flag;
@@ -447,7 +643,7 @@ static int sam_tid(const emsar_rsh *rs, samfile *s, int ref)
 static int read_sam(const emsar_rsh *rs, const char *path, const emsar_reader_opts *o, int *readlength, grouper *g, char *err)
 {
     samfile s;
-    if (sam_open(&s, path, o->format, err)) { sam_close(&s); return 1; }
+    if (sam_open(&s, path, o->format, o->io_threads, err)) { sam_close(&s); return 1; }
     int rc = 0, st;
     samrec a, b;
     char *qn = NULL; size_t qcap = 0;

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import dataclasses
 import os
+import struct
+import zlib
 from typing import Optional
 
 import numpy as np
@@ -304,6 +306,64 @@ def write_sam_pe(idx: SynthIndex, reads: SynthReads, path: str, tlen=100000):
                     # pos2 == pos1 is treated as "mate2(f)...mate1(r)" (:461-465)
                     f.write(f"r{r}\t{0x1 | 0x2 | 0x10 | 0x40}\t{n}\t{p1}\t255\t{L}M\t=\t{p2}\t{L}\t{seq}\t{seq}\tMD:Z:{L}\n")
                     f.write(f"r{r}\t{0x1 | 0x2 | 0x20 | 0x80}\t{n}\t{p2}\t255\t{L}M\t=\t{p1}\t{-L}\t{seq}\t{seq}\tMD:Z:{L}\n")
+
+
+def sam_to_bam(sam_path, bam_path):
+    """Minimal BAM writer (BGZF blocks over zlib) for the fixtures; records carry what the reference reads."""
+    refs, recs, text = [], [], []
+    for line in open(sam_path):
+        line = line.rstrip("\n")
+        if line.startswith("@"):
+            text.append(line)
+            if line.startswith("@SQ"):
+                d = dict(x.split(":", 1) for x in line.split("\t")[1:])
+                refs.append((d["SN"], int(d["LN"])))
+            continue
+        recs.append(line.split("\t"))
+    ref_id = {n: i for i, (n, _) in enumerate(refs)}
+    out = bytearray()
+    htext = ("\n".join(text) + "\n").encode()
+    out += b"BAM\1" + struct.pack("<i", len(htext)) + htext + struct.pack("<i", len(refs))
+    for n, ln in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln)
+    codes = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    for f in recs:
+        qname, flag, rname, pos, mapq, cigar, rnext, pnext, tlen, seq, qual = f[:11]
+        tags = f[11:]
+        rid = ref_id.get(rname, -1)
+        nid = rid if rnext == "=" else ref_id.get(rnext, -1)
+        cig = []
+        num = ""
+        for ch in cigar:
+            if ch.isdigit():
+                num += ch
+            elif ch != "*":
+                cig.append((int(num) << 4) | "MIDNSHP=X".index(ch))
+                num = ""
+        l_seq = 0 if seq == "*" else len(seq)
+        sq = bytearray((l_seq + 1) // 2)
+        for i, ch in enumerate(seq if seq != "*" else ""):
+            sq[i // 2] |= codes.get(ch, 15) << (4 if i % 2 == 0 else 0)
+        ql = bytes([0xFF] * l_seq) if qual == "*" else bytes(ord(c) - 33 for c in qual)
+        aux = bytearray()
+        for t in tags:
+            tag, ty, val = t.split(":", 2)
+            if ty == "Z":
+                aux += tag.encode() + b"Z" + val.encode() + b"\0"
+            elif ty == "i":
+                aux += tag.encode() + b"i" + struct.pack("<i", int(val))
+        body = struct.pack("<iiBBHHHiiii", rid, int(pos) - 1, len(qname) + 1, int(mapq), 4680, len(cig), int(flag), l_seq, nid,
+                           int(pnext) - 1, int(tlen))
+        body += qname.encode() + b"\0" + b"".join(struct.pack("<I", c) for c in cig) + bytes(sq) + ql + bytes(aux)
+        out += struct.pack("<i", len(body)) + body
+    with open(bam_path, "wb") as g:
+        for o in list(range(0, len(out), 60000)) + [None]:
+            chunk = b"" if o is None else bytes(out[o:o + 60000])
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            cd = co.compress(chunk) + co.flush()
+            bsize = len(cd) + 25
+            g.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + cd +
+                    struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
 
 
 def ensure_dir(p):

@@ -159,6 +159,16 @@ int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, double *expected
 int emsar_sample_wf_get(emsar_sample *s, double *Wf);
 int emsar_sample_end(emsar_sample *s);
 
+/* -------- ingestion pipeline: page-locked batch buffers and asynchronous counting ----------
+ * emsar_sample_count returns as soon as the copies and the kernel are enqueued when its arrays live in page-locked memory
+ * (emsar_host_alloc); the arrays must then stay untouched until emsar_sample_count_wait(s, lag) has returned, which blocks
+ * until the batch submitted `lag` calls before the latest one has been consumed (lag 0 = the latest). A reader with two
+ * buffer sets calls emsar_sample_count(batch k) and then emsar_sample_count_wait(s, 1) before it refills the set of batch
+ * k-1 (emsar_b200/host/emsar_main.c). The reference parses and counts on one thread (emsar_functions.c:323-836). */
+int emsar_host_alloc(emsar_ctx *ctx, size_t bytes, void **p);
+int emsar_host_free(emsar_ctx *ctx, void *p);
+int emsar_sample_count_wait(emsar_sample *s, int32_t lag);
+
 /* -------- one sample sharded over several GPUs (BASELINE.json configs[2]) ------------------------
  * One process (or thread) per GPU, each with its own context holding the SAME index. The multi-tid classes that are
  * active in the sample are cut into nnz-balanced contiguous ranges, one per rank; every EM iteration each rank computes

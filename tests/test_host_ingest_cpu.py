@@ -1,0 +1,62 @@
+"""Host ingestion pipeline, CPU only: the threaded BGZF reader and the double-buffered grouper must hand
+the device exactly the read groups the single-threaded reader produces (which the golden tests pin against the reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from emsar_b200 import host, synth
+import golden_util as gu
+
+
+def _same(a, b):
+    return (np.array_equal(a.read_ptr, b.read_ptr) and np.array_equal(a.read_tid, b.read_tid) and np.array_equal(a.read_fraglen, b.read_fraglen))
+
+
+@pytest.fixture(scope="module")
+def pe_bam(built, tmp_path_factory):
+    """~60K PE fragments, multi-mapping, as a multi-block BAM (several hundred BGZF blocks)."""
+    tmp = tmp_path_factory.mktemp("ingest")
+    idx = synth.make_index(T=300, n_multi=1500, kmax=12, seed=7, module_cap=40, nF=41, frag_min=60, readlength=50)
+    reads = synth.make_reads(idx, 60000, seed=7)
+    synth.write_rsh(idx, str(tmp / "in.rsh"))
+    synth.write_sam_pe(idx, reads, str(tmp / "in.sam"))
+    synth.sam_to_bam(str(tmp / "in.sam"), str(tmp / "in.bam"))
+    return tmp
+
+
+def test_threaded_bgzf_matches_zlib_reader(pe_bam):
+    rsh = host.Rsh(str(pe_bam / "in.rsh"))
+    ref, rl0 = host.read_alignments(rsh, str(pe_bam / "in.bam"), pe=True, fmt="bam")
+    sam, _ = host.read_alignments(rsh, str(pe_bam / "in.sam"), pe=True, fmt="sam")
+    assert _same(ref, sam) and len(ref.read_fraglen) > 50000
+    for thr in (1, 3, 8):
+        for nbuf in (1, 2):
+            got, rl = host.read_alignments(rsh, str(pe_bam / "in.bam"), pe=True, fmt="bam", io_threads=thr, nbuf=nbuf, batch_reads=4096)
+            assert rl == rl0 and _same(ref, got), (thr, nbuf)
+    rsh.close()
+
+
+def test_golden_bam_through_the_pipeline(built, tmp_path):
+    fx = gu.FIXTURES["pe_bam_ssfr"]
+    rsh = host.Rsh(gu.materialize(fx["rsh"], tmp_path))
+    bam = gu.materialize(fx["aln"], tmp_path)
+    a, _ = host.read_alignments(rsh, bam, pe=True, strand=fx["strand"], fmt="bam")
+    b, _ = host.read_alignments(rsh, bam, pe=True, strand=fx["strand"], fmt="bam", io_threads=4, nbuf=2, batch_reads=1000)
+    assert _same(a, b)
+    rsh.close()
+
+
+def test_corrupt_block_is_an_error(pe_bam, tmp_path):
+    raw = bytearray(open(pe_bam / "in.bam", "rb").read())
+    raw[len(raw) // 2] ^= 0x5A                      # flip bits inside a compressed block: inflate or the CRC must notice
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(bytes(raw))
+    rsh = host.Rsh(str(pe_bam / "in.rsh"))
+    with pytest.raises(host.HostError):
+        host.read_alignments(rsh, str(bad), pe=True, fmt="bam", io_threads=3)
+    trunc = tmp_path / "trunc.bam"
+    trunc.write_bytes(bytes(raw[: len(raw) // 3]))
+    with pytest.raises(host.HostError):
+        host.read_alignments(rsh, str(trunc), pe=True, fmt="bam", io_threads=3)
+    rsh.close()
