@@ -40,6 +40,9 @@ def lib():
             raise HostError(f"{_SO} is missing: run `python -m emsar_b200.build`")
         L = C.CDLL(_SO)
         L.emsar_rsh_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(_Rsh)), C.c_char_p]
+        L.emsar_rsh_load_packed.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.POINTER(_Rsh)), C.c_char_p]
+        L.emsar_rsh_save_packed.argtypes = [C.POINTER(_Rsh), C.c_char_p, C.c_char_p, C.c_char_p]
+        L.emsar_rsh_load_auto.argtypes = [C.c_char_p, C.POINTER(C.POINTER(_Rsh)), C.POINTER(C.c_int), C.c_char_p]
         L.emsar_rsh_free.argtypes = [C.POINTER(_Rsh)]
         L.emsar_rsh_tid.argtypes = [C.POINTER(_Rsh), C.c_char_p]
         L.emsar_rsh_write.argtypes = [C.POINTER(_Rsh), C.c_int, C.c_char_p, C.c_char_p]
@@ -51,10 +54,23 @@ def lib():
 class Rsh:
     """A loaded `.rsh` index. Exposes the same fields as emsar_b200.synth.SynthIndex (numpy views are copies)."""
 
-    def __init__(self, path):
+    def __init__(self, path, packed=False, src=None, auto=False):
+        """Text `.rsh` (default), a packed image (`packed=True`; `src` = the text file it must match), or `auto`: what the
+        command line does for -I (the fresh `<path>.pack` if there is one, else the text)."""
         self._p = C.POINTER(_Rsh)()
+        self.from_cache = bool(packed)
         err = C.create_string_buffer(ERRLEN)
-        if lib().emsar_rsh_load(os.fsencode(path), C.byref(self._p), err):
+        if packed:
+            rc = lib().emsar_rsh_load_packed(os.fsencode(path), os.fsencode(src) if src else None, C.byref(self._p), err)
+            if rc == 2:
+                raise HostError("stale packed image")
+        elif auto:
+            fc = C.c_int(0)
+            rc = lib().emsar_rsh_load_auto(os.fsencode(path), C.byref(self._p), C.byref(fc), err)
+            self.from_cache = bool(fc.value)
+        else:
+            rc = lib().emsar_rsh_load(os.fsencode(path), C.byref(self._p), err)
+        if rc:
             raise HostError(err.value.decode())
         r = self._p.contents
         self.T, self.C, self.nF = int(r.T), int(r.C), int(r.nF)
@@ -74,6 +90,11 @@ class Rsh:
     def write(self, path, pe=False):
         err = C.create_string_buffer(ERRLEN)
         if lib().emsar_rsh_write(self._p, int(bool(pe)), os.fsencode(path), err):
+            raise HostError(err.value.decode())
+
+    def save_packed(self, path, src=None):
+        err = C.create_string_buffer(ERRLEN)
+        if lib().emsar_rsh_save_packed(self._p, os.fsencode(path), os.fsencode(src) if src else None, err):
             raise HostError(err.value.decode())
 
     def close(self):

@@ -39,6 +39,10 @@ int emsar_rsh_load(const char *path, emsar_rsh **out, char *err);
 void emsar_rsh_free(emsar_rsh *r);
 int emsar_rsh_tid(const emsar_rsh *r, const char *name);           /* -1 when absent (search_treehash) */
 int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err); /* print_rsh :2071-2130 */
+/* packed binary image of a loaded index: same arrays, no parsing; tied to the text file it was made from */
+int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_path, char *err);
+int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **out, char *err);   /* 2 = stale w.r.t. src_path */
+int emsar_rsh_load_auto(const char *path, emsar_rsh **out, int *from_cache, char *err);          /* <path>.pack if fresh, else text */
 
 /* ---- alignment readers ------------------------------------------------------------------------ */
 typedef struct {

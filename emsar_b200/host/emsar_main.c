@@ -285,7 +285,9 @@ int main(int argc, char *argv[])
     stamp(&o, "reading rsh array...");
     char err[EMSAR_HOST_ERRLEN] = "";
     emsar_rsh *rsh = NULL;
-    if (emsar_rsh_load(o.rshfile, &rsh, err)) { printf("%s\n", err); exit(1); }
+    int from_cache = 0;       /* <rshfile>.pack (written when EMSAR_RSH_CACHE is set) replaces the text parse while it is fresh */
+    if (emsar_rsh_load_auto(o.rshfile, &rsh, &from_cache, err)) { printf("%s\n", err); exit(1); }
+    if (from_cache && o.verbose > 0) fprintf(stdout, "rsh index taken from its packed image\n");
     fprintf(stderr, "done reading rsh. rshsize=%lld\n", (long long)(rsh->C - rsh->T));
     if (o.verbose > 0) fprintf(stdout, "max_tid=%d, rshsize=%lld, max_cid=%lld\n", rsh->T - 1, (long long)(rsh->C - rsh->T), (long long)rsh->C - 1);
     if (o.print_rsh) {

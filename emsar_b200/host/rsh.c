@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "emsar_host.h"
 
@@ -229,4 +231,121 @@ int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err)
     }
     fclose(f);
     return 0;
+}
+
+/* ---- packed binary image of a loaded index ------------------------------------------------------
+ * The text `.rsh` stays the interchange format (emsar-build writes it, -R writes it); parsing it costs a getline + atoi
+ * pass over every class line each run. The packed image holds the arrays exactly as emsar_rsh keeps them (scan order
+ * already applied), so loading it is a handful of large reads. It records size and mtime of the text file it was made
+ * from and is ignored when they no longer match. */
+typedef struct {
+    char magic[8];                      /* "EMSARPK1" */
+    int32_t T, nF, min_fraglength, max_fraglength, readlength, max_t_size, frag_min, frag_max;
+    int64_t C, nnz, names_bytes, src_size, src_mtime_ns;
+} pack_header;
+
+static void src_stamp(const char *src, int64_t *size, int64_t *mtime_ns)
+{
+    struct stat st;
+    *size = -1; *mtime_ns = -1;
+    if (src && stat(src, &st) == 0) { *size = (int64_t)st.st_size; *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec; }
+}
+
+int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_path, char *err)
+{
+    char tmp[4096];
+    snprintf(tmp, sizeof tmp, "%s.tmp%d", path, (int)getpid());
+    FILE *f = fopen(tmp, "wb");
+    if (!f) return fail(err, "can't write packed rsh image %s", tmp);
+    pack_header h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "EMSARPK1", 8);
+    h.T = r->T; h.nF = r->nF; h.min_fraglength = r->min_fraglength; h.max_fraglength = r->max_fraglength; h.readlength = r->readlength;
+    h.max_t_size = r->max_t_size; h.frag_min = r->frag_min; h.frag_max = r->frag_max;
+    h.C = r->C; h.nnz = r->class_ptr[r->C];
+    for (int32_t t = 0; t < r->T; t++) h.names_bytes += (int64_t)strlen(r->names[t]) + 1;
+    src_stamp(src_path, &h.src_size, &h.src_mtime_ns);
+    int ok = fwrite(&h, sizeof h, 1, f) == 1;
+    ok = ok && fwrite(r->class_ptr, sizeof(int64_t), (size_t)r->C + 1, f) == (size_t)r->C + 1;
+    ok = ok && (h.nnz == 0 || fwrite(r->class_tid, sizeof(int32_t), (size_t)h.nnz, f) == (size_t)h.nnz);
+    ok = ok && fwrite(r->euma, sizeof(int32_t), (size_t)r->C * r->nF, f) == (size_t)r->C * r->nF;
+    ok = ok && fwrite(r->has_node, 1, (size_t)r->C, f) == (size_t)r->C;
+    for (int32_t t = 0; ok && t < r->T; t++) ok = fwrite(r->names[t], 1, strlen(r->names[t]) + 1, f) == strlen(r->names[t]) + 1;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp, path) != 0) { remove(tmp); return fail(err, "can't write packed rsh image %s", path); }
+    return 0;
+}
+
+/* src_path != NULL: the image must have been made from exactly that file (size + mtime), else -> 2 ("stale"), no error text */
+int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **out, char *err)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(err, "can't open packed rsh image %s", path);
+    pack_header h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "EMSARPK1", 8) != 0 || h.T <= 0 || h.C < h.T || h.nF <= 0 || h.nnz < h.C || h.names_bytes < h.T) {
+        fclose(f);
+        return fail(err, "%s is not a packed rsh image", path);
+    }
+    if (src_path) {
+        int64_t sz, mt;
+        src_stamp(src_path, &sz, &mt);
+        if (sz != h.src_size || mt != h.src_mtime_ns) { fclose(f); return 2; }
+    }
+    emsar_rsh *r = (emsar_rsh *)calloc(1, sizeof(emsar_rsh));
+    r->T = h.T; r->nF = h.nF; r->min_fraglength = h.min_fraglength; r->max_fraglength = h.max_fraglength; r->readlength = h.readlength;
+    r->max_t_size = h.max_t_size; r->frag_min = h.frag_min; r->frag_max = h.frag_max; r->C = h.C;
+    r->class_ptr = (int64_t *)malloc(sizeof(int64_t) * ((size_t)h.C + 1));
+    r->class_tid = (int32_t *)malloc(sizeof(int32_t) * (size_t)(h.nnz > 0 ? h.nnz : 1));
+    r->euma = (int32_t *)malloc(sizeof(int32_t) * (size_t)h.C * h.nF);
+    r->has_node = (uint8_t *)malloc((size_t)h.C);
+    char *blob = (char *)malloc((size_t)h.names_bytes);
+    r->names = (char **)calloc((size_t)h.T, sizeof(char *));
+    int ok = r->class_ptr && r->class_tid && r->euma && r->has_node && blob && r->names;
+    ok = ok && fread(r->class_ptr, sizeof(int64_t), (size_t)h.C + 1, f) == (size_t)h.C + 1;
+    ok = ok && fread(r->class_tid, sizeof(int32_t), (size_t)h.nnz, f) == (size_t)h.nnz;
+    ok = ok && fread(r->euma, sizeof(int32_t), (size_t)h.C * h.nF, f) == (size_t)h.C * h.nF;
+    ok = ok && fread(r->has_node, 1, (size_t)h.C, f) == (size_t)h.C;
+    ok = ok && fread(blob, 1, (size_t)h.names_bytes, f) == (size_t)h.names_bytes;
+    fclose(f);
+    ok = ok && r->class_ptr[0] == 0 && r->class_ptr[h.C] == h.nnz && blob[h.names_bytes - 1] == 0;
+    if (ok) {
+        const char *p = blob, *end = blob + h.names_bytes;
+        for (int32_t t = 0; t < h.T; t++) {
+            if (p >= end) { ok = 0; break; }
+            r->names[t] = strdup(p);           /* emsar_rsh_free frees names one by one */
+            p += strlen(p) + 1;
+        }
+    }
+    free(blob);
+    if (!ok) { emsar_rsh_free(r); return fail(err, "packed rsh image %s is truncated or corrupt", path); }
+    uint32_t slots = 16;
+    while (slots < (uint32_t)r->T * 2u) slots <<= 1;
+    r->name_mask = slots - 1;
+    r->name_slots = (uint32_t *)calloc(slots, sizeof(uint32_t));
+    for (int32_t t = 0; t < r->T; t++) name_insert(r, t);
+    *out = r;
+    return 0;
+}
+
+/* What the command line uses for -I: `<path>.pack` when it is fresh, else the text (and, with EMSAR_RSH_CACHE set, the image is
+ * (re)written for the next run). A path that itself ends in ".pack" is loaded as an image. `from_cache`: 1 when no text was parsed. */
+int emsar_rsh_load_auto(const char *path, emsar_rsh **out, int *from_cache, char *err)
+{
+    if (from_cache) *from_cache = 0;
+    const size_t n = strlen(path);
+    if (n > 5 && strcmp(path + n - 5, ".pack") == 0) {
+        int rc = emsar_rsh_load_packed(path, NULL, out, err);
+        if (!rc && from_cache) *from_cache = 1;
+        return rc;
+    }
+    char pk[4096];
+    snprintf(pk, sizeof pk, "%s.pack", path);
+    struct stat st;
+    if (stat(pk, &st) == 0) {
+        char e2[EMSAR_HOST_ERRLEN];
+        if (emsar_rsh_load_packed(pk, path, out, e2) == 0) { if (from_cache) *from_cache = 1; return 0; }
+    }
+    int rc = emsar_rsh_load(path, out, err);
+    if (!rc && getenv("EMSAR_RSH_CACHE")) { char e2[EMSAR_HOST_ERRLEN]; emsar_rsh_save_packed(*out, pk, path, e2); }
+    return rc;
 }

@@ -56,6 +56,16 @@ def main():
         print(f"  reference emsar (whole run, -n 1 -i 1): {total:.1f} s; its own stamps put reading the BAM at ~{read_s} s "
               f"(1 s resolution) -> ~{n_rec / max(read_s or total, 1) / 1e6:.2f} M records/s")
     rsh.close()
+    # ---- §8 f3: text parse vs packed image of a larger index ----
+    big = synth.make_index(T=50000, n_multi=500000, alpha=2.4, kmax=99, seed=10, module_cap=500)
+    synth.write_rsh(big, f"{tmp}/big.rsh")
+    t0 = time.perf_counter(); a = host.Rsh(f"{tmp}/big.rsh"); t_text = time.perf_counter() - t0
+    a.save_packed(f"{tmp}/big.rsh.pack", src=f"{tmp}/big.rsh")
+    t0 = time.perf_counter(); b = host.Rsh(f"{tmp}/big.rsh", auto=True); t_pack = time.perf_counter() - t0
+    assert b.from_cache and a.C == b.C
+    print(f"rsh index T={a.T} C={a.C}: text {os.path.getsize(tmp + '/big.rsh') / 1e6:.0f} MB parsed in {t_text:.2f} s; packed image "
+          f"{os.path.getsize(tmp + '/big.rsh.pack') / 1e6:.0f} MB loaded in {t_pack:.2f} s (both include the copy into numpy)")
+    a.close(); b.close()
 
 
 if __name__ == "__main__":

@@ -60,3 +60,46 @@ def test_corrupt_block_is_an_error(pe_bam, tmp_path):
     with pytest.raises(host.HostError):
         host.read_alignments(rsh, str(trunc), pe=True, fmt="bam", io_threads=3)
     rsh.close()
+
+
+def _same_index(a, b):
+    return (a.T == b.T and a.C == b.C and a.nF == b.nF and np.array_equal(a.class_ptr, b.class_ptr) and np.array_equal(a.class_tid, b.class_tid)
+            and np.array_equal(a.euma, b.euma) and np.array_equal(a.has_node, b.has_node) and a.names == b.names
+            and (a.min_fraglength, a.max_fraglength, a.readlength, a.max_t_size, a.frag_min, a.frag_max) ==
+            (b.min_fraglength, b.max_fraglength, b.readlength, b.max_t_size, b.frag_min, b.frag_max))
+
+
+def test_packed_rsh_image_round_trip(built, tmp_path, monkeypatch):
+    """§8 f3: the packed image reproduces the parsed text index exactly and is dropped when the text changes."""
+    idx = synth.make_index(T=400, n_multi=3000, kmax=15, seed=8, module_cap=50, nF=21, frag_min=40, readlength=25, p_no_node=0.1)
+    txt = str(tmp_path / "x.rsh")
+    synth.write_rsh(idx, txt)
+    a = host.Rsh(txt)
+    a.save_packed(txt + ".pack", src=txt)
+    b = host.Rsh(txt + ".pack", packed=True, src=txt)
+    assert _same_index(a, b) and b.tid(a.names[17]) == a.tid(a.names[17]) and b.tid("no such transcript") == -1
+    c = host.Rsh(txt, auto=True)                     # what `emsar -I x.rsh` does
+    assert c.from_cache and _same_index(a, c)
+    for golden in ("pe.in.rsh", "built.in.rsh"):     # the reference's own text files
+        g = gu.materialize(golden, tmp_path)
+        ga = host.Rsh(g)
+        ga.save_packed(g + ".pack", src=g)
+        gb = host.Rsh(g, auto=True)
+        assert gb.from_cache and _same_index(ga, gb)
+        ga.close(); gb.close()
+    # the text changes (same content, new mtime): the image is stale, the text is parsed again and, with the switch on, re-cached
+    os.utime(txt, ns=(1, 1))
+    with pytest.raises(host.HostError):
+        host.Rsh(txt + ".pack", packed=True, src=txt)
+    d = host.Rsh(txt, auto=True)
+    assert not d.from_cache and _same_index(a, d)
+    monkeypatch.setenv("EMSAR_RSH_CACHE", "1")
+    e = host.Rsh(txt, auto=True)
+    f = host.Rsh(txt, auto=True)
+    assert not e.from_cache and f.from_cache and _same_index(a, f)
+    # garbage is rejected
+    (tmp_path / "bad.pack").write_bytes(b"EMSARPK1" + b"\0" * 40)
+    with pytest.raises(host.HostError):
+        host.Rsh(str(tmp_path / "bad.pack"), packed=True)
+    for r in (a, b, c, d, e, f):
+        r.close()
