@@ -96,6 +96,8 @@ extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
         cudaGetLastError();
     }
     g_cur_ctx = ctx;
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 9; i++) CU(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
     // [0..63] scalars of the EM kernel (delta slots, iteration count), then one 128-byte barrier line per CTA
@@ -122,6 +124,8 @@ extern "C" int emsar_cuda_close(emsar_ctx *ctx)
     cudaFree(ctx->d_scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 9; i++) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->pool) cudaMemPoolDestroy((cudaMemPool_t)ctx->pool);
     cudaStreamDestroy(ctx->stream);
     if (g_cur_ctx == ctx) g_cur_ctx = nullptr;

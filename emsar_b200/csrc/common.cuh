@@ -62,6 +62,8 @@ struct KSeg {          // multi-tid classes of one cardinality, contiguous in ci
 struct emsar_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;  // H2D of large read batches, overlapped with the counting kernel
+    cudaEvent_t copy_ev[9];
     cudaDeviceProp prop;
     void *pool;               // cudaMemPool_t of the stream-ordered allocations (NULL: plain cudaMalloc / cudaFree)
     int64_t launches;
