@@ -143,19 +143,19 @@ __global__ void k_nat_fill(int32_t T, const uint32_t *__restrict__ rflag, const 
 
 // E-phase cost lands on the row that owns the class (its first member)
 __global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
-                             const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost)
+                             const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost, int per_class)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_multi || !act[i]) return;
     const uint32_t o = cls_off[T + i];
-    atomicAdd(&ecost[nat[cls_tid[o]]], (int)(cls_off[T + i + 1] - o));
+    atomicAdd(&ecost[nat[cls_tid[o]]], (int)(cls_off[T + i + 1] - o) + per_class);       // gathers + the class's own work (divide, store)
 }
 
-__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost)
+__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost, int per_row)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > P) return;
-    cost[p] = p < P ? degn[p] + (uint32_t)ecost[p] + 2u : 0u;
+    cost[p] = p < P ? degn[p] + (uint32_t)ecost[p] + (uint32_t)per_row : 0u;
 }
 
 // cut the rows (natural order) into B ranges of equal cost
@@ -791,13 +791,17 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.blk_nhr = arena_take<int32_t>(ac, (size_t)B + 1);
     m.blk_nhc = arena_take<int32_t>(ac, (size_t)B + 1);
     // ---- rows: costs, ownership ranges, length-sorted order inside each CTA ----
+    // cost of a row = its M entries + the members of the classes it owns (one gather each) + fixed work per row / per class,
+    // in units of one gather (tuning knobs: EMSAR_COST_ROW / EMSAR_COST_CLASS)
+    const int cost_row = getenv("EMSAR_COST_ROW") ? atoi(getenv("EMSAR_COST_ROW")) : 2;
+    const int cost_class = getenv("EMSAR_COST_CLASS") ? atoi(getenv("EMSAR_COST_CLASS")) : 0;
     k_nat_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_nat, d_deg, d_pos, d_degn, d_tn, d_ecost, P);
     LAUNCHED(ctx);
     if (nm > 0) {
-        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_nat, d_ecost);
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_nat, d_ecost, cost_class);
         LAUNCHED(ctx);
     }
-    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost);
+    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost, cost_row);
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cost, d_costp, P + 1, st));
     LAUNCHED(ctx);
