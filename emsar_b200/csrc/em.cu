@@ -1088,6 +1088,11 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     CU(cudaEventRecord(ctx->ev0, st));
+    // the limit is a per-device attribute of the function, not of this context: another context of the process (another GPU, or a
+    // differently sized test context) may have changed it since
+    const void *fn = s->sharded ? (const void *)k_em_persistent<2> : dataflow ? (const void *)k_em_persistent<3>
+                     : s->m.direct ? (const void *)k_em_persistent<1> : (const void *)k_em_persistent<0>;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));
     if (s->sharded) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<2>, p));
     else if (dataflow) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<3>, p));
     else if (s->m.direct) CU(cudaLaunchKernelEx(&cfg, k_em_persistent<1>, p));

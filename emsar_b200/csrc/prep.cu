@@ -55,6 +55,59 @@ __global__ void __launch_bounds__(ADJ_ROWS) k_adjeuma(int64_t C, int nF, const i
     if (row < C) adj[row] = has_node[row] ? acc : 0.0;
 }
 
+
+// Streaming version for nF a multiple of 4 (row starts are then 16-byte aligned): the only kernel of the path that is bound by
+// HBM proper - 4*C*nF bytes, 3.2 GB at config #3. A CTA owns 128 consecutive rows (one contiguous piece of the matrix) and walks
+// their columns in chunks of 64 through a 3-stage cp.async pipeline (16-byte copies straight into shared memory, no registers
+// in between), so that ~200 KB per SM are in flight while thread r adds up row r. The sum itself stays strictly sequential in
+// the column index (compute_adjEUMA :2517-2523; no FMA contraction), which is what makes the result bit-identical to the
+// reference; rows are padded to 68 words in shared memory, (68 / 4) odd, so the 128-bit reads of a quarter-warp hit distinct banks.
+constexpr int AJ_ROWS = 128, AJ_COLS = 64, AJ_STRIDE = AJ_COLS + 4, AJ_STAGES = 3;
+constexpr int AJ_SMEM = AJ_STAGES * AJ_ROWS * AJ_STRIDE * 4;
+__global__ void __launch_bounds__(AJ_ROWS) k_adjeuma_stream(int64_t C, int nF, const int32_t *__restrict__ euma, const uint8_t *__restrict__ has_node,
+                                                             const double *__restrict__ Wf, double *__restrict__ adj)
+{
+    extern __shared__ __align__(16) int aj_sm[];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * AJ_ROWS;
+    const int nch = (nF + AJ_COLS - 1) / AJ_COLS;
+    auto issue = [&](int ch) {
+        if (ch < nch) {
+            int *stage = aj_sm + (ch % AJ_STAGES) * (AJ_ROWS * AJ_STRIDE);
+#pragma unroll 4
+            for (int k = 0; k < AJ_ROWS * (AJ_COLS / 4) / AJ_ROWS; k++) {
+                const int idx = tid + k * AJ_ROWS, r = idx >> 4, q = idx & 15, col = ch * AJ_COLS + q * 4;
+                const int64_t gr = row0 + r;
+                if (gr < C && col < nF) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + r * AJ_STRIDE + q * 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(euma + gr * nF + col) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int c = 0; c < AJ_STAGES - 1; c++) issue(c);
+    double acc = 0;
+    for (int ch = 0; ch < nch; ch++) {
+        issue(ch + AJ_STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(AJ_STAGES - 1) : "memory");
+        __syncthreads();
+        const int4 *rowp = (const int4 *)(aj_sm + (ch % AJ_STAGES) * (AJ_ROWS * AJ_STRIDE) + tid * AJ_STRIDE);
+        const int c0 = ch * AJ_COLS, lim = min(AJ_COLS, nF - c0) >> 2;
+        for (int q = 0; q < lim; q++) {
+            const int4 v = rowp[q];
+            const double *w = Wf + c0 + q * 4;
+            acc += w[0] * (double)v.x;
+            acc += w[1] * (double)v.y;
+            acc += w[2] * (double)v.z;
+            acc += w[3] * (double)v.w;
+        }
+        __syncthreads();                       // the stage is refilled two iterations from now
+    }
+    const int64_t row = row0 + tid;
+    if (row < C) adj[row] = has_node[row] ? acc : 0.0;
+}
+
 // EUMAps, modelled / active flags.  nscale = (double)N / 1e6, p10 = pow(10, DELTA) (both formed on the host exactly
 // as construct_EUMAps does).
 __global__ void k_class_model(int64_t C, int32_t T, const double *__restrict__ adj, const uint8_t *__restrict__ in_model,
@@ -614,7 +667,12 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     long long *d_N = (long long *)(s->d_Wf + ix->nF);
     k_wf<<<1, 32, 0, st>>>(s->d_hist, ix->frag_min, ix->nF, ix->max_fl, s->d_Wf, d_N);
     LAUNCHED(ctx);
-    k_adjeuma<<<(unsigned)((C + ADJ_ROWS - 1) / ADJ_ROWS), ADJ_ROWS, 0, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+    if (ix->nF >= 16 && ix->nF % 4 == 0 && !getenv("EMSAR_ADJEUMA_SIMPLE")) {
+        CU(cudaFuncSetAttribute(k_adjeuma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, AJ_SMEM));       // per device; cheap
+        k_adjeuma_stream<<<(unsigned)((C + AJ_ROWS - 1) / AJ_ROWS), AJ_ROWS, AJ_SMEM, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+    } else {
+        k_adjeuma<<<(unsigned)((C + ADJ_ROWS - 1) / ADJ_ROWS), ADJ_ROWS, 0, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+    }
     LAUNCHED(ctx);
     CU(cudaGetLastError());
     long long N = 0;
