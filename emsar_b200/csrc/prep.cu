@@ -58,15 +58,16 @@ __global__ void __launch_bounds__(ADJ_ROWS) k_adjeuma(int64_t C, int nF, const i
 
 // Streaming version for nF a multiple of 4 (row starts are then 16-byte aligned): the only kernel of the path that is bound by
 // HBM proper - 4*C*nF bytes, 3.2 GB at config #3. A CTA owns 128 consecutive rows (one contiguous piece of the matrix) and walks
-// their columns in chunks of 64 through a 3-stage cp.async pipeline (16-byte copies straight into shared memory, no registers
-// in between), so that ~200 KB per SM are in flight while thread r adds up row r. The sum itself stays strictly sequential in
+// their columns in chunks of AJ_COLS through an AJ_STAGES-deep cp.async pipeline (16-byte copies straight into shared memory,
+// no registers in between), so that ~150 KB per SM are in flight while thread r adds up row r. The sum itself stays strictly sequential in
 // the column index (compute_adjEUMA :2517-2523; no FMA contraction), which is what makes the result bit-identical to the
-// reference; rows are padded to 68 words in shared memory, (68 / 4) odd, so the 128-bit reads of a quarter-warp hit distinct banks.
-constexpr int AJ_ROWS = 128, AJ_COLS = 64, AJ_STRIDE = AJ_COLS + 4, AJ_STAGES = 3;
-constexpr int AJ_SMEM = AJ_STAGES * AJ_ROWS * AJ_STRIDE * 4;
+// reference; rows are padded to AJ_COLS + 4 words in shared memory, ((AJ_COLS + 4) / 4) odd, so the 128-bit reads of a
+// quarter-warp hit distinct banks.
+template <int AJ_ROWS, int AJ_COLS, int AJ_STAGES>
 __global__ void __launch_bounds__(AJ_ROWS) k_adjeuma_stream(int64_t C, int nF, const int32_t *__restrict__ euma, const uint8_t *__restrict__ has_node,
                                                              const double *__restrict__ Wf, double *__restrict__ adj)
 {
+    constexpr int AJ_STRIDE = AJ_COLS + 4, Q = AJ_COLS / 4;      // (AJ_STRIDE / 4) is odd for AJ_COLS = 64, 128
     extern __shared__ __align__(16) int aj_sm[];
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * AJ_ROWS;
@@ -75,8 +76,8 @@ __global__ void __launch_bounds__(AJ_ROWS) k_adjeuma_stream(int64_t C, int nF, c
         if (ch < nch) {
             int *stage = aj_sm + (ch % AJ_STAGES) * (AJ_ROWS * AJ_STRIDE);
 #pragma unroll 4
-            for (int k = 0; k < AJ_ROWS * (AJ_COLS / 4) / AJ_ROWS; k++) {
-                const int idx = tid + k * AJ_ROWS, r = idx >> 4, q = idx & 15, col = ch * AJ_COLS + q * 4;
+            for (int k = 0; k < Q; k++) {
+                const int idx = tid + k * AJ_ROWS, r = idx / Q, q = idx % Q, col = ch * AJ_COLS + q * 4;
                 const int64_t gr = row0 + r;
                 if (gr < C && col < nF) {
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + r * AJ_STRIDE + q * 4);
@@ -102,10 +103,19 @@ __global__ void __launch_bounds__(AJ_ROWS) k_adjeuma_stream(int64_t C, int nF, c
             acc += w[2] * (double)v.z;
             acc += w[3] * (double)v.w;
         }
-        __syncthreads();                       // the stage is refilled two iterations from now
+        __syncthreads();                       // the stage is refilled AJ_STAGES - 1 iterations from now
     }
     const int64_t row = row0 + tid;
     if (row < C) adj[row] = has_node[row] ? acc : 0.0;
+}
+template <int R, int Cc, int S>
+static int launch_adjeuma_stream(emsar_sample *s, cudaStream_t st)
+{
+    emsar_index *ix = s->index;
+    constexpr int smem = S * R * (Cc + 4) * 4;
+    CU(cudaFuncSetAttribute(k_adjeuma_stream<R, Cc, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       // per device; cheap
+    k_adjeuma_stream<R, Cc, S><<<(unsigned)((ix->C + R - 1) / R), R, smem, st>>>(ix->C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+    return EMSAR_OK;
 }
 
 // EUMAps, modelled / active flags.  nscale = (double)N / 1e6, p10 = pow(10, DELTA) (both formed on the host exactly
@@ -668,8 +678,9 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     k_wf<<<1, 32, 0, st>>>(s->d_hist, ix->frag_min, ix->nF, ix->max_fl, s->d_Wf, d_N);
     LAUNCHED(ctx);
     if (ix->nF >= 16 && ix->nF % 4 == 0 && !getenv("EMSAR_ADJEUMA_SIMPLE")) {
-        CU(cudaFuncSetAttribute(k_adjeuma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, AJ_SMEM));       // per device; cheap
-        k_adjeuma_stream<<<(unsigned)((C + AJ_ROWS - 1) / AJ_ROWS), AJ_ROWS, AJ_SMEM, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+        // 128 rows x 32 columns x 3 stages = 54 KB per CTA -> 4 CTAs (512 row sums in flight) per SM: the best of the
+        // {64,128,256} x {16,32,64,128} x {2,3,4} sweep (profiles/r1i_adjeuma.txt); fewer resident rows starve the fp64 add chains
+        TRY((launch_adjeuma_stream<128, 32, 3>(s, st)));
     } else {
         k_adjeuma<<<(unsigned)((C + ADJ_ROWS - 1) / ADJ_ROWS), ADJ_ROWS, 0, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
     }
