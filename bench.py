@@ -94,6 +94,33 @@ def make_workload(name, seed):
     return idx, reads, time.time() - t0
 
 
+def reference_binary_twin(cores):
+    """the UNMODIFIED reference binary (oracle/_ref/emsar, compiled from /root/reference by oracle/Makefile) on the
+    scaled twin of config #2 (T = 20K, C ~ 190K, 3M reads, modules <= 500): its estimator is quadratic in module size and cannot
+    finish the full config. One round (-n 1) instead of its default four. Returns None when the binary did not travel here."""
+    import re
+    import tempfile
+    from emsar_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "emsar")
+    if not os.path.exists(ref):
+        return None
+    idx, reads, _ = make_workload("small", seed=1000)
+    d = tempfile.mkdtemp(prefix="emsar_twin_")
+    synth.write_rsh(idx, d + "/x.rsh")
+    synth.write_bowtie_se(idx, reads, d + "/x.bowtie")
+    t0 = time.perf_counter()
+    out = subprocess.run([ref, "-p", str(cores), "-n", "1", "-I", d + "/x.rsh", d + "/out", "p", d + "/x.bowtie"], capture_output=True, text=True)
+    sec = time.perf_counter() - t0
+    hms = [int(h) * 3600 + int(m) * 60 + int(s_) for h, m, s_ in re.findall(r"\d\d/\d\d,(\d\d):(\d\d):(\d\d)", out.stdout)]
+    mle = None
+    m = re.search(r"round 1/1\.\.\.\n\d\d/\d\d,(\d\d):(\d\d):(\d\d)(?s:.*?)computing effective length[^\n]*\n\d\d/\d\d,(\d\d):(\d\d):(\d\d)", out.stdout)
+    if m:
+        a = [int(x) for x in m.groups()]
+        mle = (a[3] * 3600 + a[4] * 60 + a[5]) - (a[0] * 3600 + a[1] * 60 + a[2])
+    return {"seconds": sec, "samples_per_min": 60.0 / sec, "mle_seconds": mle, "rc": out.returncode, "threads": cores,
+            "workload": f"scaled twin: T={idx.T} C={idx.C} reads={len(reads.read_fraglen)}, modules <= 500 transcripts, -n 1"}
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path: no EM exists in parklab/emsar, so the
     metric 'EM iterations/s' is timed on the oracle port (same update as the CUDA kernel) with all host threads;
@@ -120,6 +147,8 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": f"{iters} EM iterations per step of the full {args.workload} model, pthread team of {cores}"},
             "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.ref_binary:
+        line["reference_binary"] = reference_binary_twin(cores)
     print(json.dumps(line), flush=True)
 
 
@@ -134,6 +163,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converge", action="store_true", help="skip the one-off run to convergence (samples/min)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg (e2e is then null)")
+    ap.add_argument("--ref-binary", action="store_true",
+                    help="--impl reference only: also time the unmodified reference binary on the scaled twin (about 1-2 minutes)")
     ap.add_argument("--shard", default="samples", choices=["samples", "classes"],
                     help="N>1: independent samples per GPU (-M list, weak scaling, the default) or ONE sample whose classes are "
                          "range-sharded over the GPUs with the per-iteration all-reduce (BASELINE.json configs[2], strong scaling)")

@@ -11,6 +11,9 @@
  *   - -k above 1024 is rejected (device sort limit, EMSAR_MAX_READ_TIDS);
  *   - EMSAR_DEVICES=0,1,.. spreads the files of a -M list over several GPUs (one host thread per GPU, no
  *     communication); EUMAcut then persists per GPU instead of per run.
+ *   - EMSAR_DEVICES=0,1,.. with EMSAR_SHARD=classes puts EVERY sample on all the GPUs: the sample's active classes are
+ *     range-sharded, theta is all-reduced over NVLink every iteration (BASELINE.json configs[2]); GPU 0 reads and counts,
+ *     the other GPUs join the collectives, the first GPU writes the files.
  */
 #define _GNU_SOURCE
 #include <getopt.h>
@@ -96,15 +99,21 @@ static void pinned_free(void *user, void *p) { emsar_host_free((emsar_ctx *)user
 
 typedef struct {
     const options *o; const emsar_rsh *rsh; int device, worker, nworker; int rc;
+    int by_class;                      /* EMSAR_SHARD=classes */
+    uint8_t *comm_id;                  /* shared: NCCL unique id made by worker 0 */
+    pthread_barrier_t *bar;
 } worker_arg;
 
-static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsar_index *ix, int i, double *eumacut)
+static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsar_index *ix, int i, double *eumacut, int shard_rank, int shard_n)
 {
+    /* shard_n > 1: this sample runs on shard_n GPUs at once; rank 0 reads, counts and writes, the others only take part in the
+     * collectives (counts all-reduce, per-iteration all-reduce inside emsar_sample_solve) */
+    const int sharded = shard_n > 1, lead = shard_rank == 0;
     char err[EMSAR_HOST_ERRLEN] = "";
     emsar_sample *s = NULL;
     int rc = emsar_sample_begin(ix, &s);
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
-    fprintf(stdout, "alnfile[%d]=%s\n", i, o->aln[i]);
+    if (lead) fprintf(stdout, "alnfile[%d]=%s\n", i, o->aln[i]);
     emsar_reader_opts ro;
     memset(&ro, 0, sizeof ro);
     ro.pe = o->pe; ro.strand = o->strand; ro.max_repeat = o->max_repeat; ro.format = o->bamflag; ro.batch_reads = 1 << 20;
@@ -114,20 +123,24 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
     count_ctx cc = {s, ctx, 0, 0, 0};
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    if (emsar_read_alignments(rsh, o->aln[i], &ro, &readlength, on_batch, &cc, err)) {
-        if (cc.rc) die("%s: %s", emsar_cuda_strerror(cc.rc), emsar_cuda_last_error());
-        die("%s", err);
-    }
-    if ((rc = emsar_sample_count_wait(s, 0))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    if (lead) {
+        if (emsar_read_alignments(rsh, o->aln[i], &ro, &readlength, on_batch, &cc, err)) {
+            if (cc.rc) die("%s: %s", emsar_cuda_strerror(cc.rc), emsar_cuda_last_error());
+            die("%s", err);
+        }
+        if ((rc = emsar_sample_count_wait(s, 0))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    } else if ((rc = emsar_sample_count(s, 0, NULL, NULL, NULL))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    if (sharded && (rc = emsar_sample_counts_allreduce(s))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());   /* everybody gets rank 0's counts */
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    if (o->verbose > 0) {
+    if (o->verbose > 0 && lead) {
         const double sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
         fprintf(stdout, "alignments read: %lld read groups in %lld batches, %.2f s (%.2f M groups/s, %d inflate threads)\n", (long long)cc.groups,
                 (long long)cc.batches, sec, sec > 0 ? 1e-6 * (double)cc.groups / sec : 0.0, ro.io_threads);
     }
-    stamp(o, "\nscanning rsh array and constructing EUMA, ReadCount and CT array...");
+    if (lead) stamp(o, "\nscanning rsh array and constructing EUMA, ReadCount and CT array...");
     emsar_solve_opts so;
     memset(&so, 0, sizeof so);
+    so.sharded = sharded;
     so.eps_abs = o->eps_abs; so.eps_rel = o->eps_rel; so.max_iter = o->max_iter; so.delta = o->delta; so.eumacut = *eumacut;
     emsar_solve_out out;
     memset(&out, 0, sizeof out);
@@ -139,8 +152,18 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
     out.tpm = (double *)malloc(sizeof(double) * T);
     rc = emsar_sample_solve(s, &so, &out);
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
-    if (out.eumacut != *eumacut && o->verbose > 0) fprintf(stdout, "module size too big. EUMAcut is readjusted to %.0f\n", out.eumacut);
+    if (out.eumacut != *eumacut && o->verbose > 0 && lead) fprintf(stdout, "module size too big. EUMAcut is readjusted to %.0f\n", out.eumacut);
     *eumacut = out.eumacut;   /* EUMAcut is a global that is never reset between files (emsar.h:94) */
+    if (!lead) {               /* the other ranks hold the same result; only the first one writes it */
+        free(out.fpkm); free(out.efflen); free(out.ireadcount); free(out.ireadcount_int); free(out.tpm);
+        emsar_sample_end(s);
+        return 0;
+    }
+    if (sharded && o->verbose > 0) {
+        int32_t pm = 0;
+        emsar_comm_info(ctx, NULL, NULL, &pm);
+        fprintf(stdout, "sample sharded by class range over %d GPUs (%s)\n", shard_n, pm == 1 ? "all-reduce inside the EM kernel, NVLink peer memory" : "ncclAllReduce per iteration");
+    }
     if (o->verbose > 0)
         fprintf(stdout, "EM finished: %d iterations, delta %.3g, %.1f ms on the device (model build %.1f ms), logL %.10g\n",
                 out.n_iter, out.final_delta, out.em_ms, out.prep_ms, out.loglik);
@@ -188,7 +211,15 @@ static void *worker(void *p)
     rc = emsar_index_create(ctx, &d, &ix);
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
     double eumacut = 0;
-    for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ctx, ix, i, &eumacut);
+    if (w->by_class) {
+        if (w->worker == 0 && (rc = emsar_comm_unique_id(w->comm_id))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+        pthread_barrier_wait(w->bar);
+        if ((rc = emsar_comm_init(ctx, w->worker, w->nworker, w->comm_id))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+        for (int i = 0; i < o->naln; i++) run_file(o, r, ctx, ix, i, &eumacut, w->worker, w->nworker);      /* every file on all GPUs */
+        emsar_comm_destroy(ctx);
+    } else {
+        for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ctx, ix, i, &eumacut, 0, 1);
+    }
     emsar_index_destroy(ix);
     emsar_cuda_close(ctx);
     return NULL;
@@ -301,10 +332,19 @@ int main(int argc, char *argv[])
     const char *env = getenv("EMSAR_DEVICES");
     if (env && *env) { char *dup = strdup(env), *sv = NULL; for (char *t = strtok_r(dup, ",", &sv); t && ndev < 64; t = strtok_r(NULL, ",", &sv)) devs[ndev++] = atoi(t); free(dup); }
     if (ndev == 0) devs[ndev++] = 0;
-    if (ndev > o.naln) ndev = o.naln;
+    const char *shard = getenv("EMSAR_SHARD");
+    const int by_class = shard && !strcmp(shard, "classes") && ndev > 1;
+    if (by_class && ndev > 8) die("error: EMSAR_SHARD=classes supports at most 8 GPUs.");
+    if (!by_class && ndev > o.naln) ndev = o.naln;
     pthread_t th[64];
     worker_arg wa[64];
-    for (int w = 0; w < ndev; w++) { wa[w].o = &o; wa[w].rsh = rsh; wa[w].device = devs[w]; wa[w].worker = w; wa[w].nworker = ndev; wa[w].rc = 0; }
+    uint8_t comm_id[128];
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)ndev);
+    for (int w = 0; w < ndev; w++) {
+        wa[w].o = &o; wa[w].rsh = rsh; wa[w].device = devs[w]; wa[w].worker = w; wa[w].nworker = ndev; wa[w].rc = 0;
+        wa[w].by_class = by_class; wa[w].comm_id = comm_id; wa[w].bar = &bar;
+    }
     for (int w = 1; w < ndev; w++) pthread_create(&th[w], NULL, worker, &wa[w]);
     worker(&wa[0]);
     for (int w = 1; w < ndev; w++) pthread_join(th[w], NULL);

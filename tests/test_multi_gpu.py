@@ -96,3 +96,34 @@ def test_class_sharded_logic_gloo_world2(built):
         assert p.exitcode == 0
     assert all(e <= 1e-12 for _, e, _ in res), res
     assert all(n > 0 for _, _, n in res)
+
+
+@pytest.mark.gpu
+def test_cli_class_sharded_two_gpus(built, tmp_path):
+    """`EMSAR_SHARD=classes EMSAR_DEVICES=0,1 emsar ...`: one sample on two GPUs (host threads of one process, peer access
+    instead of CUDA IPC) must write the files the single-GPU run writes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as gu
+    fx = gu.FIXTURES["pe"]
+    rsh, aln = gu.materialize(fx["rsh"], tmp_path), gu.materialize(fx["aln"], tmp_path)
+    emsar = os.path.join(ROOT, "emsar_b200", "bin", "emsar")
+    outs = {}
+    for tag, env_extra in (("one", {}), ("two", {"EMSAR_DEVICES": "0,1", "EMSAR_SHARD": "classes"})):
+        out = os.path.join(str(tmp_path), tag)
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([emsar, "-g", "-P", "-S", "-k", str(fx["k"]), "-s", fx["strand"], "-I", rsh, out, "p", aln], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = (out, r.stdout)
+    assert "sharded by class range over 2 GPUs" in outs["two"][1]
+    a, b = outs["one"][0], outs["two"][0]
+    assert gu.parse_out_file(a + "/p.0.fraglength_effect") == gu.parse_out_file(b + "/p.0.fraglength_effect")
+    sa, sb = gu.parse_out_file(a + "/p.0.segments"), gu.parse_out_file(b + "/p.0.segments")
+    assert [r[:6] for r in sa] == [r[:6] for r in sb]
+    fa, fb = gu.parse_out_file(a + "/p.0.fpkm"), gu.parse_out_file(b + "/p.0.fpkm")
+    assert [r[0] for r in fa] == [r[0] for r in fb]
+    for col in (1, 4, 6):           # FPKM, iReadcount, TPM: same optimum, sums in a different order
+        x, y = np.array([float(r[col]) for r in fa]), np.array([float(r[col]) for r in fb])
+        assert np.allclose(x, y, rtol=1e-6, atol=2e-6), col
