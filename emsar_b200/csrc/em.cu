@@ -1074,11 +1074,12 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     attrs[na].val.cooperative = 1;
     na++;
     if (ctx->l2_persist_bytes > 0 && s->state_bytes > 0) {
-        // the global copies of theta | q (halo traffic) stay resident in L2 while the index streams through
-        size_t win = s->state_bytes;
+        // the global copies of theta | q (halo traffic; in the barrier-free kernel their tagged slots) stay resident in L2 while
+        // the index streams through
+        size_t win = dataflow ? s->slots_bytes : s->state_bytes;
         if (win > (size_t)ctx->prop.accessPolicyMaxWindowSize) win = (size_t)ctx->prop.accessPolicyMaxWindowSize;
         attrs[na].id = cudaLaunchAttributeAccessPolicyWindow;
-        attrs[na].val.accessPolicyWindow.base_ptr = s->d_state;
+        attrs[na].val.accessPolicyWindow.base_ptr = dataflow ? s->d_slots : (void *)s->d_state;
         attrs[na].val.accessPolicyWindow.num_bytes = win;
         attrs[na].val.accessPolicyWindow.hitRatio = win <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)win;
         attrs[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
