@@ -3,7 +3,7 @@ import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__
 import bench
 from emsar_b200.api import Context, Index
 from emsar_b200 import _lib
-idx, reads, _ = bench.make_workload("config2_human_se", 1000)
+idx, reads, _ = bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "config2_human_se", 1000)
 ctx = Context(0); ix = Index(ctx, idx); s = ix.sample()
 s.count(reads.read_ptr, reads.read_tid, reads.read_fraglen); s.prepare()
 s.em_run(max_iter=50, stop_on_conv=False)
