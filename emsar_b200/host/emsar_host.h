@@ -44,6 +44,21 @@ int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_
 int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **out, char *err);   /* 2 = stale w.r.t. src_path */
 int emsar_rsh_load_auto(const char *path, emsar_rsh **out, int *from_cache, char *err);          /* <path>.pack if fresh, else text */
 
+/* ---- index construction from a fasta (what emsar-build / emsar -x do; emsar_b200/host/build_index.c) ---- */
+typedef struct {
+    int pe;                        /* -P */
+    int stranded;                  /* library strand type other than "ns" */
+    int readlength;                /* PE: the read length */
+    int readlen_min, readlen_max;  /* SE: read length range ("50" or "48-52") */
+    int min_fraglength, max_fraglength; /* PE: -f / -F (reference defaults 1 / 400) */
+    int max_repeat;                /* -k MAX_REPEAT: substrings occurring this often or more are dropped (default 100) */
+    char header;                   /* 'E' Ensembl header (name up to the first blank, default), 'R' RefSeq (4th '|' field) */
+} emsar_build_opts;
+int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh **out, char *err);
+/* read length(s) of an alignment file, as emsar -x learns them (emsar_main.c:306-316): PE -> the first aligned record,
+ * SE -> minimum and maximum over the whole file */
+int emsar_sniff_readlengths(const char *path, char format, int pe, int *rl_min, int *rl_max, char *err);
+
 /* ---- alignment readers ------------------------------------------------------------------------ */
 typedef struct {
     int pe;            /* -P */

@@ -5,8 +5,9 @@
  * Differences that are visible and deliberate:
  *   - the estimator is one deterministic EM run, not NUM_ROUND random restarts: `sd.of.FPKM` prints 0.000000, -n is
  *     accepted and ignored; -e / -r / -i map to eps_abs / eps_rel / max EM iterations when given;
- *   - -x (build the index from a fasta inside emsar) is not part of the hot path: it fails with a message that
- *     points to emsar-build + -I;  -T (print suffix array) likewise;  -m/-W/-w (positional bias, undocumented and
+ *   - -x builds the index on the host first (emsar_b200/host/build_index.c: same classes and counts as the reference's
+ *     suffix-array construction, the read length(s) are learnt from the first alignment file like emsar_main.c:306-316);
+ *     -T (print suffix array) is rejected: there is no suffix array;  -m/-W/-w (positional bias, undocumented and
  *     half-implemented in the reference) are rejected;
  *   - -k above 1024 is rejected (device sort limit, EMSAR_MAX_READ_TIDS);
  *   - EMSAR_DEVICES=0,1,.. spreads the files of a -M list over several GPUs (one host thread per GPU, no
@@ -35,7 +36,7 @@ typedef struct {
     char rshfile[FILENAMEMAX], fasta[FILENAMEMAX], strand_str[8];
     int pe, multisample, print_segments, print_rsh, verbose, max_repeat, nthread, max_iter;
     int min_fl, max_fl, num_round;
-    char bamflag, strand;
+    char bamflag, strand, fasta_header;
     double eps_abs, eps_rel, delta;
     const char *outdir, *outprefix;
     char **aln; int naln;
@@ -66,7 +67,9 @@ static void stamp(const options *o, const char *what)
 static void usage(const char *p)
 {
     fprintf(stdout,
-            "usage: %s <options> -I rshfile outdir outprefix [alignmentfile | listfile (with -M)]\n"
+            "usage: %s <options> -I rshfile | -x fastafile  outdir outprefix [alignmentfile | listfile (with -M)]\n"
+            "  -x fastafile build the index from the transcriptome first (read lengths are taken from the first alignment file;\n"
+            "               -h E|R fasta header style, -F/-f fragment length range for -P, -k also caps repeated substrings)\n"
             "  -I rshfile   rsh index built by emsar-build          -M  third argument is a list of alignment files\n"
             "  -P           paired-end                              -s  ns|ssf|ssr (SE)  ns|ssfr|ssrf (PE)\n"
             "  -S / -B      SAM / BAM input (default: bowtie out)   -k  max alignments per read (default 100)\n"
@@ -251,7 +254,8 @@ int main(int argc, char *argv[])
         case 'x': strncpy(o.fasta, optarg, FILENAMEMAX - 1); break;
         case 'P': o.pe = 1; break;
         case 's': strncpy(o.strand_str, optarg, sizeof(o.strand_str) - 1); break;
-        case 'b': case 'h': case 't': case 'l': case 'H': break;                 /* index-build / MLE-loop knobs: accepted, unused */
+        case 'h': o.fasta_header = optarg[0]; if (o.fasta_header != 'E' && o.fasta_header != 'R') die("error: invalid fasta option."); break;
+        case 'b': case 't': case 'l': case 'H': break;                           /* suffix-array / MLE-loop knobs: accepted, unused */
         case 'p': o.nthread = atoi(optarg); if (o.nthread < 1) die("error: number of threads must be at least 1 (option -p)."); break;
         case 'F': o.max_fl = atoi(optarg); break;
         case 'f': o.min_fl = atoi(optarg); break;
@@ -276,8 +280,6 @@ int main(int argc, char *argv[])
         }
     }
     if (strlen(o.rshfile) == 0 && strlen(o.fasta) == 0) die("error: either fasta file or an rsh file must be used as an input.");
-    if (strlen(o.rshfile) == 0)
-        die("error: -x builds the rsh index from a fasta, which is outside the GPU hot path: run emsar-build once and pass its output with -I.");
     if (o.min_fl > o.max_fl || o.min_fl < 1 || o.max_fl < 1) die("error: invalid fragment length range.");
     /* set_library_strand_type (:16-22); unlike the reference an unknown type IS an error here */
     if (!strcmp(o.strand_str, "ns")) o.strand = 0;
@@ -305,6 +307,7 @@ int main(int argc, char *argv[])
     }
     if (o.naln == 0) { fprintf(stderr, "No alignment files in the alignment list\n"); return 1; }
     if (o.verbose > 0) {
+        if (strlen(o.rshfile) == 0) fprintf(stdout, "input fastafile name= %s\n", o.fasta);
         fprintf(stdout, "input rshfile name= %s\nInput type= %s\nPaired-end= %c\nstrand type= %s\nMultisample= %c\nMAX_REPEAT= %d\n", o.rshfile,
                 o.bamflag == 0 ? "default bowtie output" : (o.bamflag == 's' ? "SAM" : "BAM"), o.pe ? 'y' : 'n', o.strand_str, o.multisample ? 'y' : 'n', o.max_repeat);
         fprintf(stdout, "print segments = %c\nprint rsh structure = %c\nfinished reading options and arguments..\n", o.print_segments ? 'y' : 'n', o.print_rsh ? 'y' : 'n');
@@ -317,7 +320,22 @@ int main(int argc, char *argv[])
     char err[EMSAR_HOST_ERRLEN] = "";
     emsar_rsh *rsh = NULL;
     int from_cache = 0;       /* <rshfile>.pack (written when EMSAR_RSH_CACHE is set) replaces the text parse while it is fresh */
-    if (emsar_rsh_load_auto(o.rshfile, &rsh, &from_cache, err)) { printf("%s\n", err); exit(1); }
+    if (strlen(o.rshfile) == 0) {
+        /* -x: learn the read length(s) from the first alignment file, then build the index from the fasta (emsar_main.c:300-346) */
+        emsar_build_opts bo;
+        memset(&bo, 0, sizeof bo);
+        bo.pe = o.pe; bo.stranded = o.strand != 0; bo.max_repeat = o.max_repeat; bo.header = o.fasta_header ? o.fasta_header : 'E';
+        bo.min_fraglength = o.min_fl; bo.max_fraglength = o.max_fl;
+        int rl0 = 0, rl1 = 0;
+        if (emsar_sniff_readlengths(o.aln[0], o.bamflag, o.pe, &rl0, &rl1, err)) die("%s", err);
+        if (o.pe) bo.readlength = rl0; else { bo.readlen_min = rl0; bo.readlen_max = rl1; }
+        if (o.verbose > 0) {
+            if (o.pe) fprintf(stdout, "read length : %d\n", rl0);
+            else fprintf(stdout, "read length range : %d - %d\n", rl0, rl1);
+        }
+        stamp(&o, "building the rsh index from the fasta file...");
+        if (emsar_rsh_build(o.fasta, &bo, &rsh, err)) { printf("%s\n", err); exit(1); }
+    } else if (emsar_rsh_load_auto(o.rshfile, &rsh, &from_cache, err)) { printf("%s\n", err); exit(1); }
     if (from_cache && o.verbose > 0) fprintf(stdout, "rsh index taken from its packed image\n");
     fprintf(stderr, "done reading rsh. rshsize=%lld\n", (long long)(rsh->C - rsh->T));
     if (o.verbose > 0) fprintf(stdout, "max_tid=%d, rshsize=%lld, max_cid=%lld\n", rsh->T - 1, (long long)(rsh->C - rsh->T), (long long)rsh->C - 1);

@@ -700,6 +700,46 @@ static int read_sam(const emsar_rsh *rs, const char *path, const emsar_reader_op
     return rc;
 }
 
+int emsar_sniff_readlengths(const char *path, char format, int pe, int *rl_min, int *rl_max, char *err)
+{
+    int mn = 30000, mx = 0, seen = 0, rc = 0;           /* the reference's initial values (:272-273) */
+    if (format == 0) {
+        FILE *fp = (path[0] == 0) ? stdin : fopen(path, "r");
+        if (!fp) return fail(err, "can't open bowtie file.");
+        char *line = NULL; size_t cap = 0; ssize_t n;
+        while ((n = getline(&line, &cap, fp)) >= 0) {
+            if (n > 0 && line[n - 1] == '\n') line[--n] = 0;
+            btline a;
+            bt_parse(line, &a);
+            if (a.nfield < 7) { rc = fail(err, "Error: input alignment file doesn't look like bowtieout file."); break; }
+            if (a.seqlen < mn) mn = a.seqlen;
+            if (a.seqlen > mx) mx = a.seqlen;
+            seen = 1;
+            if (pe) break;
+        }
+        free(line);
+        if (fp != stdin) fclose(fp);
+    } else {
+        samfile s;
+        if (sam_open(&s, path, format, 2, err)) { sam_close(&s); return 1; }
+        samrec a;
+        int st;
+        while ((st = sam_next(&s, &a, err)) != 0) {
+            if (st < 0) { rc = 1; break; }
+            if (a.ref == -1) continue;
+            if (a.l_qseq < mn) mn = a.l_qseq;
+            if (a.l_qseq > mx) mx = a.l_qseq;
+            seen = 1;
+            if (pe) break;
+        }
+        sam_close(&s);
+    }
+    if (rc) return rc;
+    if (!seen) return fail(err, "no aligned read in %s: cannot learn the read length", path);
+    *rl_min = mn; *rl_max = mx;
+    return 0;
+}
+
 int emsar_read_alignments(const emsar_rsh *r, const char *path, const emsar_reader_opts *o, int *readlength,
                           emsar_batch_fn fn, void *user, char *err)
 {

@@ -51,6 +51,17 @@ static void name_insert(emsar_rsh *r, int tid)
     }
 }
 
+/* (re)build the tname -> tid map of an index whose names[] are filled in */
+void emsar_rsh_name_index(emsar_rsh *r)
+{
+    free(r->name_slots);
+    uint32_t slots = 16;
+    while (slots < (uint32_t)r->T * 2u) slots <<= 1;
+    r->name_mask = slots - 1;
+    r->name_slots = (uint32_t *)calloc(slots, sizeof(uint32_t));
+    for (int32_t t = 0; t < r->T; t++) name_insert(r, t);
+}
+
 void emsar_rsh_free(emsar_rsh *r)
 {
     if (!r) return;
