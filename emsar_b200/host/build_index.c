@@ -20,6 +20,7 @@
  *    (mate-1 bases, mate-2 bases); unstranded libraries keep the smaller of a fragment and its flip (tie: forward); a run with
  *    one member -> singleton, with several members -> class only if all share d and r < MAX_REPEAT, else dropped. */
 #define _GNU_SOURCE
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -151,14 +152,6 @@ static int txome_read(const char *path, char option, txome *x, char *err)
     return 0;
 }
 
-/* transcript of a forward-half position */
-static int32_t tid_fw(const txome *x, int64_t p)
-{
-    int32_t lo = 0, hi = x->T - 1;
-    while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (x->start[mid] <= p) lo = mid; else hi = mid - 1; }
-    return lo;
-}
-
 /* ---- class store ------------------------------------------------------------------------------------------------------ */
 typedef struct { int32_t k; int64_t tid_off; int64_t euma_row; } bclass;
 typedef struct {
@@ -226,6 +219,36 @@ static void cs_add(cstore *c, const int32_t *t, int k, int fi)
 }
 static void cs_add_single(cstore *c, int32_t tid, int fi) { c->s_node[tid] = 1; c->s_euma[(size_t)tid * c->nF + fi]++; }
 
+/* fold the store of a worker thread into dst (counts add up; the final order does not depend on who found a class first) */
+static void cs_merge(cstore *dst, const cstore *src)
+{
+    for (int32_t t = 0; t < src->T; t++) {
+        if (!src->s_node[t]) continue;
+        dst->s_node[t] = 1;
+        for (int i = 0; i < src->nF; i++) dst->s_euma[(size_t)t * dst->nF + i] += src->s_euma[(size_t)t * src->nF + i];
+    }
+    for (int64_t j = 0; j < src->ncls; j++) {
+        const bclass *b = &src->cls[j];
+        const int32_t *row = src->euma + b->euma_row * src->nF;
+        int first = 1;
+        for (int i = 0; i < src->nF; i++) {
+            if (!row[i]) continue;
+            cs_add(dst, src->tids + b->tid_off, b->k, i);              /* creates the class on its first count */
+            if (row[i] > 1) {
+                /* the class exists now: find it once more and add the rest of the count */
+                uint64_t s = key_hash(src->tids + b->tid_off, b->k) & dst->mask;
+                for (;;) {
+                    const bclass *d = &dst->cls[dst->slots[s] - 1];
+                    if (d->k == b->k && memcmp(dst->tids + d->tid_off, src->tids + b->tid_off, sizeof(int32_t) * (size_t)b->k) == 0) { dst->euma[d->euma_row * dst->nF + i] += row[i] - 1; break; }
+                    s = (s + 1) & dst->mask;
+                }
+            }
+            first = 0;
+        }
+        (void)first;
+    }
+}
+
 /* ---- substrings: rolling hash + exact comparison ---------------------------------------------------------------------- */
 static const uint64_t HB = 0x100000001B3ULL * 31 + 2;      /* odd multiplier of the polynomial hash (mod 2^64) */
 static inline uint64_t code(char ch) { return ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 4 : 0; }
@@ -271,9 +294,9 @@ static void emit_run(cstore *c, const sub *e, int64_t r, int max_repeat, int fi_
     qsort(*tbuf, (size_t)r, sizeof(int32_t), i32_cmp);
     cs_add(c, *tbuf, (int)r, pe ? e[0].d + fi_base : fi_base);
 }
+/* g_S / g_L must be set by the caller (they are the same for every thread of a PE build) */
 static void scan_runs(cstore *c, sub *e, int64_t n, int L, const char *S, int max_repeat, int fi_base, int pe, int32_t **tbuf, int64_t *tcap)
 {
-    g_S = S; g_L = L;
     qsort(e, (size_t)n, sizeof(sub), sub_cmp);
     for (int64_t a = 0; a < n;) {
         int64_t b = a + 1;
@@ -293,6 +316,7 @@ static void build_se(const txome *x, const emsar_build_opts *o, cstore *c)
     int32_t *tbuf = NULL; int64_t tcap = 0;
     for (int L = o->readlen_min; L <= o->readlen_max; L++) {
         hash_all(x, L, H, ok);
+        g_S = x->S; g_L = L;
         int64_t m = 0;
         for (int32_t t = 0; t < x->T; t++) {
             const int64_t s0 = x->start[t], len = x->start[t + 1] - 1 - s0;          /* start[t+1] - 1 is the '@' / '$' */
@@ -319,6 +343,47 @@ static int cmp_pe(const char *a, const char *b, int d, int L)       /* strcmp_pe
     return r ? r : memcmp(a + d, b + d, (size_t)L);
 }
 
+typedef struct { const txome *x; const emsar_build_opts *o; const sub *m1; int64_t a, b; const uint8_t *ok; const uint64_t *H; int fmin, fmax; cstore *c; } pe_job;
+
+/* the clusters inside m1[a..b): every member with every admissible mate 2 (process_mate1_cluster_by_mate_3 :2852-2874) */
+static void *pe_worker(void *arg)
+{
+    pe_job *jb = (pe_job *)arg;
+    const txome *x = jb->x;
+    const emsar_build_opts *o = jb->o;
+    const sub *m1 = jb->m1;
+    const int L = o->readlength, dmin = jb->fmin - L, dmax = jb->fmax - L;
+    sub *e = NULL; int64_t cap = 0;
+    int32_t *tbuf = NULL; int64_t tcap = 0;
+    for (int64_t a = jb->a; a < jb->b;) {
+        int64_t b = a + 1;
+        while (b < jb->b && m1[b].h == m1[a].h && memcmp(x->S + m1[b].pos, x->S + m1[a].pos, (size_t)L) == 0) b++;
+        int64_t m = 0;
+        for (int64_t j = a; j < b; j++) {
+            const int64_t p = m1[j].pos;
+            const int32_t t = m1[j].tid;
+            int64_t lo, hi;                                  /* mate 2 must start in [lo, hi]: the member's transcript, in the half it lies in */
+            if (p < x->border) { lo = x->start[t]; hi = x->start[t + 1] - 1 - L; }
+            else { lo = x->end - (x->start[t + 1] - 1); hi = x->end - x->start[t] - L; }
+            for (int d = dmin; d <= dmax; d++) {
+                const int64_t q = p + d;
+                if (q < lo || q > hi || !jb->ok[q]) continue;
+                if (!o->stranded) {
+                    const int cr = cmp_pe(x->S + p, x->S + (x->end - q - L), d, L);
+                    if (!((p < x->border && cr <= 0) || (p > x->border && cr < 0))) continue;
+                }
+                if (m == cap) { cap = cap ? cap * 2 : 1 << 16; e = (sub *)realloc(e, sizeof(sub) * (size_t)cap); }
+                e[m].h = jb->H[q]; e[m].pos = q; e[m].tid = t; e[m].d = d;
+                m++;
+            }
+        }
+        if (m > 0) scan_runs(jb->c, e, m, L, x->S, o->max_repeat, L - jb->fmin, 1, &tbuf, &tcap);
+        a = b;
+    }
+    free(e); free(tbuf);
+    return NULL;
+}
+
 static void build_pe(const txome *x, const emsar_build_opts *o, cstore *c, int fmin, int fmax)
 {
     const int L = o->readlength;
@@ -343,37 +408,29 @@ static void build_pe(const txome *x, const emsar_build_opts *o, cstore *c, int f
     }
     g_S = x->S; g_L = L;
     qsort(m1, (size_t)nm1, sizeof(sub), sub_cmp);
-    sub *e = NULL; int64_t cap = 0;
-    int32_t *tbuf = NULL; int64_t tcap = 0;
-    const int dmin = fmin - L, dmax = fmax - L;
-    for (int64_t a = 0; a < nm1;) {
-        int64_t b = a + 1;
-        while (b < nm1 && m1[b].h == m1[a].h && memcmp(x->S + m1[b].pos, x->S + m1[a].pos, (size_t)L) == 0) b++;
-        /* the cluster m1[a..b): every member with every admissible mate 2 (process_mate1_cluster_by_mate_3 :2852-2874) */
-        int64_t m = 0;
-        for (int64_t j = a; j < b; j++) {
-            const int64_t p = m1[j].pos;
-            const int32_t t = m1[j].tid;
-            /* the member's transcript as a range of the half it lies in */
-            int64_t lo, hi;                                  /* mate 2 must start in [lo, hi] */
-            if (p < x->border) { lo = x->start[t]; hi = x->start[t + 1] - 1 - L; }
-            else { lo = x->end - (x->start[t + 1] - 1); hi = x->end - x->start[t] - L; }
-            for (int d = dmin; d <= dmax; d++) {
-                const int64_t q = p + d;
-                if (q < lo || q > hi || !ok[q]) continue;
-                if (!o->stranded) {
-                    const int cr = cmp_pe(x->S + p, x->S + (x->end - q - L), d, L);
-                    if (!((p < x->border && cr <= 0) || (p > x->border && cr < 0))) continue;
-                }
-                if (m == cap) { cap = cap ? cap * 2 : 1 << 16; e = (sub *)realloc(e, sizeof(sub) * (size_t)cap); }
-                e[m].h = H[q]; e[m].pos = q; e[m].tid = t; e[m].d = d;
-                m++;
-            }
-        }
-        if (m > 0) scan_runs(c, e, m, L, x->S, o->max_repeat, L - fmin, 1, &tbuf, &tcap);
-        a = b;
+    /* clusters of equal mate 1 are independent: cut the sorted list at cluster boundaries into one piece per thread */
+    int nthr = o->threads > 1 ? (o->threads > 64 ? 64 : o->threads) : 1;
+    if (nm1 < 2000) nthr = 1;
+    pe_job jobs[64];
+    pthread_t th[64];
+    int64_t cut = 0;
+    for (int w = 0; w < nthr; w++) {
+        int64_t nxt = w == nthr - 1 ? nm1 : nm1 * (w + 1) / nthr;
+        while (nxt > cut && nxt < nm1 && m1[nxt].h == m1[nxt - 1].h && memcmp(x->S + m1[nxt].pos, x->S + m1[nxt - 1].pos, (size_t)L) == 0) nxt++;
+        jobs[w].x = x; jobs[w].o = o; jobs[w].m1 = m1; jobs[w].a = cut; jobs[w].b = nxt; jobs[w].ok = ok; jobs[w].H = H; jobs[w].fmin = fmin; jobs[w].fmax = fmax;
+        jobs[w].c = w == 0 ? c : (cstore *)malloc(sizeof(cstore));
+        if (w > 0) cs_init(jobs[w].c, c->T, c->nF);
+        cut = nxt;
     }
-    free(H); free(ok); free(m1); free(e); free(tbuf);
+    for (int w = 1; w < nthr; w++) pthread_create(&th[w], NULL, pe_worker, &jobs[w]);
+    pe_worker(&jobs[0]);
+    for (int w = 1; w < nthr; w++) {
+        pthread_join(th[w], NULL);
+        cs_merge(c, jobs[w].c);
+        cs_free(jobs[w].c);
+        free(jobs[w].c);
+    }
+    free(H); free(ok); free(m1);
 }
 
 /* ---- class store -> emsar_rsh in the reference's scan / print order ------------------------------------------------------ */

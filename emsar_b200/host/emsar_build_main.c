@@ -15,7 +15,7 @@ static void usage(const char *p)
            "  readlength   a number (PE), or a number / range such as 48-52 (SE)\n"
            "  -P  paired-end        -s ns|ssf|ssr|ssfr|ssrf        -F / -f  max / min fragment length (PE; default 400 / 1)\n"
            "  -k  MAX_REPEAT (default 100)        -h E|R  fasta header: Ensembl (default) or RefSeq        -q / -v\n"
-           "  -p -b -t are accepted for compatibility (threads, bin size, tag length of the reference's suffix arrays)\n", p);
+           "  -p  threads (paired-end construction)        -b -t are accepted for compatibility (bin size, tag length of the reference's suffix arrays)\n", p);
 }
 
 int main(int argc, char *argv[])
@@ -40,7 +40,8 @@ int main(int argc, char *argv[])
         case 'h': o.header = optarg[0]; if (o.header != 'E' && o.header != 'R') { fprintf(stderr, "error: invalid fasta option.\n"); return 0; } break;
         case 'm': if (optarg[0] != '0') { fprintf(stderr, "error: the positional bias model (-m 1) is not supported.\n"); return 1; } break;
         case 'T': fprintf(stderr, "error: -T (print suffix array) is not supported: this builder has no suffix array.\n"); return 1;
-        case 'p': case 'b': case 't': case 'W': case 'w': break;
+        case 'p': o.threads = atoi(optarg); break;
+        case 'b': case 't': case 'W': case 'w': break;
         case 'v': verbose = 2; break;
         case 'q': verbose = 0; break;
         default: return 0;

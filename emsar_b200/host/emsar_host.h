@@ -53,6 +53,7 @@ typedef struct {
     int min_fraglength, max_fraglength; /* PE: -f / -F (reference defaults 1 / 400) */
     int max_repeat;                /* -k MAX_REPEAT: substrings occurring this often or more are dropped (default 100) */
     char header;                   /* 'E' Ensembl header (name up to the first blank, default), 'R' RefSeq (4th '|' field) */
+    int threads;                   /* worker threads of the paired-end construction (-p); results do not depend on it */
 } emsar_build_opts;
 int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh **out, char *err);
 /* read length(s) of an alignment file, as emsar -x learns them (emsar_main.c:306-316): PE -> the first aligned record,

@@ -325,7 +325,7 @@ int main(int argc, char *argv[])
         emsar_build_opts bo;
         memset(&bo, 0, sizeof bo);
         bo.pe = o.pe; bo.stranded = o.strand != 0; bo.max_repeat = o.max_repeat; bo.header = o.fasta_header ? o.fasta_header : 'E';
-        bo.min_fraglength = o.min_fl; bo.max_fraglength = o.max_fl;
+        bo.min_fraglength = o.min_fl; bo.max_fraglength = o.max_fl; bo.threads = o.nthread > 0 ? o.nthread : 4;
         int rl0 = 0, rl1 = 0;
         if (emsar_sniff_readlengths(o.aln[0], o.bamflag, o.pe, &rl0, &rl1, err)) die("%s", err);
         if (o.pe) bo.readlength = rl0; else { bo.readlen_min = rl0; bo.readlen_max = rl1; }
