@@ -127,3 +127,35 @@ def test_cli_class_sharded_two_gpus(built, tmp_path):
     for col in (1, 4, 6):           # FPKM, iReadcount, TPM: same optimum, sums in a different order
         x, y = np.array([float(r[col]) for r in fa]), np.array([float(r[col]) for r in fb])
         assert np.allclose(x, y, rtol=1e-6, atol=2e-6), col
+
+
+@pytest.mark.gpu
+def test_cli_multisample_over_two_gpus(built, tmp_path):
+    """`EMSAR_DEVICES=0,1 emsar -M ...`: the files of the list are spread over the GPUs (one host thread each, no communication)
+    and every output file is the one the single-GPU run writes, byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as gu
+    fx = gu.FIXTURES["se"]
+    rsh, aln = gu.materialize(fx["rsh"], tmp_path), gu.materialize(fx["aln"], tmp_path)
+    lines = open(aln).read().splitlines(True)
+    files = [aln]
+    for i, frac in enumerate((2, 3, 4)):
+        p = os.path.join(str(tmp_path), f"part{i}.bowtie")
+        open(p, "w").writelines(lines[:len(lines) // frac])
+        files.append(p)
+    lst = os.path.join(str(tmp_path), "list.txt")
+    open(lst, "w").write("\n".join(files) + "\n")
+    emsar = os.path.join(ROOT, "emsar_b200", "bin", "emsar")
+    outs = []
+    for tag, env_extra in (("one", {}), ("two", {"EMSAR_DEVICES": "0,1"})):
+        out = os.path.join(str(tmp_path), tag)
+        r = subprocess.run([emsar, "-q", "-g", "-M", "-I", rsh, out, "p", lst], capture_output=True, text=True, env=dict(os.environ, **env_extra), timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(out)
+    for i in range(len(files)):
+        for ext in ("fpkm", "fraglength_effect", "segments"):
+            a, b = (open(os.path.join(o, f"p.{i}.{ext}")).read() for o in outs)
+            assert a == b, (i, ext)
