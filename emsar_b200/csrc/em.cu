@@ -131,20 +131,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *g, uint32_t byte
                  "r"(smem_u32(bar))
                  : "memory");
 }
-// one chunk copy split into EM_WARPS pieces, each issued by lane 0 of a different warp (TMA issue is slow per thread)
-__device__ __forceinline__ void bulk_g2s_split(void *dst, const void *g, uint32_t bytes, unsigned long long *bar, int warp, int lane)
-{
-    (void)warp;
-    if (lane >= 1) return;                        // one bulk copy per stream piece: issuing costs ~55 ns each, so do not split
-    const uint32_t piece = bytes;
-    const uint32_t o = 0;
-    if (o >= bytes) return;
-    const uint32_t n = min(piece, bytes - o);
-    const uintptr_t ga = ((uintptr_t)g & ~(uintptr_t)15) + o;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst) + o), "l"(ga), "r"(n),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
     asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra LAB_DONE;\nbra LAB_WAIT;\nLAB_DONE:\n}" ::"r"(smem_u32(bar)),
@@ -569,8 +555,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&sm_full[sg], stage_bytes(gi, n_idx) + stage_bytes(gr, j1 - j0));
             __syncwarp();
-            bulk_g2s_split(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, n_idx), &sm_full[sg], warp, lane);
-            bulk_g2s_split((int *)(sm_dyn + sg * CH_BYTES) + ro, gr, stage_bytes(gr, j1 - j0), &sm_full[sg], warp, lane);
+            if (lane == 0) bulk_g2s(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, n_idx), &sm_full[sg]);     // one bulk copy per stream piece: issuing costs ~55 ns each
+            if (lane == 0) bulk_g2s((int *)(sm_dyn + sg * CH_BYTES) + ro, gr, stage_bytes(gr, j1 - j0), &sm_full[sg]);
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm_full[sg]);       // oversized item: read straight from global
@@ -586,7 +572,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             const int32_t *gi = p.m.m_cls + (uint32_t)c.z;
             if (lane == 0) mbar_expect_tx(&sm_full[sg], stage_bytes(gi, c.w));
             __syncwarp();
-            bulk_g2s_split(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, c.w), &sm_full[sg], warp, lane);
+            if (lane == 0) bulk_g2s(sm_dyn + sg * CH_BYTES, gi, stage_bytes(gi, c.w), &sm_full[sg]);
         } else if (lane == 0) mbar_arrive(&sm_full[sg]);
     };
 
@@ -906,7 +892,6 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 const int n_idx = c.w - (s_et[c.y - 1].x + s_et[c.y - 1].y - jbase);
                 const int ro = (sh + n_idx + 3) & ~3, sr = stage_shift(p.m.e_R + jbase);
                 // tiles are ordered by cardinality: take them from the heaviest end
-                if (p.eps_abs < 0) { /* tuning aid: stream only */ } else
                 if (staged && all_local) {
                     const int tbase = sg * (CH_BYTES / 4) + sh - c.z, rbase = sg * (CH_BYTES / 4) + ro + sr - jbase;
                     for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
@@ -945,7 +930,6 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 const bool staged = c.w >= 0;
                 const int sh = stage_shift(p.m.m_cls + (uint32_t)c.z);
                 // items are ordered longest first
-                if (p.eps_abs < 0) { /* tuning aid: stream only */ } else
                 if (staged && all_local) {
                     const int ebase = sg * (CH_BYTES / 4) + sh - c.z;
                     for (int tk = next_item(&sm_ctr[sg], lane); tk < n_items; tk = next_item(&sm_ctr[sg], lane)) {
@@ -1021,7 +1005,7 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     cudaStream_t st = ctx->stream;
     EmParams p;
     p.m = s->m;
-    p.eps_abs = getenv("EMSAR_DEBUG_STREAM_ONLY") ? -1.0 : s->opts.eps_abs; p.eps_rel = s->opts.eps_rel;
+    p.eps_abs = s->opts.eps_abs; p.eps_rel = s->opts.eps_rel;
     p.max_iter = max_iter; p.stop_on_conv = stop_on_conv;
     p.bar = ctx->d_barrier + 64;                                   // one 128-byte line per CTA
     p.dmax = (unsigned long long *)(ctx->d_barrier + 4);
