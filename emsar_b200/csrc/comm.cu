@@ -152,7 +152,7 @@ int comm_window_ensure(emsar_ctx *ctx, int64_t rows)
     CU(cudaStreamSynchronize(st));
     comm_window_release(ctx);
     const int64_t cap = rows + (rows >> 3) + 1024;
-    const size_t bytes = WIN_HDR_BYTES + 16 * (size_t)cap + 16 * (size_t)(win_slice_rows(cap, R) * R + 64);
+    const size_t bytes = WIN_HDR_BYTES + 32 * (size_t)cap + 16 * (size_t)(win_slice_rows(cap, R) * R + 64);       // dm | 2 x theta | xbuf
     ctx->win_bytes = bytes;
     WinInfo mine;
     memset(&mine, 0, sizeof(mine));

@@ -87,7 +87,7 @@ struct emsar_ctx {
     size_t win_bytes;
     int win_state;             // 0 = not tried, 1 = usable, -1 = peer memory unavailable (NCCL path only)
 };
-// Window layout (bytes): [dm: 2 parities x nranks x WIN_MAX_CTAS slots][theta: win_rows slots][xbuf: nranks x S slots].
+// Window layout (bytes): [dm: 2 parities x nranks x WIN_MAX_CTAS slots][theta: 2 parities x win_rows slots][xbuf: nranks x S slots].
 // A slot is 16 bytes: two 64-bit words {low half of the double | tag << 32}, {high half | tag << 32}. Each word is written
 // with one 8-byte store, so a reader that polls until both tags match has the value - no fence, no separate flag.
 constexpr int WIN_MAX_CTAS = 256;

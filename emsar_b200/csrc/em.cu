@@ -37,6 +37,7 @@ struct EmParams {
         int fused;                 // 1: all-reduce inside the kernel over peer memory; 0: one pass, sums to q_out (NCCL path)
         unsigned char *win[EMSAR_MAX_RANKS];   // every rank's window (comm.cu): dm | theta | xbuf, 16-byte tagged slots
         long long theta_off, xbuf_off;         // byte offsets inside a window
+        long long theta_cap;                   // slots per theta parity array
         unsigned tag0;             // tags of this launch start above tag0 (windows are zeroed before every launch)
         int *abort_flag;           // set when a wait ran out of patience (a peer died): every wait then falls through
         double *q_out;             // NCCL path: [P] partial row sums in natural order
@@ -722,8 +723,13 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         // rank's E -> M grid barrier, which every reader of theta(i) has passed. The dm slots alternate by parity.
         const EmParams::Shard &sh = p.sh;
         const int R = sh.nranks, S = sh.S, me = sh.rank;
-        const unsigned char *my_theta = sh.win[me] + sh.theta_off;
         const unsigned char *my_xbuf = sh.win[me] + sh.xbuf_off;
+        // theta lives in two slot arrays used in turn (iteration parity): without the E -> M grid barrier (df below) a reader of
+        // theta(i) may still be at it while the owner already publishes theta(i+1)
+        auto theta_slot = [&](int r, int iter, int n) -> unsigned char * { return sh.win[r] + sh.theta_off + 16 * ((size_t)(iter & 1) * sh.theta_cap + (size_t)n); };
+        // df: no grid barrier between the phases either - q of the classes other CTAs read goes through local tagged slots as in
+        // k_em_persistent<3> (needs every halo row / class of every CTA of this rank in shared memory)
+        const bool df = sh.fused && p.m.all_local && p.q_slots != nullptr;
         const int n0 = v.row0;                                                   // the CTA's rows are a contiguous natural range
         int *s_noff = (int *)(s_rsa + 0) + 2 * v.nrows;                          // second half of the {Rs,A} area
         double *s_stage = (double *)s_rsa;
@@ -759,10 +765,11 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         bool stopped = false;
         while (it < p.max_iter) {
             const unsigned tag = sh.tag0 + (unsigned)it + 1u;             // theta(it) and partials / dm of iteration it carry it
+            f.tag = p.df_tag0 + (unsigned)it + 1u;                        // tag of the local q slots (df)
             TRACE(0);
             if (sh.fused) {
-                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = ll_load(my_theta + 16 * (size_t)(n0 + s_noff[i]), tag, sh.abort_flag);
-                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = ll_load(my_theta + 16 * (size_t)s_hrl[i], tag, sh.abort_flag);
+                for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) v.sm_theta[i] = ll_load(theta_slot(me, it, n0 + s_noff[i]), tag, sh.abort_flag);
+                for (int i = threadIdx.x; i < v.nhr; i += EM_BLOCK) v.sm_theta[v.nrows + i] = ll_load(theta_slot(me, it, s_hrl[i]), tag, sh.abort_flag);
                 if (!p.m.all_local)    // overflow path (some CTA): halo rows without a slot are read from the permuted global copy during the E-phase
                     for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = v.sm_theta[i];
             } else {
@@ -771,7 +778,17 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
             if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
             if (sh.fused && !p.m.all_local) grid_barrier(p.bar, gridDim.x, 2 * it + 1);  // the global copy is complete before anybody gathers from it
             else __syncthreads();
-            if (all_local) {
+            if (df) {
+                for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                    const int ti = n_et - 1 - tk;
+                    const int4 tile = s_et[ti];
+                    const int ro = s_eres[ti];
+                    if (ro >= 0) {
+                        const int cpb = 32 >> ((tile.w >> 12) & 0xf), ints = ((tile.y + cpb - 1) / cpb) * 32 * (tile.w & 0xfff);
+                        f_e_tile<1>(p, f, tile, IdxS{sm_dyn}, IdxS{sm_dyn}, res4 + ro, res4 + ro + ints, lane);
+                    } else f_e_tile<1>(p, f, tile, IdxG{p.m.e_tid}, IdxG{(const int32_t *)p.m.e_R}, tile.z, tile.x, lane);
+                }
+            } else if (all_local) {
                 for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
                     const int ti = n_et - 1 - tk;
                     const int4 tile = s_et[ti];
@@ -802,9 +819,13 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 }
                 if (p.stop_on_conv && d <= 1.0) { stopped = true; break; }
             }
-            grid_barrier(p.bar, gridDim.x, 2 * it + 2);
+            if (df) {
+                for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = ll_load(p.q_slots + 16 * (size_t)s_hcl[i], f.tag, sh.abort_flag);
+            } else {
+                grid_barrier(p.bar, gridDim.x, 2 * it + 2);
+                for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
+            }
             TRACE(2);
-            for (int i = threadIdx.x; i < v.nhc; i += EM_BLOCK) v.sm_q[v.nres + 1 + i] = __ldcg(p.m.q + s_hcl[i]);
             __syncthreads();
             if (all_local) {
                 for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
@@ -838,11 +859,11 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
                 double Q = 0;
                 for (int r = 0; r < R; r++) Q += ll_load(my_xbuf + 16 * ((size_t)r * S + (n - own0)), tag, sh.abort_flag);   // rank order: deterministic
                 const double2 ra = p.m.rsa_nat[n];
-                const double th = ll_load(my_theta + 16 * (size_t)n, tag, sh.abort_flag);
+                const double th = ll_load(theta_slot(me, it, n), tag, sh.abort_flag);
                 const double nn = ra.x + th * Q;
                 const double thn = fast_div(nn, ra.y);
                 dm = fmax(dm, fast_div(fabs(thn - th) * ra.y, p.eps_abs + p.eps_rel * nn));
-                for (int r = 0; r < R; r++) ll_store(sh.win[r] + sh.theta_off + 16 * (size_t)n, thn, tag + 1);
+                for (int r = 0; r < R; r++) ll_store(theta_slot(r, it + 1, n), thn, tag + 1);
             }
             TRACE(4);
 #pragma unroll
@@ -861,7 +882,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_persistent(EmParams p)
         if (sh.fused && *((volatile int *)sh.abort_flag) != 0) d = INFINITY;
         if (sh.fused) {      // the permuted copy the output kernels read
             const unsigned tag = sh.tag0 + (unsigned)it + 1u;
-            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = ll_load(my_theta + 16 * (size_t)(n0 + s_noff[i]), tag, sh.abort_flag);
+            for (int i = threadIdx.x; i < v.nrows; i += EM_BLOCK) p.m.theta[v.row0 + i] = ll_load(theta_slot(me, it, n0 + s_noff[i]), tag, sh.abort_flag);
         }
     }
     while (it < p.max_iter && MODE == 0) {
@@ -1025,7 +1046,8 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
             if (s->m.B > WIN_MAX_CTAS) { emsar_set_err("sharded EM: more than %d CTAs", WIN_MAX_CTAS); return EMSAR_ERR_UNSUPPORTED; }
             for (int r = 0; r < ctx->nranks; r++) p.sh.win[r] = (unsigned char *)ctx->peer_win[r];
             p.sh.theta_off = (long long)WIN_HDR_BYTES;
-            p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 16 * (size_t)ctx->win_rows);
+            p.sh.theta_cap = (long long)ctx->win_rows;
+            p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 32 * (size_t)ctx->win_rows);
         }
     }
     CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)s->m.B * 128, st));
@@ -1033,6 +1055,13 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
     const char *em_mode = getenv("EMSAR_EM_MODE");
     const bool dataflow = !s->sharded && s->m.direct && s->m.all_local && s->d_slots && !(em_mode && !strcmp(em_mode, "barrier"));
     p.th_slots = p.q_slots = p.dm_slots = nullptr; p.df_tag0 = 0; p.df_abort = (int *)(ctx->d_barrier + 14);
+    if (s->sharded && fused && s->m.all_local && s->d_slots && !(em_mode && !strcmp(em_mode, "barrier"))) {
+        // the sharded kernel's local q exchange: same tagged slots, a fresh tag range per launch
+        p.q_slots = (unsigned char *)s->d_slots + 16 * (size_t)(s->m.P + 1);
+        if ((unsigned)(s->slot_tag + (unsigned)max_iter + 4u) < s->slot_tag) { CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st)); s->slot_tag = 0; }
+        p.df_tag0 = s->slot_tag;
+        s->slot_tag += (unsigned)max_iter + 2u;
+    }
     if (dataflow) {
         p.th_slots = (unsigned char *)s->d_slots;
         p.q_slots = p.th_slots + 16 * (size_t)(s->m.P + 1);
