@@ -1,15 +1,18 @@
 // The EM loop: one persistent cooperative kernel, one CTA per SM. Each CTA owns a contiguous range of transcripts
 // (rows) and the classes whose first member lies in it, and keeps theta / q of what it owns in SHARED MEMORY: the
 // gathers of both phases hit 32 independent banks instead of one L1 line per wavefront; only references that leave
-// the range (halo) go through the L2-resident global copies. Per iteration:
+// the range (halo) go through L2-resident global memory. Per iteration:
 //   E-phase  q_c = R_c / sum_{t in c} theta_t        class-major, binned by cardinality
-//   -- grid barrier --
 //   M-phase  theta_t' = (Rs_t + theta_t * sum_{c∋t} q_c) / A_t   transposed CSR, deterministic segmented reduction,
 //            fused with the convergence measure  max_t |dtheta_t| A_t / (eps_abs + eps_rel n_t)
-//   -- grid barrier --  (every CTA reads the reduced delta and decides to stop: no host round trip)
-// until convergence or max_iter.  It replaces run_MLE_threads / MLE_range / MLE / Fp / lambdap of the reference
-// (emsar_functions.c:2946-3126), which reach the same Poisson-likelihood optimum by a randomized pattern search.
+// until convergence or max_iter, with no host round trip.  It replaces run_MLE_threads / MLE_range / MLE / Fp / lambdap of the
+// reference (emsar_functions.c:2946-3126), which reach the same Poisson-likelihood optimum by a randomized pattern search.
 // No floating-point atomics anywhere: every sum has an order fixed by the packed layout alone.
+// Instantiations (k_em_persistent<MODE>):
+//   3  default: no grid barrier; halo theta / q and the convergence measure travel through tagged 16-byte slots (ll_store / ll_load)
+//   1  two grid barriers per iteration (overflow: some halo row / class has no shared-memory slot; EMSAR_EM_MODE=barrier)
+//   0  as 1 with TMA-pipelined index streams instead of the resident index cache (EMSAR_EM_MODE=pipe)
+//   2  one sample class-sharded over several GPUs: the per-iteration all-reduce runs inside the kernel over NVLink peer memory
 #include <cooperative_groups.h>
 #include <math.h>
 
