@@ -147,3 +147,38 @@ def test_emsar_dash_x_builds_the_same_index(built, tmp_path, pe):
     tool = REF if os.path.exists(REF) else MINE
     assert subprocess.run([tool] + bflags + [fa, str(L), bdir, "x"], capture_output=True).returncode == 0
     assert mine == open(os.path.join(bdir, "x.rsh"), "rb").read()
+
+
+def test_emsar_dash_x_se_read_length_range_from_bowtie(built, tmp_path):
+    """SE: -x scans the whole alignment file for the shortest and the longest read (read_bowtie_get_readlengths_se :260-288)
+    and builds one EUMA column per length."""
+    emsar = os.path.join(ROOT, "emsar_b200", "bin", "emsar")
+    fa = str(tmp_path / "t.fa")
+    tx = make_fasta(fa)
+    rng = np.random.default_rng(4)
+    with open(tmp_path / "in.bowtie", "w") as f:
+        for r in range(150):
+            t = int(rng.integers(0, len(tx)))
+            L = int(rng.integers(24, 28)) if r not in (0, 1) else (24, 27)[r]      # both ends of the range are present
+            if len(tx[t]) < 40:
+                continue
+            f.write(f"r{r}\t+\tTX{t:03d}\t{int(rng.integers(0, len(tx[t]) - 30))}\t{'A' * L}\t{'I' * L}\t0\t\n")
+    out = str(tmp_path / "out")
+    subprocess.run([emsar, "-q", "-R", "-x", fa, out, "p", str(tmp_path / "in.bowtie")], capture_output=True, text=True)
+    mine = open(os.path.join(out, "p.rsh"), "rb").read()
+    assert mine.startswith(b"#") and b",24,27,-1\n" in mine.split(b"\n")[0] + b"\n"
+    bdir = str(tmp_path / "b")
+    tool = REF if os.path.exists(REF) else MINE
+    assert subprocess.run([tool, "-q", fa, "24-27", bdir, "x"], capture_output=True).returncode == 0
+    assert mine == open(os.path.join(bdir, "x.rsh"), "rb").read()
+
+
+def test_fasta_errors(built, tmp_path):
+    bad = tmp_path / "bad.fa"
+    bad.write_text("ACGT\n>t\nACGT\n")                       # does not start with '>'
+    r = subprocess.run([MINE, "-q", str(bad), "25", str(tmp_path / "o"), "x"], capture_output=True, text=True)
+    assert r.returncode != 0 and "wrong fasta file format" in r.stderr
+    r = subprocess.run([MINE, "-q", str(tmp_path / "none.fa"), "25", str(tmp_path / "o"), "x"], capture_output=True, text=True)
+    assert r.returncode != 0 and "can't open fasta file" in r.stderr
+    r = subprocess.run([MINE, "-q", "-s", "ssfr", str(bad), "25", str(tmp_path / "o"), "x"], capture_output=True, text=True)
+    assert r.returncode != 0 and "invalid strand type" in r.stderr      # a PE strand type without -P
