@@ -204,14 +204,30 @@ __global__ void k_nat_fill(int32_t T, const uint32_t *__restrict__ rflag, const 
     else pos[t] = -1;
 }
 
-// E-phase cost lands on the row that owns the class (its first member)
-__global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
+// The member of a class whose row (and so whose CTA) owns it. rule 0: the first member (classes of a CTA are then contiguous in
+// cid order). rule 1 (EMSAR_OWNER=light): the member with the fewest active entries, first one on ties - the classes of a hub
+// transcript then spread over its partners' CTAs instead of piling their E-phase work onto the hub's CTA.
+__global__ void k_class_owner(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
+                              const int32_t *__restrict__ act, const int32_t *__restrict__ deg, int rule, int32_t *__restrict__ owner)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_multi || !act[i]) return;
+    const uint32_t o = cls_off[T + i], e = cls_off[T + i + 1];
+    int best = cls_tid[o];
+    if (rule == 1) {
+        int bd = deg[best];
+        for (uint32_t j = o + 1; j < e; j++) { const int u = cls_tid[j], d = deg[u]; if (d < bd) { bd = d; best = u; } }
+    }
+    owner[i] = best;
+}
+
+// E-phase cost lands on the row that owns the class
+__global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ owner,
                              const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost, int per_class)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_multi || !act[i]) return;
-    const uint32_t o = cls_off[T + i];
-    atomicAdd(&ecost[nat[cls_tid[o]]], (int)(cls_off[T + i + 1] - o) + per_class);       // gathers + the class's own work (divide, store)
+    atomicAdd(&ecost[nat[owner[i]]], (int)(cls_off[T + i + 1] - cls_off[T + i]) + per_class);       // gathers + the class's own work (divide, store)
 }
 
 __global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost, int per_row)
@@ -360,31 +376,29 @@ __global__ void k_item_finish(int n_items, int B, const int32_t *__restrict__ it
     }
 }
 
-// cell = (owner CTA, cardinality segment). Classes of one cell are contiguous in cid order (first tids ascend inside a
-// cardinality segment and CTA ranges are natural-order ranges), so a class's rank inside its cell is
-// (old compact id - smallest old compact id of the cell).
+// cell = (owner CTA, cardinality segment). The new compact id of a class is its rank in the order (cell, old compact id): the
+// classes of a cell stay in cid order whatever the ownership rule is, so the layout is a function of the model alone.
 __global__ void k_class_cells(int64_t n_multi, int32_t T, int n_kseg, int B, const int64_t *__restrict__ kseg_cid0,
-                              const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
+                              const int32_t *__restrict__ owner, const int32_t *__restrict__ act,
                               const int32_t *__restrict__ newid, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
-                              int32_t *__restrict__ cellof, int32_t *__restrict__ cell_cnt, int32_t *__restrict__ cell_first)
+                              int32_t *__restrict__ cellof, int32_t *__restrict__ cell_cnt, unsigned long long *__restrict__ keys, int32_t *__restrict__ vals)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_multi || !act[i]) return;
-    const int ob = block_of_row(row0, B, pos[cls_tid[cls_off[T + i]]]);
+    const int ob = block_of_row(row0, B, pos[owner[i]]);
     const int cell = ob * n_kseg + seg_of_cid(kseg_cid0, n_kseg, T + i);
     const int j = newid[i];
     cellof[j] = cell;
     atomicAdd(&cell_cnt[cell], 1);
-    atomicMin(&cell_first[cell], j);
+    keys[j] = ((unsigned long long)(uint32_t)cell << 32) | (unsigned long long)(uint32_t)j;
+    vals[j] = (int32_t)i;
 }
 
-__global__ void k_class_newid(int64_t n_multi, const int32_t *__restrict__ act, const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof,
-                              const int32_t *__restrict__ cell_first, const int32_t *__restrict__ clsbase, int32_t *__restrict__ newid2)
+// after sorting (cell, old id): the class at sorted position r gets the new compact id r
+__global__ void k_class_newid(int64_t C_a, const int32_t *__restrict__ sorted_vals, int32_t *__restrict__ newid2)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_multi || !act[i]) return;
-    const int jo = newid[i], cell = cellof[jo];
-    newid2[i] = clsbase[cell] + jo - cell_first[cell];
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < C_a) newid2[sorted_vals[r]] = (int32_t)r;
 }
 
 __global__ void k_cell_sizes(int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ cell_cnt,
@@ -411,14 +425,14 @@ __global__ void k_block_tables(int B, int n_kseg, const int32_t *__restrict__ cl
 // every reference that leaves the owner's range is appended as (CTA << 32 | global index); sorting + unique gives each
 // CTA its list of distinct remote rows (E side) / classes (M side), in a deterministic order
 __global__ void k_halo_collect_e(int64_t n_multi, int32_t T, int B, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid,
-                                 const int32_t *__restrict__ act, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
+                                 const int32_t *__restrict__ owner, const int32_t *__restrict__ act, const int32_t *__restrict__ pos, const int32_t *__restrict__ row0,
                                  unsigned long long *__restrict__ keys, unsigned int *__restrict__ count)
 {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_multi || !act[i]) return;
     const uint32_t o = cls_off[T + i], e = cls_off[T + i + 1];
-    const int ob = block_of_row(row0, B, pos[cls_tid[o]]);
+    const int ob = block_of_row(row0, B, pos[owner[i]]);
     const int r0 = row0[ob], r1 = row0[ob + 1];
     for (uint32_t j = o + lane; j < e; j += 32) {
         const int p = pos[cls_tid[j]];
@@ -472,7 +486,7 @@ __device__ __forceinline__ int halo_find(const unsigned long long *uniq, int h0,
 __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int32_t *__restrict__ blk_nres, const int32_t *__restrict__ blk_hr0,
                                const int32_t *__restrict__ blk_nhr, const unsigned long long *__restrict__ uniq_e, const int32_t *__restrict__ kseg_k,
                                const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const int32_t *__restrict__ act,
-                               const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof, const int32_t *__restrict__ cell_first,
+                               const int32_t *__restrict__ newid, const int32_t *__restrict__ cellof, const int32_t *__restrict__ newid2,
                                const int32_t *__restrict__ clsbase, const uint32_t *__restrict__ intbase, const int32_t *__restrict__ R,
                                const int32_t *__restrict__ pos, const int32_t *__restrict__ row0, const int32_t *__restrict__ cls0,
                                int32_t *__restrict__ e_tid, uint32_t *__restrict__ e_R)
@@ -483,8 +497,8 @@ __global__ void k_pack_classes(int64_t n_multi, int32_t T, int n_kseg, const int
     const int jo = newid[i];
     const int cell = cellof[jo];
     const int ob = cell / n_kseg, k = kseg_k[cell % n_kseg];
-    const int jl = jo - cell_first[cell];
-    const int jn = clsbase[cell] + jl;
+    const int jn = newid2[i];
+    const int jl = jn - clsbase[cell];
     const int r0 = row0[ob], r1 = row0[ob + 1];
     const int nres = blk_nres[ob];
     const uint32_t o = cls_off[T + i];
@@ -723,11 +737,12 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t *)nullptr, (int32_t *)nullptr, scan_max);
     cub::DeviceRadixSort::SortPairs(nullptr, b4, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, T + 1, 0, 44);
     const size_t href_max = (size_t)ix->nnz_multi + 1;          // remote references of one side: at most every member entry
-    size_t b5 = 0, b6 = 0;
+    size_t b5 = 0, b6 = 0, b7 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b7, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)(nm + 1), 0, 64);
     cub::DeviceRadixSort::SortKeys(nullptr, b5, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)href_max, 0, 44);
     cub::DeviceSelect::Unique(nullptr, b6, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (unsigned int *)nullptr, (int)href_max);
-    cub_bytes = std::max(std::max(std::max(b1, b2), std::max(b3, b4)), std::max(b5, b6));
-    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 16 + (size_t)(T + 1) * 72 + (size_t)(2 * (size_t)T + B + 64) * 8 + (size_t)(B + 1) * 16 + (size_t)(n_cells + 1) * 28 + 4 * href_max * 8 + 64 * 256;
+    cub_bytes = std::max(std::max(std::max(b1, b2), std::max(b3, b4)), std::max(std::max(b5, b6), b7));
+    size_t need = ((cub_bytes + 255) / 256) * 256 + (size_t)(nm + 1) * 20 + (size_t)(T + 1) * 72 + (size_t)(2 * (size_t)T + B + 64) * 8 + (size_t)(B + 1) * 16 + (size_t)(n_cells + 1) * 28 + 4 * href_max * 8 + 64 * 256;
     void *scr = nullptr;
     TRY(ctx_scratch(ctx, need, &scr));
     char *cur = (char *)scr;
@@ -736,6 +751,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     int32_t *d_newid = arena_take<int32_t>(cur, (size_t)nm + 1);
     int32_t *d_newid2 = arena_take<int32_t>(cur, (size_t)nm + 1);
     int32_t *d_cellof = arena_take<int32_t>(cur, (size_t)nm + 1);
+    int32_t *d_owner = arena_take<int32_t>(cur, (size_t)nm + 1);
     uint32_t *d_rflag = arena_take<uint32_t>(cur, (size_t)T + 1);
     uint32_t *d_nat = arena_take<uint32_t>(cur, (size_t)T + 1);
     int32_t *d_deg = arena_take<int32_t>(cur, (size_t)T + 1);
@@ -864,11 +880,13 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     // in units of one gather (tuning knobs: EMSAR_COST_ROW / EMSAR_COST_CLASS)
     const int cost_row = getenv("EMSAR_COST_ROW") ? atoi(getenv("EMSAR_COST_ROW")) : 2;
     const int cost_class = getenv("EMSAR_COST_CLASS") ? atoi(getenv("EMSAR_COST_CLASS")) : 0;
+    const int owner_rule = (getenv("EMSAR_OWNER") && !strcmp(getenv("EMSAR_OWNER"), "light")) ? 1 : 0;
     k_nat_fill<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, d_rflag, d_nat, d_deg, d_pos, d_degn, d_tn, d_ecost, P);
     LAUNCHED(ctx);
     if (nm > 0) {
-        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_nat, d_ecost, cost_class);
-        LAUNCHED(ctx);
+        k_class_owner<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_deg, owner_rule, d_owner);
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_owner, d_act, d_nat, d_ecost, cost_class);
+        ctx->launches += 2;
     }
     k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost, cost_row);
     LAUNCHED(ctx);
@@ -892,8 +910,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     k_fill_int<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, st>>>(d_cell_first, n_cells + 1, 0x7fffffff);
     LAUNCHED(ctx);
     if (nm > 0 && n_kseg > 0) {
-        k_class_cells<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, B, ix->d_kseg_cid0, ix->d_cls_off, ix->d_cls_tid, d_act, d_newid,
-                                                                   d_pos, m.blk_row0, d_cellof, d_cell_cnt, d_cell_first);
+        k_class_cells<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, B, ix->d_kseg_cid0, d_owner, d_act, d_newid,
+                                                                   d_pos, m.blk_row0, d_cellof, d_cell_cnt, d_hkeys, (int32_t *)d_uniq_e);
         LAUNCHED(ctx);
     }
     k_cell_sizes<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, st>>>(n_cells, n_kseg > 0 ? n_kseg : 1, ix->d_kseg_k, d_cell_cnt, d_cell_ints, d_cell_tiles);
@@ -914,9 +932,13 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     unsigned int h_cnt[4] = {0, 0, 0, 0};    // collected e, unique e, collected m, unique m
     CU(cudaMemsetAsync(d_hcount, 0, 32, st));
     if (nm > 0 && n_kseg > 0) {
-        k_class_newid<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, d_act, d_newid, d_cellof, d_cell_first, d_clsbase, d_newid2);
-        LAUNCHED(ctx);
-        k_halo_collect_e<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, B, ix->d_cls_off, ix->d_cls_tid, d_act, d_pos, m.blk_row0, d_hkeys, d_hcount);
+        if (C_a > 0) {
+            // new compact ids = rank in (cell, old id) order
+            CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_hkeys, d_hsort, (int32_t *)d_uniq_e, (int32_t *)d_uniq_m, (int)C_a, 0, 64, st));
+            k_class_newid<<<(unsigned)((C_a + 255) / 256), 256, 0, st>>>(C_a, (const int32_t *)d_uniq_m, d_newid2);
+            ctx->launches += 4;
+        }
+        k_halo_collect_e<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, B, ix->d_cls_off, ix->d_cls_tid, d_owner, d_act, d_pos, m.blk_row0, d_hkeys, d_hcount);
         LAUNCHED(ctx);
     }
     CU(cudaMemcpyAsync(&h_cnt[0], d_hcount, 4, cudaMemcpyDeviceToHost, st));
@@ -1132,7 +1154,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     CU(cudaMemsetAsync(m.e_tid, 0, e_ints_max * 4, st));
     if (nm > 0 && n_kseg > 0) {
         k_pack_classes<<<(unsigned)((nm * 32 + 255) / 256), 256, 0, st>>>(nm, T, n_kseg, m.blk_nres, m.blk_hr0, m.blk_nhr, d_uniq_e, ix->d_kseg_k, ix->d_cls_off,
-                                                                          ix->d_cls_tid, d_act, d_newid, d_cellof, d_cell_first, d_clsbase, d_intbase, s->d_R,
+                                                                          ix->d_cls_tid, d_act, d_newid, d_cellof, d_newid2, d_clsbase, d_intbase, s->d_R,
                                                                           d_pos, m.blk_row0, m.blk_cls0, m.e_tid, m.e_R);
         LAUNCHED(ctx);
     }
