@@ -167,9 +167,15 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
         emsar_comm_info(ctx, NULL, NULL, &pm);
         fprintf(stdout, "sample sharded by class range over %d GPUs (%s)\n", shard_n, pm == 1 ? "all-reduce inside the EM kernel, NVLink peer memory" : "ncclAllReduce per iteration");
     }
-    if (o->verbose > 0)
+    if (o->verbose > 0) {
         fprintf(stdout, "EM finished: %d iterations, delta %.3g, %.1f ms on the device (model build %.1f ms), logL %.10g\n",
                 out.n_iter, out.final_delta, out.em_ms, out.prep_ms, out.loglik);
+        emsar_model_stats ms;
+        if (emsar_sample_model_stats(s, &ms) == 0 && out.n_iter > 0 && out.em_ms > 0)     /* the per-phase profile line */
+            fprintf(stdout, "EM model: %lld active classes, %lld members, %d transcripts; %.1f us per iteration, %.0f GB/s of algorithmic bytes (%lld per iteration)\n",
+                    (long long)ms.C_a, (long long)ms.nnz_a, ms.T, 1e3 * out.em_ms / out.n_iter,
+                    (double)ms.bytes_per_iter * out.n_iter / (out.em_ms * 1e-3) / 1e9, (long long)ms.bytes_per_iter);
+    }
     int32_t *F = (int32_t *)malloc(sizeof(int32_t) * ((size_t)rsh->max_fraglength + 1));
     int32_t *R = (int32_t *)malloc(sizeof(int32_t) * (size_t)rsh->C);
     double *Wf = (double *)malloc(sizeof(double) * rsh->nF);
