@@ -307,6 +307,23 @@ static void scan_runs(cstore *c, sub *e, int64_t n, int L, const char *S, int ma
 }
 
 /* ---- the two library layouts -------------------------------------------------------------------------------------------- */
+typedef struct { sub *part; const int64_t *cnt; int nb; int *next; pthread_mutex_t *mu; int L; const char *S; int max_repeat, fi; cstore *c; } se_job;
+static void *se_worker(void *arg)
+{
+    se_job *jb = (se_job *)arg;
+    int32_t *tbuf = NULL; int64_t tcap = 0;
+    for (;;) {
+        pthread_mutex_lock(jb->mu);
+        const int b = (*jb->next)++;
+        pthread_mutex_unlock(jb->mu);
+        if (b >= jb->nb) break;
+        const int64_t a0 = jb->cnt[b], a1 = jb->cnt[b + 1];
+        if (a1 > a0) scan_runs(jb->c, jb->part + a0, a1 - a0, jb->L, jb->S, jb->max_repeat, jb->fi, 0, &tbuf, &tcap);
+    }
+    free(tbuf);
+    return NULL;
+}
+
 static void build_se(const txome *x, const emsar_build_opts *o, cstore *c)
 {
     const int64_t n = x->end + 1;
@@ -332,7 +349,33 @@ static void build_se(const txome *x, const emsar_build_opts *o, cstore *c)
                 m++;
             }
         }
-        scan_runs(c, e, m, L, x->S, o->max_repeat, L - o->readlen_min, 0, &tbuf, &tcap);
+        const int nthr = (o->threads > 1 && m >= 200000) ? (o->threads > 64 ? 64 : o->threads) : 1;
+        if (nthr == 1) { scan_runs(c, e, m, L, x->S, o->max_repeat, L - o->readlen_min, 0, &tbuf, &tcap); continue; }
+        /* equal substrings share their hash: partition the occurrences by its top bits and let every thread sort and scan whole
+         * partitions into a class store of its own (merged afterwards; the result does not depend on the thread count) */
+        enum { NB = 256 };
+        int64_t cnt[NB + 1];
+        memset(cnt, 0, sizeof cnt);
+        for (int64_t i = 0; i < m; i++) cnt[(e[i].h >> 56) + 1]++;
+        for (int b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
+        sub *part = (sub *)malloc(sizeof(sub) * (size_t)m);
+        int64_t fill[NB];
+        memcpy(fill, cnt, sizeof fill);
+        for (int64_t i = 0; i < m; i++) part[fill[e[i].h >> 56]++] = e[i];
+        se_job jobs[64];
+        pthread_t th[64];
+        int next_bucket = 0;
+        pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+        for (int w = 0; w < nthr; w++) {
+            jobs[w].part = part; jobs[w].cnt = cnt; jobs[w].nb = NB; jobs[w].next = &next_bucket; jobs[w].mu = &mu;
+            jobs[w].L = L; jobs[w].S = x->S; jobs[w].max_repeat = o->max_repeat; jobs[w].fi = L - o->readlen_min;
+            jobs[w].c = w == 0 ? c : (cstore *)malloc(sizeof(cstore));
+            if (w > 0) cs_init(jobs[w].c, c->T, c->nF);
+        }
+        for (int w = 1; w < nthr; w++) pthread_create(&th[w], NULL, se_worker, &jobs[w]);
+        se_worker(&jobs[0]);
+        for (int w = 1; w < nthr; w++) { pthread_join(th[w], NULL); cs_merge(c, jobs[w].c); cs_free(jobs[w].c); free(jobs[w].c); }
+        free(part);
     }
     free(H); free(ok); free(e); free(tbuf);
 }

@@ -182,3 +182,28 @@ def test_fasta_errors(built, tmp_path):
     assert r.returncode != 0 and "can't open fasta file" in r.stderr
     r = subprocess.run([MINE, "-q", "-s", "ssfr", str(bad), "25", str(tmp_path / "o"), "x"], capture_output=True, text=True)
     assert r.returncode != 0 and "invalid strand type" in r.stderr      # a PE strand type without -P
+
+
+def test_threaded_single_end_build_on_a_larger_transcriptome(built, tmp_path):
+    """> 200K substrings: the single-end construction partitions by hash and runs on several threads; same bytes as with one
+    thread and as the reference."""
+    rng = np.random.default_rng(11)
+    exons = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(80, 300)))) for _ in range(900)]
+    fa = str(tmp_path / "big.fa")
+    with open(fa, "w") as f:
+        t = 0
+        for g in range(260):
+            pool = [exons[(5 * g + j) % len(exons)] for j in range(7)]
+            for iso in range(int(rng.integers(1, 4))):
+                keep = [e for e in pool if rng.random() < 0.7] or pool[:1]
+                f.write(f">T{t}\n{''.join(keep)}\n")
+                t += 1
+    outs = {}
+    for tag, tool, extra in (("p4", MINE, ["-p", "4"]), ("p1", MINE, []), ("ref", REF, [])):
+        if not os.path.exists(tool):
+            continue
+        d = str(tmp_path / tag)
+        assert subprocess.run([tool, "-q"] + extra + [fa, "40-41", d, "x"], capture_output=True).returncode == 0
+        outs[tag] = open(os.path.join(d, "x.rsh"), "rb").read()
+    assert outs["p4"].count(b"\n") > 1000
+    assert len(set(outs.values())) == 1, {k: len(v) for k, v in outs.items()}
