@@ -223,24 +223,54 @@ int emsar_rsh_load(const char *path, emsar_rsh **out, char *err)
     return 0;
 }
 
+/* print_rsh writes hundreds of millions of small integers for a paired-end index (C x nF counts): they go through a
+ * hand-rolled decimal formatter into a 1 MB buffer instead of one fprintf each */
+typedef struct { FILE *f; char *buf; size_t n, cap; int failed; } wbuf;
+static void wb_flush(wbuf *w) { if (w->n && fwrite(w->buf, 1, w->n, w->f) != w->n) w->failed = 1; w->n = 0; }
+static inline void wb_room(wbuf *w, size_t need) { if (w->n + need > w->cap) wb_flush(w); }
+static inline void wb_ch(wbuf *w, char c) { wb_room(w, 1); w->buf[w->n++] = c; }
+static void wb_str(wbuf *w, const char *s)
+{
+    size_t l = strlen(s);
+    if (l >= w->cap) { wb_flush(w); if (fwrite(s, 1, l, w->f) != l) w->failed = 1; return; }
+    wb_room(w, l);
+    memcpy(w->buf + w->n, s, l);
+    w->n += l;
+}
+static void wb_int(wbuf *w, long long v)
+{
+    char t[24];
+    int k = 0;
+    unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    do { t[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    wb_room(w, (size_t)k + 1);
+    if (v < 0) w->buf[w->n++] = '-';
+    while (k) w->buf[w->n++] = t[--k];
+}
+
 int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err)
 {
     FILE *f = fopen(path, "w");
     if (!f) return fail(err, "Can't write to output rsh file %s", path);
-    fprintf(f, "#%d,%d,%d,%d,%d\n", r->T - 1, r->max_t_size, r->frag_min, r->frag_max, pe ? r->readlength : -1);
-    for (int32_t t = 0; t < r->T; t++) fprintf(f, "@%d\t%s\n", t, r->names[t]);
-    fprintf(f, "cid\tno.tids\tfirst.tid\tother.tids\tsegment.length\n");
+    wbuf w = {f, (char *)malloc(1 << 20), 0, 1 << 20, 0};
+    wb_ch(&w, '#'); wb_int(&w, r->T - 1); wb_ch(&w, ','); wb_int(&w, r->max_t_size); wb_ch(&w, ','); wb_int(&w, r->frag_min); wb_ch(&w, ',');
+    wb_int(&w, r->frag_max); wb_ch(&w, ','); wb_int(&w, pe ? r->readlength : -1); wb_ch(&w, '\n');
+    for (int32_t t = 0; t < r->T; t++) { wb_ch(&w, '@'); wb_int(&w, t); wb_ch(&w, '\t'); wb_str(&w, r->names[t]); wb_ch(&w, '\n'); }
+    wb_str(&w, "cid\tno.tids\tfirst.tid\tother.tids\tsegment.length\n");
     for (int64_t c = 0; c < r->C; c++) {
         int64_t o = r->class_ptr[c];
         int k = (int)(r->class_ptr[c + 1] - o);
-        if (k == 1 && !r->has_node[c]) { fprintf(f, "%lld\t%d\t%d\t\t\t\n", (long long)c, 1, r->class_tid[o]); continue; }
-        fprintf(f, "%lld\t%d\t%d\t", (long long)c, k, r->class_tid[o]);
-        for (int j = 1; j < k; j++) fprintf(f, "%d,", r->class_tid[o + j]);
-        fprintf(f, "\t");
-        for (int i = 0; i < r->nF; i++) fprintf(f, "%d,", r->euma[(size_t)c * r->nF + i]);
-        fprintf(f, "\n");
+        wb_int(&w, c); wb_ch(&w, '\t'); wb_int(&w, k); wb_ch(&w, '\t'); wb_int(&w, r->class_tid[o]); wb_ch(&w, '\t');
+        if (k == 1 && !r->has_node[c]) { wb_str(&w, "\t\t\n"); continue; }
+        for (int j = 1; j < k; j++) { wb_int(&w, r->class_tid[o + j]); wb_ch(&w, ','); }
+        wb_ch(&w, '\t');
+        const int32_t *e = r->euma + (size_t)c * r->nF;
+        for (int i = 0; i < r->nF; i++) { wb_int(&w, e[i]); wb_ch(&w, ','); }
+        wb_ch(&w, '\n');
     }
-    fclose(f);
+    wb_flush(&w);
+    free(w.buf);
+    if (fclose(f) != 0 || w.failed) return fail(err, "Can't write to output rsh file %s", path);
     return 0;
 }
 
