@@ -149,8 +149,11 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": f"{iters} EM iterations per step of the full {args.workload} model, pthread team of {cores}"},
             "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if args.ref_binary:
-        line["reference_binary"] = reference_binary_twin(cores)
+    if not args.no_ref_binary:
+        try:
+            line["reference_binary"] = reference_binary_twin(cores)      # `emsar -p N` itself, timed in the same run
+        except Exception as e:                                           # a reported side figure: never lose the line over it
+            line["reference_binary"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -165,8 +168,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converge", action="store_true", help="skip the one-off run to convergence (samples/min)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg (e2e is then null)")
-    ap.add_argument("--ref-binary", action="store_true",
-                    help="--impl reference only: also time the unmodified reference binary on the scaled twin (about 1-2 minutes)")
+    ap.add_argument("--no-ref-binary", action="store_true",
+                    help="--impl reference only: skip timing the unmodified reference binary (oracle/_ref/emsar -p N) on the scaled twin (about 1-2 minutes)")
     ap.add_argument("--shard", default="samples", choices=["samples", "classes"],
                     help="N>1: independent samples per GPU (-M list, weak scaling, the default) or ONE sample whose classes are "
                          "range-sharded over the GPUs with the per-iteration all-reduce (BASELINE.json configs[2], strong scaling)")
