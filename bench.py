@@ -113,6 +113,8 @@ def reference_binary_twin(cores):
     t0 = time.perf_counter()
     out = subprocess.run([ref, "-p", str(cores), "-n", "1", "-I", d + "/x.rsh", d + "/out", "p", d + "/x.bowtie"], capture_output=True, text=True)
     sec = time.perf_counter() - t0
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
     hms = [int(h) * 3600 + int(m) * 60 + int(s_) for h, m, s_ in re.findall(r"\d\d/\d\d,(\d\d):(\d\d):(\d\d)", out.stdout)]
     mle = None
     m = re.search(r"round 1/1\.\.\.\n\d\d/\d\d,(\d\d):(\d\d):(\d\d)(?s:.*?)computing effective length[^\n]*\n\d\d/\d\d,(\d\d):(\d\d):(\d\d)", out.stdout)
