@@ -1053,7 +1053,9 @@ int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, 
             p.sh.xbuf_off = (long long)(WIN_HDR_BYTES + 32 * (size_t)ctx->win_rows);
         }
     }
-    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)s->m.B * 128, st));
+    // scalars, barrier flags and the delta slots of the barrier-free kernel (behind the two flag arrays): the slots must be clean at every
+    // launch because their tags restart with every sample (s->slot_tag), and a launch that ended after 1-2 iterations leaves tags 1 and 2 behind
+    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256 + 2 * (size_t)ctx->prop.multiProcessorCount * 128 + 2 * (size_t)s->m.B * 16, st));
     // barrier-free variant: whenever every CTA holds its whole halo in shared memory (EMSAR_EM_MODE=barrier keeps the grid barriers)
     const char *em_mode = getenv("EMSAR_EM_MODE");
     const bool dataflow = !s->sharded && s->m.direct && s->m.all_local && s->d_slots && !(em_mode && !strcmp(em_mode, "barrier"));

@@ -157,6 +157,9 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
     if (out.eumacut != *eumacut && o->verbose > 0 && lead) fprintf(stdout, "module size too big. EUMAcut is readjusted to %.0f\n", out.eumacut);
     *eumacut = out.eumacut;   /* EUMAcut is a global that is never reset between files (emsar.h:94) */
+    if (lead && out.final_delta > 1.0)       /* whatever -q says: the reference prints "FPKM not converging, reinitializing.." (:3110) */
+        fprintf(stderr, "WARNING: %s: the estimator did not converge in %d iterations (delta %.3g > 1); the results are written but not final. "
+                        "Raise -i or loosen the tolerances.\n", o->aln[i], out.n_iter, out.final_delta);
     if (!lead) {               /* the other ranks hold the same result; only the first one writes it */
         free(out.fpkm); free(out.efflen); free(out.ireadcount); free(out.ireadcount_int); free(out.tpm);
         emsar_sample_end(s);

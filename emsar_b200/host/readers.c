@@ -517,14 +517,19 @@ static int sam_open(samfile *s, const char *path, char fmt, int io_threads, char
         int32_t l_text, n_ref;
         if (bam_read(s, magic, 4) != 4 || memcmp(magic, "BAM\1", 4) != 0) return fail(err, "can't open BAM file.");
         if (bam_read(s, &l_text, 4) != 4) return fail(err, "truncated BAM header");
+        if (l_text < 0) return fail(err, "corrupt BAM header (negative l_text)");
         char *text = (char *)malloc((size_t)l_text + 1);
+        if (!text) return fail(err, "out of memory reading the BAM header");
         if (bam_read(s, text, (unsigned)l_text) != l_text) { free(text); return fail(err, "truncated BAM header"); }
         free(text);
         if (bam_read(s, &n_ref, 4) != 4) return fail(err, "truncated BAM header");
+        if (n_ref < 0) return fail(err, "corrupt BAM header (negative n_ref)");
         for (int i = 0; i < n_ref; i++) {
             int32_t l_name, l_ref;
             if (bam_read(s, &l_name, 4) != 4) return fail(err, "truncated BAM header");
+            if (l_name < 0) return fail(err, "corrupt BAM header (negative l_name)");
             char *nm = (char *)malloc((size_t)l_name + 1);
+            if (!nm) return fail(err, "out of memory reading the BAM header");
             if (bam_read(s, nm, (unsigned)l_name) != l_name) { free(nm); return fail(err, "truncated BAM header"); }
             nm[l_name] = 0;
             if (bam_read(s, &l_ref, 4) != 4) { free(nm); return fail(err, "truncated BAM header"); }
@@ -549,6 +554,9 @@ static int sam_open(samfile *s, const char *path, char fmt, int io_threads, char
                 }
             }
         }
+        /* samtools 0.1.19 (the reference's reader) aborts on a text SAM without @SQ lines ("missing header"); every RNAME would resolve
+           to -1 here and the run would "succeed" with zero counts */
+        if (s->n_ref == 0) return fail(err, "SAM file has no @SQ header lines (missing header)");
         sam_build_ref_map(s);
     }
     return 0;
@@ -581,23 +589,33 @@ static int sam_next(samfile *s, samrec *r, char *err)
         memcpy(&n_cigar, b + 12, 2); memcpy(&flag, b + 14, 2); memcpy(&l_seq, b + 16, 4);
         r->ref = refID; r->pos = pos; r->flag = flag; r->l_qseq = l_seq;
         r->qname = (char *)(b + 32);
+        s->blk[bs] = 0;                      /* terminator first: nothing below can run past the record */
+        if (l_seq < 0 || l_read_name == 0) { fail(err, "corrupt BAM record"); return -1; }
         size_t off = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+        if (off > (size_t)bs || b[32 + (size_t)l_read_name - 1] != 0) { fail(err, "corrupt BAM record (fields exceed the record)"); return -1; }
         r->md = NULL;
-        /* aux fields: tag[2] type value */
+        /* aux fields: tag[2] type value; every length is checked against what is left of the record */
         while (off + 3 <= (size_t)bs) {
             const unsigned char *t = b + off;
+            const size_t left = (size_t)bs - off - 3;
             char ty = (char)t[2];
             size_t vlen;
             if (ty == 'A' || ty == 'c' || ty == 'C') vlen = 1;
             else if (ty == 's' || ty == 'S') vlen = 2;
             else if (ty == 'i' || ty == 'I' || ty == 'f') vlen = 4;
             else if (ty == 'd') vlen = 8;
-            else if (ty == 'Z' || ty == 'H') { vlen = strlen((const char *)t + 3) + 1; }
-            else if (ty == 'B') {
+            else if (ty == 'Z' || ty == 'H') {
+                const void *z = memchr(t + 3, 0, left);
+                if (!z) { fail(err, "corrupt BAM record (unterminated aux string)"); return -1; }
+                vlen = (size_t)((const unsigned char *)z - (t + 3)) + 1;
+            } else if (ty == 'B') {
+                if (left < 5) { fail(err, "corrupt BAM record (aux array)"); return -1; }
                 char st = (char)t[3]; int32_t cnt; memcpy(&cnt, t + 4, 4);
                 size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                if (cnt < 0) { fail(err, "corrupt BAM record (aux array)"); return -1; }
                 vlen = 5 + es * (size_t)cnt;
             } else break;
+            if (vlen > left) { fail(err, "corrupt BAM record (aux field exceeds the record)"); return -1; }
             if (t[0] == 'M' && t[1] == 'D' && ty == 'Z') r->md = (const char *)t + 3;
             off += 3 + vlen;
         }

@@ -14,6 +14,14 @@ static int fail(char *err, const char *fmt, ...)
     return 1;
 }
 
+/* a full disk shows up in ferror() or in fclose()'s flush: a truncated result file must not pass for a complete one */
+static int finish(FILE *f, const char *path, char *err)
+{
+    const int bad = ferror(f);
+    if (fclose(f) != 0 || bad) return fail(err, "write error on %s (disk full?)", path);
+    return 0;
+}
+
 int emsar_write_fpkm(const char *path, const emsar_rsh *r, const double *fpkm, const double *sd, const double *efflen,
                      const double *ireadcount, const int32_t *ireadcount_int, const double *tpm, char *err)
 {
@@ -22,8 +30,7 @@ int emsar_write_fpkm(const char *path, const emsar_rsh *r, const double *fpkm, c
     fprintf(f, "transcriptID\tFPKM\tsd.of.FPKM\teff.length\tiReadcount\tiReadcount.int\tTPM\n");
     for (int32_t t = 0; t < r->T; t++)
         fprintf(f, "%s\t%lf\t%lf\t%lf\t%lf\t%d\t%lf\n", r->names[t], fpkm[t], sd ? sd[t] : 0.0, efflen[t], ireadcount[t], ireadcount_int[t], tpm[t]);
-    fclose(f);
-    return 0;
+    return finish(f, path, err);
 }
 
 int emsar_write_fraglength(const char *path, const emsar_rsh *r, const int32_t *FraglengthCounts, const double *Wf, char *err)
@@ -32,8 +39,7 @@ int emsar_write_fraglength(const char *path, const emsar_rsh *r, const int32_t *
     if (!f) return fail(err, "Can't write to fraglength file %s", path);
     fprintf(f, "Fragment.length\tObs.Counts\tnormalized.Fragment.length.sampling.prob\n");
     for (int i = 0; i < r->nF; i++) fprintf(f, "%d\t%d\t%lg\n", i + r->frag_min, FraglengthCounts[i + r->frag_min], Wf[i]);
-    fclose(f);
-    return 0;
+    return finish(f, path, err);
 }
 
 int emsar_write_segments(const char *path, const emsar_rsh *r, const int32_t *set_id, const double *adjEUMA,
@@ -50,6 +56,5 @@ int emsar_write_segments(const char *path, const emsar_rsh *r, const int32_t *se
         for (int64_t j = o; j < e; j++) fprintf(f, "%s%s", j > o ? "+" : "", r->names[r->class_tid[j]]);
         fprintf(f, "\t%lf\t%d\t%f\n", adjEUMA[c], ReadCount[c], expected[c]);
     }
-    fclose(f);
-    return 0;
+    return finish(f, path, err);
 }

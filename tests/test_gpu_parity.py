@@ -196,3 +196,32 @@ def test_solve_kernel_variants(built, monkeypatch, variant, name):
     rel = np.abs(r["fpkm"] - o["fpkm"]) / np.maximum(np.abs(o["fpkm"]), 1e-300)
     reads_abs = np.abs(r["ireadcount"] - o["ireadcount"])
     assert np.all((rel <= 1e-9) | (reads_abs <= 1e-9)), (rel.max(), reads_abs.max())
+
+
+def test_short_launch_then_normal_sample_same_context(built):
+    """A launch that ends after 1-2 iterations leaves low tags in the convergence slots of the barrier-free kernel; the next
+    sample on the SAME context restarts its tags at 0 and must not accept them (the slots are cleared at every launch)."""
+    from emsar_b200.api import Context
+    idx, reads = _make("se_longk")
+    o = _oracle().quantify(idx, reads)
+    c = Context(0)
+    try:
+        ix = Index(c, idx)
+        for short in (1, 2, 3, 2, 1):
+            a = ix.sample()
+            a.count(reads.read_ptr, reads.read_tid, reads.read_fraglen)
+            a.prepare()
+            it, fd, ms = a.em_run(max_iter=short, stop_on_conv=True)
+            assert it == short
+            a.close()
+            s = ix.sample()
+            s.count(reads.read_ptr, reads.read_tid, reads.read_fraglen)
+            r = s.solve()
+            s.close()
+            assert abs(r["n_iter"] - o["n_iter"]) <= 1, (short, r["n_iter"], o["n_iter"])
+            assert r["final_delta"] <= 1.0
+            rel = np.abs(r["fpkm"] - o["fpkm"]) / np.maximum(np.abs(o["fpkm"]), 1e-300)
+            assert np.all((rel <= 1e-9) | (np.abs(r["ireadcount"] - o["ireadcount"]) <= 1e-9)), (short, rel.max())
+        ix.close()
+    finally:
+        c.close()

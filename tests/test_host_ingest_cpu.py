@@ -103,3 +103,50 @@ def test_packed_rsh_image_round_trip(built, tmp_path, monkeypatch):
         host.Rsh(str(tmp_path / "bad.pack"), packed=True)
     for r in (a, b, c, d, e, f):
         r.close()
+
+
+def test_sam_without_sq_header_is_an_error(pe_bam, tmp_path):
+    """samtools 0.1.19 (the reference's reader) aborts with 'missing header'; a silent zero-count run is not acceptable."""
+    body = [l for l in open(pe_bam / "in.sam") if not l.startswith("@SQ")]
+    p = tmp_path / "nosq.sam"
+    p.write_text("".join(body))
+    rsh = host.Rsh(str(pe_bam / "in.rsh"))
+    with pytest.raises(host.HostError, match="@SQ"):
+        host.read_alignments(rsh, str(p), pe=True, fmt="sam")
+    rsh.close()
+
+
+def test_malformed_bam_aux_is_an_error(pe_bam, tmp_path):
+    """Aux fields are bounds-checked against the record: an unterminated MD:Z string or an oversized B array must fail, not read on."""
+    import struct
+    import zlib
+
+    def bam(records):
+        out = bytearray(b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", 1))
+        out += struct.pack("<i", 3) + b"T0\0" + struct.pack("<i", 1000)
+        for body in records:
+            out += struct.pack("<i", len(body)) + body
+        res = bytearray()
+        for chunk in (bytes(out), b""):
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            cd = co.compress(chunk) + co.flush()
+            res += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+        return bytes(res)
+
+    def rec(aux, l_seq=4):
+        core = struct.pack("<iiBBHHHiiii", 0, 10, 3, 255, 4680, 1, 0x43, l_seq, 0, 50, 100)
+        return core + b"r0\0" + struct.pack("<I", (l_seq << 4) | 0) + bytes((l_seq + 1) // 2) + bytes(l_seq) + aux
+
+    rsh = host.Rsh(str(pe_bam / "in.rsh"))
+    cases = {
+        "unterminated_z": rec(b"MDZ4444"),                                    # no NUL before the record ends
+        "huge_b_array": rec(b"XBBi" + struct.pack("<i", 1 << 28)),
+        "negative_b_count": rec(b"XBBi" + struct.pack("<i", -5)),
+        "fields_exceed_record": rec(b"", l_seq=4)[:40],
+    }
+    for name, body in cases.items():
+        p = tmp_path / f"{name}.bam"
+        p.write_bytes(bam([body]))
+        with pytest.raises(host.HostError):
+            host.read_alignments(rsh, str(p), pe=True, fmt="bam")
+    rsh.close()
