@@ -27,14 +27,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+V2 = dict(T=200000, n_multi=1800000, alpha=2.4, kmax=99, module_cap=5000, p_cross=0.1, scatter=True)
 WORKLOADS = {
-    # name: (index kwargs, reads)
-    "config2_human_se": (dict(T=200000, n_multi=2100000, alpha=2.4, kmax=99, module_cap=5000), 30_000_000),
-    # scaled stand-in of BASELINE.json configs[4] (-k 1000, heavy-tailed cardinality up to 999, hub transcripts in 8000 classes each)
-    "config5_stress": (dict(T=60000, n_multi=250000, alpha=1.5, kmax=999, module_cap=3000, hubs=20, hub_classes=8000), 3_000_000),
-    "small": (dict(T=20000, n_multi=200000, alpha=2.4, kmax=99, module_cap=500), 3_000_000),
-    "tiny": (dict(T=2000, n_multi=20000, alpha=2.4, kmax=40, module_cap=200), 200_000),
+    # name: generator ("v2" = SURVEY.md section 8d spec at full size, emsar_b200.synth.make_index_v2 / make_reads_fast; "v1" = the
+    # family-block generator of the small parity cases), index kwargs, reads per sample
+    # BASELINE.json configs[1]: 200K transcripts, 2M classes (mean cardinality 4.47), 10 % of the classes across a paralog family whose
+    # gene families lie scattered over the tid range, 30M reads
+    "config2_human_se": ("v2", V2, 30_000_000),
+    "config2_shuffled": ("v2", dict(V2, shuffle_tids=True), 30_000_000),       # the same transcriptome under random transcript names
+    "config2_100m": ("v2", V2, 100_000_000),                                   # north star: 200K / 2M / 100M reads on one B200
+    # BASELINE.json configs[2]: PE L101 F101-500 (nF = 400: 3.2 GB of EUMA), 100M reads
+    "config3_pe_100m": ("v2", dict(V2, nF=400, frag_min=101, readlength=101), 100_000_000),
+    # BASELINE.json configs[4]: -k 1000, cardinality ~ k^-1.5 on [2, 999] (mean 39, nnz 70M), 200 hub transcripts in ~10^4 classes each
+    "config5_full": ("v2", dict(V2, alpha=1.5, kmax=999, hubs=200, hub_classes=10000), 10_000_000),
+    # round-1 workloads (family blocks of consecutive tids only; kept for continuity with profiles/r1*)
+    "config2_r1": ("v1", dict(T=200000, n_multi=2100000, alpha=2.4, kmax=99, module_cap=5000), 30_000_000),
+    "config5_stress": ("v1", dict(T=60000, n_multi=250000, alpha=1.5, kmax=999, module_cap=3000, hubs=20, hub_classes=8000), 3_000_000),
+    "small": ("v1", dict(T=20000, n_multi=200000, alpha=2.4, kmax=99, module_cap=500), 3_000_000),
+    "tiny": ("v1", dict(T=2000, n_multi=20000, alpha=2.4, kmax=40, module_cap=200), 200_000),
 }
+INDEX_SEED = {"config3_pe_100m": 3, "config5_full": 5}
 
 
 def peaks():
@@ -87,12 +99,27 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def make_workload(name, seed):
+_INDEX_CACHE = {}
+
+
+def make_index(name):
+    """One index per workload, shared by every sample / rank (cached inside the process)."""
     from emsar_b200 import synth
-    kw, n_reads = WORKLOADS[name]
+    if name not in _INDEX_CACHE:
+        gen, kw, _ = WORKLOADS[name]
+        seed = INDEX_SEED.get(name, 2)
+        _INDEX_CACHE.clear()                # one big index at a time
+        _INDEX_CACHE[name] = synth.make_index_v2(seed=seed, **kw) if gen == "v2" else synth.make_index(seed=seed, **kw)
+    return _INDEX_CACHE[name]
+
+
+def make_workload(name, seed, n_reads=None):
+    from emsar_b200 import synth
+    gen, kw, n_default = WORKLOADS[name]
     t0 = time.time()
-    idx = synth.make_index(seed=2, **kw)                 # one index shared by every sample / rank
-    reads = synth.make_reads(idx, n_reads, seed=seed)    # this rank's sample
+    idx = make_index(name)
+    n = n_default if n_reads is None else n_reads
+    reads = synth.make_reads_fast(idx, n, seed=seed) if gen == "v2" else synth.make_reads(idx, n, seed=seed)    # this rank's sample
     return idx, reads, time.time() - t0
 
 

@@ -99,9 +99,19 @@ def build_host(force=False):
     return outs
 
 
+def build_tools(force=False):
+    """Bench / test tooling: the fast synthetic-workload generator (no CUDA, not on the product path)."""
+    src = os.path.join(PKG, "tools", "synth_gen.c")
+    out = os.path.join(PKG, "libemsar_synth.so")
+    if force or _newer(out, [src]):
+        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"])
+    return [out]
+
+
 def build_all(force=False, verbose=False):
     outs = [build_cuda(force=force, verbose=verbose)]
     outs += build_host(force=force)
+    outs += build_tools(force=force)
     return outs
 
 

@@ -106,6 +106,7 @@ struct emsar_index {
     uint8_t *d_has_node;   // [C]
     uint32_t *d_txm_off;   // [T+1]   transpose of the multi-tid classes, ascending cid, multiplicity kept
     int32_t *d_txm_cid;    // [nnz_multi]
+    int32_t *d_order;      // [T] locality order: connected components kept together (the "natural order" of the EM rows follows it)
     unsigned long long *d_hash; // open addressing: (fingerprint << 32) | (cid + 1), 0 = empty
     uint64_t hash_mask;
     int64_t hash_inserted;
@@ -115,6 +116,7 @@ struct emsar_index {
     // host copies kept for the set decomposition (emsar_main.c:411-425)
     std::vector<uint32_t> h_cls_off;
     std::vector<int32_t> h_cls_tid;
+    std::vector<int32_t> h_order;
     int32_t n_sets_nocut, max_set_tids;
     int64_t device_bytes;
 };

@@ -69,6 +69,130 @@ static int uf_find(std::vector<int32_t> &p, int x)
     return x;
 }
 
+// ---- locality order of the transcripts (host only; no device needed) -----------------------------------------------------------
+// The EM kernel cuts the participating rows into contiguous per-CTA ranges in THIS order, so what matters is that transcripts which
+// share classes sit close together however the fasta was sorted (by name, randomly) and wherever paralogs lie.
+//   level 1: connected components of the class <-> transcript graph (in the order of their smallest tid) are kept together;
+//   level 2: inside a component, transcripts that co-occur in at least TWO small classes (cardinality <= 8) form a cluster - the isoforms
+//            of a gene / a tight gene family share many segments, whereas two paralogs or a repeat typically share one - and the
+//            clusters follow each other in the order of their smallest tid; inside a cluster the transcripts are laid out breadth-first
+//            over those strong links from a pseudo-peripheral transcript (a chain of overlapping isoform groups becomes a band).
+// mode 3 = level 1, plus level 2 when that lowers the share of member references leaving an SM's range (what the library uses),
+// 2 = both levels, 1 = components only, 0 = plain tid order (EMSAR_ORDER=cluster / component / tid: A-B runs).
+// share of the member references that leave the block of their class's first member when the transcripts are cut, in this order, into
+// nblocks equal ranges: the quantity the per-SM ownership of the EM kernel wants small
+static double order_remote_share(int32_t T, int64_t C, const int64_t *class_ptr, const int32_t *class_tid, const int32_t *order, int nblocks)
+{
+    std::vector<int32_t> blk((size_t)T);
+    for (int32_t i = 0; i < T; i++) blk[(size_t)order[i]] = (int32_t)((int64_t)i * nblocks / T);
+    int64_t remote = 0, all = 0;
+    for (int64_t c = T; c < C; c++) {
+        const int64_t o = class_ptr[c], e = class_ptr[c + 1];
+        const int32_t b0 = blk[(size_t)class_tid[o]];
+        for (int64_t j = o + 1; j < e; j++) remote += blk[(size_t)class_tid[j]] != b0;
+        all += e - o;
+    }
+    return all ? (double)remote / (double)all : 0.0;
+}
+
+extern "C" int emsar_locality_order(int32_t T, int64_t C, const int64_t *class_ptr, const int32_t *class_tid, int32_t mode, int32_t *order)
+{
+    CHECK_ARG(T > 0 && C >= T && class_ptr && class_tid && order, "emsar_locality_order: bad argument");
+    if (mode == 0) { std::iota(order, order + T, 0); return EMSAR_OK; }
+    if (mode == 3) {
+        // automatic: the component order is kept when it is already local (a fasta sorted by gene); otherwise the cluster order is
+        // tried and the better of the two wins
+        constexpr int NB = 148;
+        TRY(emsar_locality_order(T, C, class_ptr, class_tid, 1, order));
+        const double s1 = order_remote_share(T, C, class_ptr, class_tid, order, NB);
+        if (s1 < 0.15) return EMSAR_OK;
+        std::vector<int32_t> o2((size_t)T);
+        TRY(emsar_locality_order(T, C, class_ptr, class_tid, 2, o2.data()));
+        if (order_remote_share(T, C, class_ptr, class_tid, o2.data(), NB) < s1) memcpy(order, o2.data(), sizeof(int32_t) * (size_t)T);
+        return EMSAR_OK;
+    }
+    std::vector<int32_t> par((size_t)T), cmin((size_t)T), smin((size_t)T);
+    std::iota(par.begin(), par.end(), 0);
+    for (int64_t c = T; c < C; c++) {
+        const int r0 = uf_find(par, class_tid[class_ptr[c]]);
+        for (int64_t j = class_ptr[c] + 1; j < class_ptr[c + 1]; j++) { const int r = uf_find(par, class_tid[j]); if (r != r0) par[(size_t)r] = r0; }
+    }
+    std::fill(cmin.begin(), cmin.end(), -1);
+    for (int32_t t = 0; t < T; t++) { const int r = uf_find(par, t); if (cmin[(size_t)r] < 0) cmin[(size_t)r] = t; }      // ascending t: first seen = smallest
+    for (int32_t t = 0; t < T; t++) cmin[(size_t)t] = cmin[(size_t)uf_find(par, t)];
+    if (mode == 2) {
+        constexpr int KP = 8;
+        std::vector<uint64_t> pairs;
+        for (int64_t c = T; c < C; c++) {
+            const int64_t o = class_ptr[c], k = class_ptr[c + 1] - o;
+            if (k > KP) break;                                  // classes are ordered by cardinality
+            for (int64_t i = 0; i < k; i++)
+                for (int64_t j = i + 1; j < k; j++)
+                    if (class_tid[o + i] != class_tid[o + j]) pairs.push_back(((uint64_t)(uint32_t)class_tid[o + i] << 32) | (uint32_t)class_tid[o + j]);
+        }
+        std::sort(pairs.begin(), pairs.end());
+        // strong edges = pairs seen at least twice; adjacency in CSR form (both directions)
+        std::vector<uint64_t> strong;
+        for (size_t i = 0; i + 1 < pairs.size(); i++)
+            if (pairs[i] == pairs[i + 1] && (strong.empty() || strong.back() != pairs[i])) strong.push_back(pairs[i]);
+        pairs.clear(); pairs.shrink_to_fit();
+        std::vector<uint32_t> adj_off((size_t)T + 1, 0);
+        for (uint64_t e : strong) { adj_off[(size_t)(e >> 32) + 1]++; adj_off[(size_t)(uint32_t)e + 1]++; }
+        for (int32_t t = 0; t < T; t++) adj_off[(size_t)t + 1] += adj_off[(size_t)t];
+        std::vector<int32_t> adj((size_t)adj_off[(size_t)T]);
+        {
+            std::vector<uint32_t> cur(adj_off.begin(), adj_off.end() - 1);
+            for (uint64_t e : strong) {                              // sorted by (a, b): every adjacency list comes out in ascending order
+                const int a = (int)(e >> 32), b = (int)(uint32_t)e;
+                adj[cur[(size_t)a]++] = b; adj[cur[(size_t)b]++] = a;
+            }
+        }
+        std::iota(par.begin(), par.end(), 0);
+        for (uint64_t e : strong) {
+            const int a = uf_find(par, (int)(e >> 32)), b = uf_find(par, (int)(uint32_t)e);
+            if (a != b) par[(size_t)b] = a;
+        }
+        std::fill(smin.begin(), smin.end(), -1);
+        for (int32_t t = 0; t < T; t++) { const int r = uf_find(par, t); if (smin[(size_t)r] < 0) smin[(size_t)r] = t; }
+        for (int32_t t = 0; t < T; t++) smin[(size_t)t] = smin[(size_t)uf_find(par, t)];
+        // inside a cluster: breadth-first order over the strong edges from a pseudo-peripheral transcript (the last one a first sweep from
+        // the smallest tid reaches), which lays a chain of overlapping isoform groups out as a band instead of in name order
+        std::vector<int32_t> pos((size_t)T, -1), queue;
+        std::vector<uint8_t> seen((size_t)T, 0);
+        queue.reserve(1024);
+        auto bfs = [&](int32_t start, uint8_t mark) {
+            queue.clear(); queue.push_back(start); seen[(size_t)start] = mark;
+            for (size_t h = 0; h < queue.size(); h++) {
+                const int32_t u = queue[h];
+                for (uint32_t e = adj_off[(size_t)u]; e < adj_off[(size_t)u + 1]; e++) {
+                    const int32_t v = adj[e];
+                    if (seen[(size_t)v] != mark) { seen[(size_t)v] = mark; queue.push_back(v); }
+                }
+            }
+        };
+        for (int32_t t = 0; t < T; t++) {
+            if (smin[(size_t)t] != t) continue;                     // t = smallest tid of its cluster
+            bfs(t, 1);
+            const int32_t far = queue.back();
+            bfs(far, 2);
+            for (size_t i = 0; i < queue.size(); i++) pos[(size_t)queue[i]] = (int32_t)i;
+        }
+        std::iota(order, order + T, 0);
+        std::sort(order, order + T, [&](int32_t a, int32_t b) {
+            if (cmin[(size_t)a] != cmin[(size_t)b]) return cmin[(size_t)a] < cmin[(size_t)b];
+            if (smin[(size_t)a] != smin[(size_t)b]) return smin[(size_t)a] < smin[(size_t)b];
+            return pos[(size_t)a] < pos[(size_t)b];
+        });
+        return EMSAR_OK;
+    }
+    std::iota(order, order + T, 0);
+    std::sort(order, order + T, [&](int32_t a, int32_t b) {
+        if (cmin[(size_t)a] != cmin[(size_t)b]) return cmin[(size_t)a] < cmin[(size_t)b];
+        return a < b;
+    });
+    return EMSAR_OK;
+}
+
 extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, emsar_index **out)
 {
     CHECK_ARG(ctx && d && out, "emsar_index_create: NULL argument");
@@ -165,6 +289,14 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
         for (int32_t t = 0; t < T; t++) { int r = uf_find(par, t); if (sz[(size_t)r]++ == 0) ns++; if (sz[(size_t)r] > mx) mx = sz[(size_t)r]; }
         ix->n_sets_nocut = ns; ix->max_set_tids = mx;
     }
+    // ---- locality order of the transcripts (emsar_locality_order below) ----
+    {
+        ix->h_order.resize((size_t)T);
+        const char *eo = getenv("EMSAR_ORDER");
+        const int mode = (eo && !strcmp(eo, "tid")) ? 0 : (eo && !strcmp(eo, "component")) ? 1 : (eo && !strcmp(eo, "cluster")) ? 2 : 3;
+        int orc = emsar_locality_order(T, C, d->class_ptr, d->class_tid, mode, ix->h_order.data());
+        if (orc != EMSAR_OK) { delete ix; return orc; }
+    }
     // ---- upload ----
     int rc;
 #define UP(dst, src, n, type)                                                                         \
@@ -179,6 +311,7 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
     UP(ix->d_has_node, hn.data(), C, uint8_t);
     UP(ix->d_txm_off, txm_off.data(), T + 1, uint32_t);
     UP(ix->d_txm_cid, txm_cid.data(), nnz - T, int32_t);
+    UP(ix->d_order, ix->h_order.data(), T, int32_t);
     std::vector<int64_t> kc0; std::vector<int32_t> kk;
     for (auto &s : kseg) { kc0.push_back(s.cid0); kk.push_back(s.k); }
     kc0.push_back(C);
@@ -210,7 +343,7 @@ extern "C" int emsar_index_destroy(emsar_index *ix)
     ctx_use(ix->ctx);
     cudaStreamSynchronize(ix->ctx->stream);
     dev_free(ix->d_cls_off); dev_free(ix->d_cls_tid); dev_free(ix->d_euma); dev_free(ix->d_has_node);
-    dev_free(ix->d_txm_off); dev_free(ix->d_txm_cid); dev_free(ix->d_hash); dev_free(ix->d_kseg_cid0); dev_free(ix->d_kseg_k);
+    dev_free(ix->d_txm_off); dev_free(ix->d_txm_cid); dev_free(ix->d_order); dev_free(ix->d_hash); dev_free(ix->d_kseg_cid0); dev_free(ix->d_kseg_k);
     delete ix;
     return EMSAR_OK;
 }

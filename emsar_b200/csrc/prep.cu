@@ -193,6 +193,20 @@ __global__ void k_shard_apply(int64_t n_multi, const uint32_t *__restrict__ wpre
     if (!mine) act[i] = 0;
 }
 
+// natural order = the index's locality order (components kept together): flags gathered in that order, scanned, scattered back
+__global__ void k_order_gather(int32_t T, const int32_t *__restrict__ order, const uint32_t *__restrict__ rflag, uint32_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > T) return;
+    out[i] = i < T ? rflag[order[i]] : 0u;
+}
+__global__ void k_order_scatter(int32_t T, const int32_t *__restrict__ order, const uint32_t *__restrict__ pre, uint32_t *__restrict__ nat)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > T) return;
+    if (i < T) nat[order[i]] = pre[i]; else nat[T] = pre[T];
+}
+
 // participating transcripts in natural order: n = rank, with their active row length
 __global__ void k_nat_fill(int32_t T, const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ nat, const int32_t *__restrict__ deg,
                            int32_t *__restrict__ pos, uint32_t *__restrict__ degn, int32_t *__restrict__ tn, int32_t *__restrict__ ecost, int32_t P)
@@ -805,8 +819,10 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     k_row_stats<<<(unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, st>>>(T, ix->d_txm_off, ix->d_txm_cid, s->d_adj, s->d_amodel, d_act, d_in_model,
                                                                           s->d_R, s->d_iE, s->d_A, s->d_Rs, d_deg, s->d_lone, d_rflag);
     LAUNCHED(ctx);
-    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_rflag, d_nat, T + 1, st));
-    LAUNCHED(ctx);
+    k_order_gather<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(T, ix->d_order, d_rflag, d_degn);      // d_degn / d_degp: free until k_nat_fill
+    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_degn, d_degp, T + 1, st));
+    k_order_scatter<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(T, ix->d_order, d_degp, d_nat);
+    ctx->launches += 3;
     CU(cudaGetLastError());
     uint32_t P32 = 0; int32_t C_a32 = 0;
     CU(cudaMemcpyAsync(&P32, d_nat + T, 4, cudaMemcpyDeviceToHost, st));
@@ -1066,6 +1082,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     const bool direct = !(getenv("EMSAR_EM_MODE") && !strcmp(getenv("EMSAR_EM_MODE"), "pipe"));
     std::vector<int32_t> h_eres((size_t)n_etiles + 1, -1), h_mres((size_t)n_mitems + 1, -1), h_resints(B + 1, 0);
     int32_t grid_all_local = 1;
+    int64_t resident_ints = 0, rows_long = 0;
+    for (int i = 0; i < n_mitems; i++) if ((h_mi[(size_t)i].w >> 30) == 1) rows_long += h_mi[(size_t)i].y;
     for (int b = 0; b < B; b++) {
         // what of a CTA's state gets a shared-memory slot: its rows (always), then halo rows, then its classes, then halo classes
         const int nrows = h_row0[b + 1] - h_row0[b];
@@ -1105,6 +1123,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
                 used += need;
             }
             h_resints[b] = used;
+            resident_ints += used;
         }
     }
     {
@@ -1179,7 +1198,15 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     emsar_model_stats &ms_ = s->stats;
     memset(&ms_, 0, sizeof(ms_));
     ms_.T = T; ms_.C_a = C_a; ms_.nnz_a = m.nnz_a;
-    ms_.rows_short = P; ms_.rows_long = 0; ms_.rows_hub = 0; ms_.rows_fixed = T - P;
+    ms_.rows_short = P; ms_.rows_long = rows_long; ms_.rows_hub = 0; ms_.rows_fixed = T - P;
+    {
+        const char *em_mode = getenv("EMSAR_EM_MODE");
+        const bool want_barrier = em_mode && !strcmp(em_mode, "barrier");
+        ms_.em_variant = s->sharded ? 2 : (m.direct && m.all_local && s->d_slots && !want_barrier) ? 3 : m.direct ? 1 : 0;      // as em_launch decides
+    }
+    ms_.all_local = m.all_local; ms_.halo_rows = n_ue; ms_.halo_classes = n_um;
+    ms_.resident_index_bytes = 4 * resident_ints;
+    ms_.index_bytes = 4 * ((int64_t)e_ints + C_a + (int64_t)m_ints);
     ms_.e_tiles = n_etiles; ms_.m_tiles = n_mitems;
     ms_.bytes_per_iter = 8 * m.nnz_a + 24 * C_a + 44 * (int64_t)T;
     // what the kernel streams per iteration: E: encoded members (padded) + R (+ q to global for halo classes);

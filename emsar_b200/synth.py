@@ -172,6 +172,193 @@ def make_index(T=2000, n_multi=10000, alpha=2.4, kmax=99, nF=1, seed=0, module_c
                       max_t_size=max(max_t_size, 2))
 
 
+# ----------------------------------------------------------------------------------------------
+# Human-scale generators (bench.py, full-size tests): the loops run in emsar_b200/tools/synth_gen.c.
+# ----------------------------------------------------------------------------------------------
+_GEN = None
+
+
+def _gen():
+    global _GEN
+    if _GEN is None:
+        import ctypes as C
+        so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libemsar_synth.so")
+        if not os.path.exists(so):
+            from . import build
+            build.build_tools()
+        _GEN = C.CDLL(so)
+        _GEN.synth_reads_pass1.restype = C.c_int64
+    return _GEN
+
+
+def _cp(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_index_v2(T=200000, n_multi=1800000, alpha=2.4, kmax=99, nF=1, seed=0, module_cap=5000, p_cross=0.1, scatter=True,
+                  p_dup_tid=0.01, hubs=0, hub_classes=0, frag_min=None, readlength=-1, shuffle_tids=False) -> SynthIndex:
+    """SURVEY.md section 8(d) generator at full size. Gene families are blocks of consecutive tids; families are grouped into
+    paralog families of at most `module_cap` transcripts (from scattered places of the tid range when `scatter`, so that the
+    fasta order does NOT keep a module together); a class draws its members inside one gene family (1 - p_cross) or anywhere
+    in its paralog family (p_cross). Connected modules therefore stay <= module_cap transcripts (EUMAcut = 0). `hubs` transcripts
+    (spread over the largest paralog families) are forced into about `hub_classes` classes each. `shuffle_tids` finally renames
+    the transcripts by a random permutation (a fasta in arbitrary order)."""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    G = _gen()
+    fam_sizes = []
+    left = T
+    while left > 0:
+        s = int(min(left, module_cap, max(1, round(rng.pareto(1.2) * 8 + 1 + rng.geometric(0.2)))))
+        fam_sizes.append(s)
+        left -= s
+    fam_sizes = np.array(fam_sizes, dtype=np.int64)
+    nfam = len(fam_sizes)
+    fam_start = np.concatenate([[0], np.cumsum(fam_sizes)[:-1]])
+    # paralog families: greedy bins of families (random order when scattered) with at most module_cap transcripts
+    order = rng.permutation(nfam) if scatter else np.arange(nfam)
+    grp_of_fam = np.zeros(nfam, dtype=np.int64)
+    g, acc = 0, 0
+    for f in order:
+        if acc + fam_sizes[f] > module_cap and acc > 0:
+            g += 1
+            acc = 0
+        grp_of_fam[f] = g
+        acc += fam_sizes[f]
+    ngrp = g + 1
+    # virtual order: families of one paralog family are contiguous; vmap[virtual position] = tid
+    forder = np.lexsort((np.arange(nfam), grp_of_fam))
+    vfam_start = np.zeros(nfam, dtype=np.int64)
+    vfam_start[forder] = np.concatenate([[0], np.cumsum(fam_sizes[forder])[:-1]])
+    vmap = np.empty(T, dtype=np.int32)
+    for f in range(nfam):
+        vmap[vfam_start[f]:vfam_start[f] + fam_sizes[f]] = np.arange(fam_start[f], fam_start[f] + fam_sizes[f], dtype=np.int32)
+    grp_size = np.bincount(grp_of_fam, weights=fam_sizes, minlength=ngrp).astype(np.int64)
+    grp_vstart = np.zeros(ngrp, dtype=np.int64)
+    np.minimum.at(grp_vstart, grp_of_fam, np.iinfo(np.int64).max)
+    grp_vstart[:] = np.iinfo(np.int64).max
+    np.minimum.at(grp_vstart, grp_of_fam, vfam_start)
+    # hubs: spread over the largest paralog families
+    hub_ptr = hub_tid = hub_p = None
+    ks = _powerlaw_k(rng, n_multi, alpha, 2, kmax)
+    if hubs > 0 and hub_classes > 0:
+        big = np.argsort(-grp_size)[:max(1, min(ngrp, (hubs + 3) // 4))]
+        hg = big[np.arange(hubs) % len(big)]
+        ht = np.array([vmap[grp_vstart[g_] + rng.integers(0, grp_size[g_])] for g_ in hg], dtype=np.int32)
+        o = np.argsort(hg, kind="stable")
+        hg, ht = hg[o], ht[o]
+        hub_ptr = np.zeros(ngrp + 1, dtype=np.int64)
+        np.add.at(hub_ptr, hg + 1, 1)
+        hub_ptr = np.cumsum(hub_ptr)
+        hub_tid = np.ascontiguousarray(ht)
+        exp_cls = n_multi * grp_size / float(T)                 # classes a paralog family receives (drawn in proportion to its size)
+        hub_p = np.minimum(0.9, 1.4 * hub_classes / np.maximum(exp_cls, 1.0))
+    blocks = {}
+    order_sizes = np.argsort(fam_sizes)
+    sizes_sorted = fam_sizes[order_sizes]
+    gorder = np.argsort(grp_size)
+    gsorted = grp_size[gorder]
+    for k in np.unique(ks):
+        k = int(k)
+        n_want = int((ks == k).sum())
+        n_k = int(n_want * (2.2 if k == 2 else 1.5 if k == 3 else 1.34)) + 8      # duplicate keys are dropped below (small genes collide often)
+        lo_f = np.searchsorted(sizes_sorted, k, side="left")
+        lo_g = np.searchsorted(gsorted, k, side="left")
+        if lo_g >= ngrp:
+            continue
+        cross = rng.random(n_k) < p_cross
+        if lo_f >= nfam:
+            cross[:] = True                      # no single gene family is large enough
+        vlo = np.zeros(n_k, dtype=np.int64)
+        w = np.zeros(n_k, dtype=np.int64)
+        grp = np.zeros(n_k, dtype=np.int32)
+        nin = int((~cross).sum())
+        if nin:
+            elig = order_sizes[lo_f:]
+            wf = fam_sizes[elig].astype(np.float64)
+            fam = elig[rng.choice(len(elig), size=nin, p=wf / wf.sum())]
+            fsz = fam_sizes[fam]
+            wide = rng.random(nin) < 0.1
+            ww = np.where(wide, k + 16 + rng.geometric(0.05, size=nin), k + rng.geometric(0.25, size=nin))
+            ww = np.maximum(np.minimum(ww, fsz), k)
+            vlo[~cross] = vfam_start[fam] + (rng.random(nin) * (fsz - ww + 1)).astype(np.int64)
+            w[~cross] = ww
+            grp[~cross] = grp_of_fam[fam]
+        nx = n_k - nin
+        if nx:
+            elig = gorder[lo_g:]
+            wg = grp_size[elig].astype(np.float64)
+            gg = elig[rng.choice(len(elig), size=nx, p=wg / wg.sum())]
+            vlo[cross] = grp_vstart[gg]
+            w[cross] = grp_size[gg]
+            grp[cross] = gg
+        rows = np.empty((n_k, k), dtype=np.int32)
+        bad = G.synth_gen_classes(C.c_int64(n_k), C.c_int32(k), _cp(vlo), _cp(w), _cp(vmap), C.c_uint64(seed * 1000003 + k),
+                                  C.c_double(p_dup_tid), _cp(grp), _cp(hub_ptr), _cp(hub_tid), _cp(hub_p), _cp(rows))
+        assert bad == 0
+        rows = np.unique(rows, axis=0)
+        if len(rows) > n_want:
+            rows = rows[np.sort(rng.choice(len(rows), size=n_want, replace=False))]
+        blocks[k] = rows
+    if shuffle_tids:
+        perm = rng.permutation(T).astype(np.int32)        # new name of every transcript
+        for k in list(blocks):
+            r = perm[blocks[k]]
+            r.sort(axis=1)
+            blocks[k] = np.unique(r, axis=0)              # canonical class order under the new names
+    k_sorted = sorted(blocks)
+    card = np.concatenate([np.full(len(blocks[k]), k, dtype=np.int64) for k in k_sorted])
+    multi_tid = np.concatenate([blocks[k].ravel() for k in k_sorted])
+    n_multi = len(card)
+    Cn = T + n_multi
+    class_ptr = np.zeros(Cn + 1, dtype=np.int64)
+    class_ptr[1:T + 1] = np.arange(1, T + 1)
+    class_ptr[T + 1:] = T + np.cumsum(card)
+    class_tid = np.concatenate([np.arange(T, dtype=np.int32), multi_tid.astype(np.int32)])
+    a_single = np.floor(rng.lognormal(6.0, 0.8, size=T)).astype(np.int64) + 1
+    a_multi = rng.geometric(np.minimum(0.9, 0.01 * card), size=n_multi).astype(np.int64)
+    a = np.concatenate([a_single, a_multi]).astype(np.float64)
+    if nF == 1:
+        euma = a[:, None].astype(np.int32)
+    else:
+        slope = a / (nF * rng.uniform(0.8, 3.0, size=Cn))
+        euma = np.empty((Cn, nF), dtype=np.int32)
+        G.synth_euma_fill(C.c_int64(Cn), C.c_int32(nF), _cp(a), _cp(slope), _cp(euma))
+    if frag_min is None:
+        frag_min = 1 if readlength < 0 else readlength
+    return SynthIndex(T=T, names=None, class_ptr=class_ptr, class_tid=class_tid, euma=euma, has_node=np.ones(Cn, dtype=np.uint8),
+                      min_fraglength=frag_min, max_fraglength=frag_min + nF - 1, readlength=readlength,
+                      max_t_size=max(int(card.max()) if n_multi else 1, 2))
+
+
+def make_reads_fast(idx: SynthIndex, N, seed=0, p_zero=0.3, p_unmatched=0.005) -> SynthReads:
+    """make_reads for 10^7..10^8 reads: the class of every read is an independent draw from p_c (alias method), which has the
+    distribution of the multinomial-then-shuffle of make_reads; tid lists rotated / reversed, unmatched pairs and fragment
+    lengths as there. Threads: OpenMP; the result depends on (idx, N, seed) only."""
+    import ctypes as C
+    G = _gen()
+    p = class_rates(idx, true_theta(idx, seed, p_zero))
+    Cn = idx.C
+    prob = np.empty(Cn, dtype=np.float64)
+    alias = np.empty(Cn, dtype=np.int64)
+    rc = G.synth_alias_build(C.c_int64(Cn), _cp(np.ascontiguousarray(p)), _cp(prob), _cp(alias))
+    assert rc == 0
+    N = int(N)
+    cls = np.empty(N, dtype=np.int64)
+    read_ptr = np.empty(N + 1, dtype=np.int64)
+    cp = np.ascontiguousarray(idx.class_ptr, dtype=np.int64)
+    ct = np.ascontiguousarray(idx.class_tid, dtype=np.int32)
+    tot = G.synth_reads_pass1(C.c_int64(N), C.c_uint64(seed), C.c_int64(Cn), _cp(cp), _cp(prob), _cp(alias), C.c_double(p_unmatched),
+                              _cp(cls), _cp(read_ptr))
+    read_tid = np.empty(int(tot), dtype=np.int32)
+    fl = np.empty(N, dtype=np.int32)
+    cdf = np.ascontiguousarray(np.cumsum(frag_weights(idx)))
+    G.synth_reads_pass2(C.c_int64(N), C.c_uint64(seed), C.c_int32(idx.T), _cp(cp), _cp(ct), _cp(cls), _cp(read_ptr), C.c_int32(idx.nF),
+                        C.c_int32(idx.frag_min), _cp(cdf), _cp(read_tid), _cp(fl))
+    return SynthReads(read_ptr=read_ptr, read_tid=read_tid, read_fraglen=fl, true_class=cls)
+
+
 def true_theta(idx: SynthIndex, seed=0, p_zero=0.3):
     rng = np.random.default_rng(seed + 7919)
     th = rng.lognormal(0.0, 2.0, size=idx.T)

@@ -96,6 +96,12 @@ typedef struct {
 } emsar_index_info;
 
 int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *desc, emsar_index **index);
+/* The order in which emsar_index_create lays the transcripts out for the EM kernel's per-SM row ranges (host-only helper, no
+ * device needed): order[i] = tid of the i-th transcript. mode 1: connected components of the class <-> transcript graph kept
+ * together, tid order inside; 2: additionally, inside a component, the clusters of transcripts that co-occur in at least two
+ * small classes (the isoforms of a gene, a tight family) kept together and laid out breadth-first; 3 (what the library uses):
+ * 1, or 2 where that leaves fewer member references outside an SM's range; 0: tid order. */
+int emsar_locality_order(int32_t T, int64_t C, const int64_t *class_ptr, const int32_t *class_tid, int32_t mode, int32_t *order);
 int emsar_index_info_get(const emsar_index *index, emsar_index_info *info);
 int emsar_index_destroy(emsar_index *index);
 
@@ -195,10 +201,18 @@ int emsar_shard_ranges(int64_t n, const int64_t *weight_prefix, int32_t nranks, 
 typedef struct {
     int32_t T;
     int64_t C_a, nnz_a;       /* active multi-tid classes (modelled, R > 0) and their members */
-    int64_t rows_short, rows_long, rows_hub, rows_fixed; /* transcripts by transposed-row length; fixed: A_t == 0 */
+    int64_t rows_short;       /* participating transcripts (A_t > 0): the rows of the EM */
+    int64_t rows_long;        /* of those: rows with more than 64 active entries (one warp per row instead of a slice lane) */
+    int64_t rows_hub;         /* of those: rows whose entries are split over several CTAs (0 = none) */
+    int64_t rows_fixed;       /* transcripts outside the EM (A_t == 0) */
     int64_t e_tiles, m_tiles;
     int64_t bytes_per_iter;   /* algorithmic bytes of one EM iteration: 8 nnz_a + 24 C_a + 44 T */
     int64_t stream_bytes_per_iter; /* bytes the kernels actually stream per iteration (index + state) */
+    int32_t em_variant;       /* k_em_persistent<V> this sample runs: 3 barrier-free, 1 grid barriers (overflow), 0 TMA-pipelined, 2 class-sharded */
+    int32_t all_local;        /* 1: every CTA holds its whole halo and all its q in shared memory */
+    int64_t halo_rows, halo_classes;   /* distinct (CTA, remote row) / (CTA, remote class) references */
+    int64_t resident_index_bytes;      /* index data kept in shared memory for the whole kernel, summed over the CTAs */
+    int64_t index_bytes;               /* packed index data of the model (E members + read counts + M entries, with padding) */
 } emsar_model_stats;
 /* Wf, adjEUMA, EUMAps, sets/EUMAcut, A_t, iEUMA and the packed active model; theta := start point */
 int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opts);
