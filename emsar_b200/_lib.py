@@ -52,7 +52,7 @@ class ModelStats(C.Structure):
                 ("rows_hub", C.c_int64), ("rows_fixed", C.c_int64), ("e_tiles", C.c_int64), ("m_tiles", C.c_int64),
                 ("bytes_per_iter", C.c_int64), ("stream_bytes_per_iter", C.c_int64),
                 ("em_variant", C.c_int32), ("all_local", C.c_int32), ("halo_rows", C.c_int64), ("halo_classes", C.c_int64),
-                ("resident_index_bytes", C.c_int64), ("index_bytes", C.c_int64)]
+                ("resident_index_bytes", C.c_int64), ("index_bytes", C.c_int64), ("peer_bytes_per_iter", C.c_int64)]
 
 
 # every symbol include/emsar_cuda.h declares (tests check that the library exports all of them)
@@ -62,7 +62,7 @@ SYMBOLS = [
     "emsar_sample_begin", "emsar_sample_count", "emsar_sample_count_device", "emsar_sample_counts_set", "emsar_sample_counts_get",
     "emsar_sample_solve", "emsar_sample_segments_get", "emsar_sample_wf_get", "emsar_sample_end", "emsar_sample_prepare",
     "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_finalize",
-    "emsar_host_alloc", "emsar_host_free", "emsar_sample_count_wait", "emsar_comm_unique_id", "emsar_comm_init", "emsar_comm_destroy", "emsar_comm_info", "emsar_sample_counts_allreduce", "emsar_shard_ranges", "emsar_locality_order",
+    "emsar_host_alloc", "emsar_host_free", "emsar_sample_count_wait", "emsar_comm_unique_id", "emsar_comm_init", "emsar_comm_destroy", "emsar_comm_info", "emsar_sample_counts_allreduce", "emsar_shard_ranges", "emsar_locality_order", "emsar_cuda_timer_start", "emsar_cuda_timer_stop", "emsar_sample_time_adjeuma",
 ]
 
 

@@ -43,6 +43,14 @@ class Context:
         L.check(L.lib().emsar_cuda_launch_count(self._h, C.byref(n)), "emsar_cuda_launch_count")
         return int(n.value)
 
+    def timer_start(self):
+        L.check(L.lib().emsar_cuda_timer_start(self._h), "emsar_cuda_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0)
+        L.check(L.lib().emsar_cuda_timer_stop(self._h, C.byref(ms)), "emsar_cuda_timer_stop")
+        return float(ms.value)
+
     def synchronize(self):
         L.check(L.lib().emsar_cuda_synchronize(self._h), "emsar_cuda_synchronize")
 
@@ -207,6 +215,11 @@ class Sample:
         L.check(L.lib().emsar_sample_em_run(self._h, int(max_iter), int(bool(stop_on_conv)), int(bool(reset_theta)),
                                             C.byref(it), C.byref(fd), C.byref(ms)), "emsar_sample_em_run")
         return int(it.value), float(fd.value), float(ms.value)
+
+    def time_adjeuma(self, reps=5) -> float:
+        ms = C.c_double(0)
+        L.check(L.lib().emsar_sample_time_adjeuma(self._h, int(reps), C.byref(ms)), "emsar_sample_time_adjeuma")
+        return float(ms.value)
 
     def theta(self):
         th = np.zeros(self.index.T)

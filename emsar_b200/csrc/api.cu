@@ -100,6 +100,8 @@ extern "C" int emsar_cuda_open(int device, emsar_ctx **out)
     for (int i = 0; i < 9; i++) CU(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaEventCreate(&ctx->tev0));
+    CU(cudaEventCreate(&ctx->tev1));
     // [0..63] scalars of the EM kernel (delta slots, iteration count), then one 128-byte barrier line per CTA
     const size_t bar_bytes = 256 + (size_t)ctx->prop.multiProcessorCount * 4 * 128;
     CU(cudaMalloc(&ctx->d_barrier, bar_bytes));
@@ -124,6 +126,8 @@ extern "C" int emsar_cuda_close(emsar_ctx *ctx)
     cudaFree(ctx->d_scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->tev0);
+    cudaEventDestroy(ctx->tev1);
     for (int i = 0; i < 9; i++) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->pool) cudaMemPoolDestroy((cudaMemPool_t)ctx->pool);
@@ -145,6 +149,26 @@ extern "C" int emsar_cuda_synchronize(emsar_ctx *ctx)
     CHECK_ARG(ctx, "emsar_cuda_synchronize: NULL ctx");
     TRY(ctx_use(ctx));
     CU(cudaStreamSynchronize(ctx->stream));
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_cuda_timer_start(emsar_ctx *ctx)
+{
+    CHECK_ARG(ctx, "emsar_cuda_timer_start: NULL ctx");
+    TRY(ctx_use(ctx));
+    CU(cudaEventRecord(ctx->tev0, ctx->stream));
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_cuda_timer_stop(emsar_ctx *ctx, double *elapsed_ms)
+{
+    CHECK_ARG(ctx && elapsed_ms, "emsar_cuda_timer_stop: NULL argument");
+    TRY(ctx_use(ctx));
+    CU(cudaEventRecord(ctx->tev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->tev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->tev0, ctx->tev1));
+    *elapsed_ms = ms;
     return EMSAR_OK;
 }
 

@@ -74,6 +74,7 @@ struct emsar_ctx {
     void *d_scratch;          // CUB temp storage (grow-only)
     size_t scratch_bytes;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t tev0, tev1;   // emsar_cuda_timer_start / _stop
     size_t l2_persist_bytes;
     // multi-GPU (class-sharded samples): NCCL communicator loaded at run time
     void *nccl_comm;

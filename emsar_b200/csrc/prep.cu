@@ -118,6 +118,38 @@ static int launch_adjeuma_stream(emsar_sample *s, cudaStream_t st)
     return EMSAR_OK;
 }
 
+static int launch_adjeuma(emsar_sample *s, cudaStream_t st)
+{
+    emsar_index *ix = s->index;
+    if (ix->nF >= 16 && ix->nF % 4 == 0 && !getenv("EMSAR_ADJEUMA_SIMPLE")) {
+        // 128 rows x 32 columns x 3 stages = 54 KB per CTA -> 4 CTAs (512 row sums in flight) per SM: the best of the
+        // {64,128,256} x {16,32,64,128} x {2,3,4} sweep (profiles/r1i_adjeuma.txt); fewer resident rows starve the fp64 add chains
+        TRY((launch_adjeuma_stream<128, 32, 3>(s, st)));
+    } else {
+        k_adjeuma<<<(unsigned)((ix->C + ADJ_ROWS - 1) / ADJ_ROWS), ADJ_ROWS, 0, st>>>(ix->C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
+    }
+    LAUNCHED(s->ctx);
+    CU(cudaGetLastError());
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_sample_time_adjeuma(emsar_sample *s, int32_t reps, double *ms_per_launch)
+{
+    CHECK_ARG(s && ms_per_launch && reps > 0, "emsar_sample_time_adjeuma: bad argument");
+    if (!s->prepared) { emsar_set_err("emsar_sample_time_adjeuma: sample not prepared"); return EMSAR_ERR_STATE; }
+    emsar_ctx *ctx = s->ctx;
+    TRY(ctx_use(ctx));
+    TRY(launch_adjeuma(s, ctx->stream));                 // warm-up
+    CU(cudaEventRecord(ctx->tev0, ctx->stream));
+    for (int i = 0; i < reps; i++) TRY(launch_adjeuma(s, ctx->stream));
+    CU(cudaEventRecord(ctx->tev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->tev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->tev0, ctx->tev1));
+    *ms_per_launch = (double)ms / reps;
+    return EMSAR_OK;
+}
+
 // EUMAps, modelled / active flags.  nscale = (double)N / 1e6, p10 = pow(10, DELTA) (both formed on the host exactly
 // as construct_EUMAps does).
 __global__ void k_class_model(int64_t C, int32_t T, const double *__restrict__ adj, const uint8_t *__restrict__ in_model,
@@ -705,15 +737,7 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     long long *d_N = (long long *)(s->d_Wf + ix->nF);
     k_wf<<<1, 32, 0, st>>>(s->d_hist, ix->frag_min, ix->nF, ix->max_fl, s->d_Wf, d_N);
     LAUNCHED(ctx);
-    if (ix->nF >= 16 && ix->nF % 4 == 0 && !getenv("EMSAR_ADJEUMA_SIMPLE")) {
-        // 128 rows x 32 columns x 3 stages = 54 KB per CTA -> 4 CTAs (512 row sums in flight) per SM: the best of the
-        // {64,128,256} x {16,32,64,128} x {2,3,4} sweep (profiles/r1i_adjeuma.txt); fewer resident rows starve the fp64 add chains
-        TRY((launch_adjeuma_stream<128, 32, 3>(s, st)));
-    } else {
-        k_adjeuma<<<(unsigned)((C + ADJ_ROWS - 1) / ADJ_ROWS), ADJ_ROWS, 0, st>>>(C, ix->nF, ix->d_euma, ix->d_has_node, s->d_Wf, s->d_adj);
-    }
-    LAUNCHED(ctx);
-    CU(cudaGetLastError());
+    TRY(launch_adjeuma(s, st));
     long long N = 0;
     CU(cudaMemcpyAsync(&N, d_N, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1207,6 +1231,8 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     ms_.all_local = m.all_local; ms_.halo_rows = n_ue; ms_.halo_classes = n_um;
     ms_.resident_index_bytes = 4 * resident_ints;
     ms_.index_bytes = 4 * ((int64_t)e_ints + C_a + (int64_t)m_ints);
+    // fused class-sharded kernel: partial row sums pushed to the slice owners + the new theta of this rank's slice pushed to every rank (16-byte slots)
+    ms_.peer_bytes_per_iter = s->sharded ? (int64_t)(32.0 * P * (ctx->nranks - 1) / ctx->nranks) : 0;
     ms_.e_tiles = n_etiles; ms_.m_tiles = n_mitems;
     ms_.bytes_per_iter = 8 * m.nnz_a + 24 * C_a + 44 * (int64_t)T;
     // what the kernel streams per iteration: E: encoded members (padded) + R (+ q to global for halo classes);

@@ -213,6 +213,7 @@ typedef struct {
     int64_t halo_rows, halo_classes;   /* distinct (CTA, remote row) / (CTA, remote class) references */
     int64_t resident_index_bytes;      /* index data kept in shared memory for the whole kernel, summed over the CTAs */
     int64_t index_bytes;               /* packed index data of the model (E members + read counts + M entries, with padding) */
+    int64_t peer_bytes_per_iter;       /* class-sharded sample: bytes this rank writes into other GPUs' memory per iteration (0 otherwise) */
 } emsar_model_stats;
 /* Wf, adjEUMA, EUMAps, sets/EUMAcut, A_t, iEUMA and the packed active model; theta := start point */
 int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opts);
@@ -222,6 +223,13 @@ int emsar_sample_model_stats(emsar_sample *s, emsar_model_stats *st);
 int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
                         int32_t *iters_done, double *final_delta, double *elapsed_ms);
 int emsar_sample_theta_get(emsar_sample *s, double *theta);
+/* Measurement helpers (bench.py): CUDA events on the context's own stream around whatever the caller enqueues in between
+ * (torch.cuda.Event only sees torch's stream). emsar_cuda_timer_stop synchronizes and returns the milliseconds since _start. */
+int emsar_cuda_timer_start(emsar_ctx *ctx);
+int emsar_cuda_timer_stop(emsar_ctx *ctx, double *elapsed_ms);
+/* re-runs the adjEUMA kernel of a prepared sample `reps` times (same inputs, same outputs) and returns the mean duration of one
+ * launch: the HBM-bound one-off of a PE index (4 * C * nF bytes) */
+int emsar_sample_time_adjeuma(emsar_sample *s, int32_t reps, double *ms_per_launch);
 int emsar_sample_finalize(emsar_sample *s, emsar_solve_out *out);
 
 #ifdef __cplusplus
