@@ -1,0 +1,389 @@
+// k_em_psum (EM variant 5): the class-owner-centric persistent EM kernel. Layout and the idea: psum.cuh.
+// One cooperative launch runs all iterations; nothing in it waits for the whole grid: a CTA depends only on the CTAs it exchanges rows
+// with, through tagged 16-byte slots, and the convergence measure of iteration i is read behind the E-phase of iteration i + 1 (theta has
+// not changed by then, so stopping there leaves exactly the state of iteration i - stopping rule and iteration count are the oracle's).
+// Replaces run_MLE_threads / MLE_range / MLE / Fp / lambdap (reference emsar_functions.c:2946-3126) like k_em_persistent does.
+#include "em_common.cuh"
+#include "psum.cuh"
+
+struct PsParams {
+    PsModel m;
+    double eps_abs, eps_rel;
+    int max_iter, stop_on_conv;
+    unsigned tag0;
+    int *abort_flag;
+    int *iters_done;
+    double *final_delta;
+    unsigned long long *trace;     // optional [B * 8] globaltimer stamps of the last iteration (tuning aid)
+};
+
+struct PsView {
+    double *theta, *q, *Q;
+    const unsigned char *cache;    // resident index cache (shared memory)
+    int nrows, ncls, hr0;
+};
+
+template <bool RES> __device__ __forceinline__ uint4 ps_ld128(const unsigned char *sm, const unsigned char *g, int off16)
+{
+    if (RES) return *(const uint4 *)(sm + 16 * (size_t)off16);
+    return __ldg((const uint4 *)g + off16);
+}
+template <bool RES> __device__ __forceinline__ uint2 ps_ld64(const unsigned char *sm, const unsigned char *g, int off8)
+{
+    if (RES) return *(const uint2 *)(sm + 8 * (size_t)off8);
+    return __ldg((const uint2 *)g + off8);
+}
+template <bool RES> __device__ __forceinline__ uint32_t ps_ld32(const unsigned char *sm, const unsigned char *g, int off4)
+{
+    if (RES) return *(const uint32_t *)(sm + 4 * (size_t)off4);
+    return __ldg((const uint32_t *)g + off4);
+}
+
+__device__ __forceinline__ double ps_q_of(uint32_t r, double s) { return s > 0 ? fast_div((double)r, s) : 0.0; }
+
+// ---- E-phase: one tile ----------------------------------------------------------------------------------------------------------------
+template <bool RES>
+__device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const unsigned char *gdat, const uint32_t *gR, int lane)
+{
+    const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf;
+    const int off16 = t.z;
+    const double *th = v.theta;
+    if (lg == 0 && steps <= 4) {
+        const uint4 w = ps_ld128<RES>(v.cache, gdat, off16 + lane);
+        // read counts: behind the 512 bytes of index data in a resident copy, in the compact class array otherwise
+        const int r4 = off16 * 4 + 128;
+        if (steps == 2) {
+            const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], b0 = th[w.y & 0xffffu], b1 = th[w.y >> 16];
+            const double c0 = th[w.z & 0xffffu], c1 = th[w.z >> 16], d0 = th[w.w & 0xffffu], d1 = th[w.w >> 16];
+            const double s[4] = {a0 + a1, b0 + b1, c0 + c1, d0 + d1};
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int c = g * 32 + lane;
+                if (c < t.y) {
+                    const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c) : __ldg(gR + t.x + c);
+                    v.q[t.x + c] = ps_q_of(r, s[g]);
+                }
+            }
+        } else {
+            const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], a2 = th[w.y & 0xffffu], a3 = th[w.y >> 16];
+            const double b0 = th[w.z & 0xffffu], b1 = th[w.z >> 16], b2 = th[w.w & 0xffffu], b3 = th[w.w >> 16];
+            double s0 = a0; s0 += a1; s0 += a2; s0 += a3;           // sequential member order (the pad slot holds 0.0)
+            double s1 = b0; s1 += b1; s1 += b2; s1 += b3;
+            if (lane < t.y) {
+                const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + lane) : __ldg(gR + t.x + lane);
+                v.q[t.x + lane] = ps_q_of(r, s0);
+            }
+            if (32 + lane < t.y) {
+                const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + 32 + lane) : __ldg(gR + t.x + 32 + lane);
+                v.q[t.x + 32 + lane] = ps_q_of(r, s1);
+            }
+        }
+        return;
+    }
+    // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
+    const int steps4 = (steps + 3) >> 2;
+    const int o8 = off16 * 2 + lane;
+    double s = 0;
+    int c = 0;
+    for (; c + 2 <= steps4; c += 2) {
+        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
+        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
+        const double x4 = th[w1.x & 0xffffu], x5 = th[w1.x >> 16], x6 = th[w1.y & 0xffffu], x7 = th[w1.y >> 16];
+        s += x0; s += x1; s += x2; s += x3; s += x4; s += x5; s += x6; s += x7;
+    }
+    if (c < steps4) {
+        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
+        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
+        s += x0; s += x1; s += x2; s += x3;
+    }
+    const int G = 1 << lg, cls = lane >> lg;
+    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((lane & (G - 1)) == 0 && cls < t.y) {
+        const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + cls) : __ldg(gR + t.x + cls);
+        v.q[t.x + cls] = ps_q_of(r, s);
+    }
+}
+
+// ---- M-phase: one item (partial row sums over the CTA's own classes) ------------------------------------------------------------------------
+__device__ __forceinline__ void ps_emit(const PsParams &p, const PsView &v, unsigned slot, double S, unsigned tag)
+{
+    if ((int)slot < v.nrows) v.Q[slot] = S;
+    else ll_store(p.m.part_slots + 16 * (size_t)__ldg(p.m.halo_tgt + v.hr0 + ((int)slot - v.nrows)), S, tag);
+}
+
+template <bool RES>
+__device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, const int4 t, const unsigned char *gdat, int lane, unsigned tag)
+{
+    const int len = t.w & 0x1fffffff;
+    const int off16 = t.z;
+    const double *q = v.q;
+    if (((t.w >> 30) & 1) == 0) {
+        const uint32_t hw = ps_ld32<RES>(v.cache, gdat, off16 * 4 + (lane >> 1));
+        const unsigned slot = (lane & 1) ? (hw >> 16) : (hw & 0xffffu);
+        const int len4 = (len + 3) >> 2;
+        const int o8 = off16 * 2 + 8 + lane;
+        double S = 0;
+        int c = 0;
+        for (; c + 2 <= len4; c += 2) {
+            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
+            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
+            const double x4 = q[w1.x & 0xffffu], x5 = q[w1.x >> 16], x6 = q[w1.y & 0xffffu], x7 = q[w1.y >> 16];
+            S += x0; S += x1; S += x2; S += x3; S += x4; S += x5; S += x6; S += x7;      // ascending class order
+        }
+        if (c < len4) {
+            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
+            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
+            S += x0; S += x1; S += x2; S += x3;
+        }
+        if (slot != 0xffffu) ps_emit(p, v, slot, S, tag);
+    } else {
+        // a group of long rows: the warp reduces one row at a time (lane-strided partial sums, fixed shuffle tree), lane r keeps row r's sum
+        const int n = t.y;
+        const uint32_t hw = lane < n ? ps_ld32<RES>(v.cache, gdat, off16 * 4 + lane) : 0u;
+        const int mywords = (int)(((hw >> 16) + 1) >> 1);
+        int start = mywords;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
+        start += ((n + 3) & ~3) - mywords;                 // exclusive prefix (32-bit words), behind the header
+        double mine = 0;
+        for (int r = 0; r < n; r++) {
+            const int a = off16 * 4 + __shfl_sync(0xffffffffu, start, r), W = __shfl_sync(0xffffffffu, mywords, r);
+            double s = 0;
+            int e = lane;
+            for (; e + 32 < W; e += 64) {
+                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e), w1 = ps_ld32<RES>(v.cache, gdat, a + e + 32);
+                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16], x2 = q[w1 & 0xffffu], x3 = q[w1 >> 16];
+                s += x0; s += x1; s += x2; s += x3;
+            }
+            if (e < W) {
+                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e);
+                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16];
+                s += x0; s += x1;
+            }
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
+            if (lane == r) mine = s;
+        }
+        if (lane < n) ps_emit(p, v, hw & 0xffffu, mine, tag);
+    }
+}
+
+#define PS_TRACE(slot) do { if (p.trace && it == p.max_iter - 1 && threadIdx.x == 0) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+
+__global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    __shared__ double sm_red[EM_WARPS];
+    __shared__ double sm_bc;
+    __shared__ int sm_ctr[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = (int)blockIdx.x + p.m.block0;
+    const int row0 = p.m.blk_row0[b], nrows = p.m.blk_row0[b + 1] - row0;
+    const int cls0 = p.m.blk_cls0[b], ncls = p.m.blk_cls0[b + 1] - cls0;
+    const int et0 = p.m.blk_etile0[b], n_et = p.m.blk_etile0[b + 1] - et0;
+    const int mi0 = p.m.blk_mitem0[b], n_mi = p.m.blk_mitem0[b + 1] - mi0;
+    const int hr0 = p.m.blk_hr0[b], nhr = p.m.blk_hr0[b + 1] - hr0;
+    const int desc_smem = p.m.blk_desc_smem[b];
+    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls);
+    PsView v;
+    v.theta = (double *)(sm_dyn + pl.off_theta);
+    v.q = (double *)(sm_dyn + pl.off_q);
+    v.Q = (double *)(sm_dyn + pl.off_Q);
+    v.cache = sm_dyn + pl.off_cache;
+    v.nrows = nrows; v.ncls = ncls; v.hr0 = hr0;
+    const int4 *et = desc_smem ? (const int4 *)(sm_dyn + pl.off_et) : p.m.e_tiles + et0;
+    const int4 *mi = desc_smem ? (const int4 *)(sm_dyn + pl.off_mi) : p.m.m_items + mi0;
+    if (desc_smem) {
+        int4 *s_et = (int4 *)(sm_dyn + pl.off_et), *s_mi = (int4 *)(sm_dyn + pl.off_mi);
+        for (int i = threadIdx.x; i < n_et; i += EM_BLOCK) s_et[i] = p.m.e_tiles[et0 + i];
+        for (int i = threadIdx.x; i < n_mi; i += EM_BLOCK) s_mi[i] = p.m.m_items[mi0 + i];
+    }
+    for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) { v.theta[i] = p.m.theta[row0 + i]; v.Q[i] = 0.0; }
+    for (int i = threadIdx.x; i <= ncls; i += EM_BLOCK) v.q[i] = 0.0;             // q[ncls] = 0.0: padding target of the M items
+    if (threadIdx.x == 0) v.theta[nrows + nhr] = 0.0;                             // zero-theta slot: padding target of the E tiles
+    {
+        // resident index cache: the data of the chosen tiles (+ their read counts) and items stays in shared memory for the whole kernel
+        unsigned char *cache = sm_dyn + pl.off_cache;
+        for (int i = warp; i < n_et; i += EM_WARPS) {
+            const int4 t = p.m.e_tiles[et0 + i];
+            if (!((t.w >> 30) & 1)) continue;
+            const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf;
+            const int n16 = (lg == 0 && steps <= 4) ? 32 : 16 * ((steps + 3) >> 2);
+            const uint4 *src = (const uint4 *)p.m.e_data + p.m.e_src[et0 + i];
+            uint4 *dst = (uint4 *)cache + t.z;
+            for (int j = lane; j < n16; j += 32) dst[j] = __ldg(src + j);
+            uint32_t *rd = (uint32_t *)(dst + n16);
+            for (int j = lane; j < t.y; j += 32) rd[j] = __ldg(p.m.e_R + cls0 + t.x + j);
+        }
+        for (int i = warp; i < n_mi; i += EM_WARPS) {
+            const int4 t = p.m.m_items[mi0 + i];
+            if (!((t.w >> 29) & 1)) continue;
+            const int n16 = t.x;                    // an item's x carries its size in 16-byte units
+            const uint4 *src = (const uint4 *)p.m.m_data + p.m.m_src[mi0 + i];
+            uint4 *dst = (uint4 *)cache + t.z;
+            for (int j = lane; j < n16; j += 32) dst[j] = __ldg(src + j);
+        }
+    }
+    __syncthreads();
+    const uint32_t *gR = p.m.e_R + cls0;
+    const int Bt = p.m.Bt;
+    // the convergence measure of iteration j: the maximum over every CTA (slots alternate by iteration parity)
+    auto read_dm = [&](int j) -> double {
+        const unsigned tg = p.tag0 + (unsigned)j + 1u;
+        double x = 0;
+        for (int i = threadIdx.x; i < Bt; i += EM_BLOCK) x = fmax(x, ll_load(p.m.dm_slots + 16 * (size_t)((j & 1) * Bt + i), tg, p.abort_flag));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) sm_red[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            double y = sm_red[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) y = fmax(y, __shfl_xor_sync(0xffffffffu, y, o));
+            if (lane == 0) sm_bc = y;
+        }
+        __syncthreads();
+        return sm_bc;
+    };
+    int it = 0;
+    double d = INFINITY;
+    bool stopped = false;
+    while (it < p.max_iter) {
+        const unsigned tag = p.tag0 + (unsigned)it + 1u;
+        PS_TRACE(0);
+        // theta of the halo rows, as their owners published it
+        for (int i = threadIdx.x; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(p.m.th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
+        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
+        __syncthreads();
+        PS_TRACE(1);
+        for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+            const int4 t = et[n_et - 1 - tk];                   // tiles are ordered by cardinality: heaviest first
+            if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
+            else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
+        }
+        PS_TRACE(2);
+        if (it > 0) {
+            d = read_dm(it - 1);
+            if (*((volatile int *)p.abort_flag) != 0 || (p.stop_on_conv && d <= 1.0)) { stopped = true; break; }
+        } else __syncthreads();
+        for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+            const int4 t = mi[tk];                              // items are ordered longest first
+            if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
+            else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
+        }
+        __syncthreads();
+        PS_TRACE(3);
+        // owner update: own partial sum + the contributions of the other CTAs, in CTA order
+        double dm = 0;
+        for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) {
+            double Q = v.Q[i];
+            const int e0 = __ldg(p.m.inc_off + row0 + i), e1 = __ldg(p.m.inc_off + row0 + i + 1);
+            for (int e = e0; e < e1; e++) Q += ll_load(p.m.part_slots + 16 * (size_t)e, tag, p.abort_flag);
+            const double2 ra = __ldg(p.m.row_RsA + row0 + i);
+            const double th = v.theta[i];
+            const double n = ra.x + th * Q;
+            const double thn = fast_div(n, ra.y);
+            v.theta[i] = thn;
+            if (e1 > e0) ll_store(p.m.th_slots + 16 * (size_t)(row0 + i), thn, tag + 1u);       // its readers are exactly its contributors
+            dm = fmax(dm, fast_div(fabs(thn - th) * ra.y, p.eps_abs + p.eps_rel * n));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        if (lane == 0) sm_red[warp] = dm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bm = 0;
+            for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
+            ll_store(p.m.dm_slots + 16 * (size_t)((it & 1) * Bt + b), bm, tag);
+        }
+        __syncthreads();                                         // sm_red is reused by read_dm
+        PS_TRACE(4);
+        it++;
+    }
+    if (it > 0 && !stopped) d = read_dm(it - 1);
+    if (*((volatile int *)p.abort_flag) != 0) d = INFINITY;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) p.m.theta[row0 + i] = v.theta[i];      // the copy the output kernels read
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *p.iters_done = it; *p.final_delta = d; }
+}
+
+__global__ void k_ps_theta_to_slots(int32_t P, const double *__restrict__ theta, unsigned char *__restrict__ th_slots, unsigned tag)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) ll_store(th_slots + 16 * (size_t)p, theta[p], tag);
+}
+
+int em_psum_attr(emsar_ctx *ctx)
+{
+    CU(cudaFuncSetAttribute(k_em_psum, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_psum, EM_BLOCK, ctx->em_smem_bytes));
+    if (nb < 1) { emsar_set_err("k_em_psum does not fit on an SM (%d bytes of shared memory)", ctx->em_smem_bytes); return EMSAR_ERR_CUDA; }
+    return EMSAR_OK;
+}
+
+int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out)
+{
+    emsar_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    PsParams p;
+    p.m = s->ps;
+    p.eps_abs = s->opts.eps_abs; p.eps_rel = s->opts.eps_rel;
+    p.max_iter = max_iter; p.stop_on_conv = stop_on_conv;
+    p.iters_done = (int *)(ctx->d_barrier + 8);
+    p.final_delta = (double *)(ctx->d_barrier + 10);
+    p.abort_flag = (int *)(ctx->d_barrier + 14);
+    p.trace = s->d_trace;
+    // scalars + the convergence slots (their tags restart with every sample, so they are cleared at every launch)
+    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256, st));
+    CU(cudaMemsetAsync(s->ps.dm_slots, 0, 2 * (size_t)s->ps.Bt * 16, st));
+    if ((unsigned)(s->slot_tag + (unsigned)max_iter + 4u) < s->slot_tag) {              // tag wrap: start over from clean slots
+        CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
+        s->slot_tag = 0;
+    }
+    p.tag0 = s->slot_tag;
+    s->slot_tag += (unsigned)max_iter + 2u;
+    if (s->ps.P > 0) { k_ps_theta_to_slots<<<(s->ps.P + 255) / 256, 256, 0, st>>>(s->ps.P, s->ps.theta, s->ps.th_slots, p.tag0 + 1u); LAUNCHED(ctx); }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)s->ps.B);
+    cfg.blockDim = dim3(EM_BLOCK);
+    cfg.dynamicSmemBytes = (size_t)ctx->em_smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeCooperative;       // co-residency of all CTAs: they wait for each other's slots
+    attrs[na].val.cooperative = 1;
+    na++;
+    if (ctx->l2_persist_bytes > 0 && s->slots_bytes > 0) {
+        // the exchange slots (theta of shared rows, partial sums) stay resident in L2 while the index streams through
+        size_t win = s->slots_bytes;
+        if (win > (size_t)ctx->prop.accessPolicyMaxWindowSize) win = (size_t)ctx->prop.accessPolicyMaxWindowSize;
+        attrs[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        attrs[na].val.accessPolicyWindow.base_ptr = s->d_slots;
+        attrs[na].val.accessPolicyWindow.num_bytes = win;
+        attrs[na].val.accessPolicyWindow.hitRatio = win <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)win;
+        attrs[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attrs[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na++;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    CU(cudaFuncSetAttribute(k_em_psum, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));    // per device, and other contexts may have changed it
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(cudaLaunchKernelEx(&cfg, k_em_psum, p));
+    LAUNCHED(ctx);
+    CU(cudaEventRecord(ctx->ev1, st));
+    int it = 0, aborted = 0; double fd = 0;
+    CU(cudaMemcpyAsync(&it, p.iters_done, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&fd, p.final_delta, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&aborted, p.abort_flag, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (aborted) { emsar_set_err("k_em_psum: a wait on a tagged slot timed out (internal error)"); return EMSAR_ERR_STATE; }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (iters_done) *iters_done = it;
+    if (final_delta) *final_delta = fd;
+    if (ms_out) *ms_out = ms;
+    return EMSAR_OK;
+}

@@ -1,0 +1,72 @@
+// k_em_psum: the class-owner-centric EM kernel (variant 5). Data layout shared by the packer (prep_psum.cu) and the kernel (em_psum.cu).
+//
+// Ownership: the participating rows, in the index's locality order, are cut into one contiguous range per CTA (= per SM); a class belongs
+// to the CTA that owns its MEDIAN member, so the classes of a wide module spread over the CTAs that hold its rows. A CTA keeps in SHARED
+// MEMORY, for the whole kernel: theta of its rows and of every other row its classes touch ("halo rows"), q of its classes, and the partial
+// row sums it is about to hand over. Both phases then run over the CTA's own classes only:
+//   E      q_c = R_c / sum_{t in c} theta_t                                  class-major tiles, gathers from shared memory
+//   M      S_t^(b) = sum_{c owned by b, c contains t} q_c                      row-major over the same members, gathers from shared memory
+//   U      theta_t' = (Rs_t + theta_t * sum_b S_t^(b)) / A_t                   by the row's owner, contributions added in CTA order
+// Across CTAs only per-row values travel, through tagged 16-byte slots (ll_store / ll_load): theta_t to the CTAs whose classes contain t,
+// and S_t^(b) back to the owner of t. q never leaves its CTA, a hub row costs its owner one slot per contributing CTA, and a class of 999
+// members costs its owner 999 shared-memory gathers. Every index is a 16-bit shared-memory slot.
+#pragma once
+#include "common.cuh"
+
+constexpr int PS_MAX_SLOT = 65534;         // 0xFFFF marks an unused lane of an M slice
+
+// ---- E side -------------------------------------------------------------------------------------------------------------------------
+// cardinality 2: a tile holds 128 classes, lane l carries classes l, 32 + l, 64 + l, 96 + l as 4 x (2 u16) = 16 bytes;
+// cardinality 3, 4: 64 classes, lane l carries classes l, 32 + l as 2 x (4 u16) = 16 bytes (the 4th entry of a 3-member class is the zero slot);
+// otherwise G = 1 << e_lgG(k) lanes share a class (32 / G classes per tile) and a lane's members come in chunks of 4 u16 (8 bytes):
+// chunk c of all 32 lanes is one 256-byte block. Entries beyond the cardinality point at the zero-theta slot.
+__host__ __device__ __forceinline__ int ps_steps4(int k) { return (e_steps(k) + 3) >> 2; }
+__host__ __device__ __forceinline__ int ps_tile_u16(int k) { return k <= 4 ? 256 : 128 * ps_steps4(k); }      // 16-bit words of index data per tile
+// a resident copy of a tile (shared memory) carries its read counts right behind the index data
+
+// ---- M side -------------------------------------------------------------------------------------------------------------------------
+// The rows a CTA's classes touch (own rows and halo rows), sorted by their number of local entries, longest first.
+// rows with more than M_LONG entries: groups of <= M_GROUP_ROWS rows, one warp per group: header = one 32-bit word {slot, length} per row
+// (padded to 16 bytes), then the rows' entries back to back, each row padded to an even number of entries;
+// the rest: slices of 32 rows: header = 32 u16 row slots (0xFFFF = unused lane), then chunks of 4 entries per lane (chunk c of all lanes = 256
+// bytes), padded with the zero-q slot up to the longest row of the slice.
+__host__ __device__ __forceinline__ int ps_slice_u16(int len) { return 32 + 128 * ((len + 3) >> 2); }
+__host__ __device__ __forceinline__ int ps_group_hdr_u16(int rows) { return ((rows + 3) & ~3) * 2; }
+
+struct PsModel {
+    int32_t P, B, block0;          // rows; CTAs of this launch; first virtual CTA of this device (0 on a single GPU)
+    int64_t C_a, nnz_a;
+    int32_t *blk_row0, *blk_cls0, *blk_etile0, *blk_mitem0, *blk_hr0;     // [Bt + 1] per virtual CTA
+    int32_t *blk_desc_smem;        // [Bt] 1: the CTA keeps its tile / item descriptors in shared memory
+    int4 *e_tiles;                 // {first local class, classes, data offset (16-byte units; bit 30 of w set: offset inside the CTA's resident cache), steps | lgG << 12 | resident << 30}
+    int4 *m_items;                 // {-, rows, data offset (as above), length | resident << 29 | group << 30}
+    int32_t *e_src, *m_src;        // global data offset of every tile / item (the resident cache is filled from it)
+    int32_t *blk_res16;            // [Bt] 16-byte units of the CTA's resident cache
+    const unsigned char *e_data, *m_data;
+    const uint32_t *e_R;           // [C_a] read counts in compact class order
+    int32_t *halo_rows;            // [n_inc] global row of every halo slot, grouped by CTA (blk_hr0)
+    int32_t *halo_tgt;             // [n_inc] partial-sum slot the CTA's contribution to that row goes to
+    int32_t *inc_off;              // [P + 1] partial-sum slots of row p: inc_off[p] .. inc_off[p + 1], ordered by contributing CTA
+    double2 *row_RsA;              // [P] {Rs, A}
+    double *theta;                 // [P]
+    unsigned char *th_slots;       // [P + 1] tagged slots: theta of every row that some other CTA reads
+    unsigned char *part_slots;     // [n_inc + 1] tagged slots: partial row sums
+    unsigned char *dm_slots;       // [2 * Bt] tagged slots: convergence measure per CTA, alternating by iteration parity
+    int32_t Bt;                    // virtual CTAs over all devices (= B on a single GPU)
+    int32_t n_inc;
+    int32_t smem_bytes;
+};
+
+struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_cache, total; };
+__host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls)
+{
+    PsPlan p;
+    p.off_et = 0;
+    p.off_mi = p.off_et + (desc_smem ? n_et * 16 : 0);
+    p.off_theta = p.off_mi + (desc_smem ? n_mi * 16 : 0);
+    p.off_q = p.off_theta + (((nrows + nhr + 1) * 8 + 15) & ~15);
+    p.off_Q = p.off_q + (((ncls + 1) * 8 + 15) & ~15);
+    p.off_cache = p.off_Q + ((nrows * 8 + 15) & ~15);
+    p.total = p.off_cache;
+    return p;
+}
