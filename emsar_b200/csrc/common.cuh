@@ -171,6 +171,8 @@ struct EmModel {
     double *q;             // [C_a]
 };
 
+#include "psum_model.cuh"
+
 struct emsar_sample {
     emsar_index *index;
     emsar_ctx *ctx;
@@ -215,6 +217,10 @@ struct emsar_sample {
     double *d_qpart;       // sharded mode, NCCL path: [2*P] partial / reduced per-row sums in natural order
     bool sharded;
     EmModel m;
+    // class-owner-centric model of k_em_psum (psum.cuh): used instead of `m` whenever the sample is eligible
+    bool use_psum;
+    PsModel ps;
+    std::vector<void *> ps_allocs;
     emsar_model_stats stats;
     // solve bookkeeping
     int32_t n_iter;
@@ -241,6 +247,8 @@ template <class T> static inline int dev_alloc(T **p, size_t n)
 
 int index_build_hash(emsar_index *ix, const std::vector<uint8_t> &insertable);
 int sample_build_model(emsar_sample *s);
+int em_psum_attr(emsar_ctx *ctx);
+int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out);
 int em_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms, bool fused = false);
 int em_query_occupancy(emsar_ctx *ctx);
 int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);

@@ -966,6 +966,7 @@ int em_query_occupancy(emsar_ctx *ctx)
     if (nb < 1) { emsar_set_err("EM kernel does not fit on an SM (%d bytes of shared memory)", smem); return EMSAR_ERR_CUDA; }
     ctx->em_blocks_per_sm = 1;
     ctx->em_smem_bytes = smem;
+    TRY(em_psum_attr(ctx));
     return EMSAR_OK;
 }
 
@@ -1100,7 +1101,7 @@ extern "C" int emsar_debug_em_trace(emsar_sample *s, int iters, unsigned long lo
 {
     if (!s || !s->prepared) return EMSAR_ERR_STATE;
     TRY(ctx_use(s->ctx));
-    const int B = s->m.B;
+    const int B = s->use_psum ? s->ps.B : s->m.B;
     TRY(dev_alloc(&s->d_trace, (size_t)B * 8 + 64 + 1600));
     CU(cudaMemsetAsync(s->d_trace, 0, (size_t)B * 64 + 512 + 12800, s->ctx->stream));
     int it = 0; double fd = 0, ms = 0;
@@ -1213,7 +1214,8 @@ extern "C" int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t st
     }
     if (max_iter <= 0) max_iter = s->opts.max_iter;
     int it = 0; double fd = 0, ms = 0;
-    if (s->sharded) TRY(em_run_sharded(s, max_iter, stop_on_conv, &it, &fd, &ms));
+    if (s->use_psum) TRY(em_psum_launch(s, max_iter, stop_on_conv, &it, &fd, &ms));
+    else if (s->sharded) TRY(em_run_sharded(s, max_iter, stop_on_conv, &it, &fd, &ms));
     else TRY(em_launch(s, max_iter, stop_on_conv, &it, &fd, &ms, false));
     s->n_iter += it; s->final_delta = fd; s->em_ms += ms;
     if (iters_done) *iters_done = it;
@@ -1450,6 +1452,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     dev_free(s->d_rd_ptr); dev_free(s->d_rd_tid); dev_free(s->d_rd_fl);
     dev_free(s->d_Wf); dev_free(s->d_adj); dev_free(s->d_amodel); dev_free(s->d_in_model);
     dev_free(s->d_A); dev_free(s->d_Rs); dev_free(s->d_iE); dev_free(s->d_lone); dev_free(s->d_pos);
+    for (void *q : s->ps_allocs) dev_free(q);
     dev_free(s->d_state); dev_free(s->d_pack); dev_free(s->d_mcls); dev_free(s->d_halo); dev_free(s->d_chunks); dev_free(s->d_qpart); dev_free(s->d_slots);
     delete s;
     return EMSAR_OK;

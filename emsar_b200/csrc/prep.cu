@@ -11,6 +11,7 @@
 #include <numeric>
 
 #include "common.cuh"
+#include "psum.cuh"
 
 int sample_check_flags(emsar_sample *s);
 
@@ -260,6 +261,7 @@ __global__ void k_class_owner(int64_t n_multi, int32_t T, const uint32_t *__rest
     if (i >= n_multi || !act[i]) return;
     const uint32_t o = cls_off[T + i], e = cls_off[T + i + 1];
     int best = cls_tid[o];
+    if (rule == 2) best = cls_tid[o + ((e - o) >> 1)];          // the median member: the classes of a wide module spread over the CTAs that hold its rows
     if (rule == 1) {
         int bd = deg[best];
         for (uint32_t j = o + 1; j < e; j++) { const int u = cls_tid[j], d = deg[u]; if (d < bd) { bd = d; best = u; } }
@@ -269,18 +271,18 @@ __global__ void k_class_owner(int64_t n_multi, int32_t T, const uint32_t *__rest
 
 // E-phase cost lands on the row that owns the class
 __global__ void k_class_cost(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ owner,
-                             const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost, int per_class)
+                             const int32_t *__restrict__ act, const uint32_t *__restrict__ nat, int32_t *__restrict__ ecost, int per_class, int per_member)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_multi || !act[i]) return;
-    atomicAdd(&ecost[nat[owner[i]]], (int)(cls_off[T + i + 1] - cls_off[T + i]) + per_class);       // gathers + the class's own work (divide, store)
+    atomicAdd(&ecost[nat[owner[i]]], per_member * (int)(cls_off[T + i + 1] - cls_off[T + i]) + per_class);       // gathers + the class's own work (divide, store)
 }
 
-__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost, int per_row)
+__global__ void k_row_cost(int32_t P, const uint32_t *__restrict__ degn, const int32_t *__restrict__ ecost, uint32_t *__restrict__ cost, int per_row, int per_entry)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > P) return;
-    cost[p] = p < P ? degn[p] + (uint32_t)ecost[p] + (uint32_t)per_row : 0u;
+    cost[p] = p < P ? (uint32_t)per_entry * degn[p] + (uint32_t)ecost[p] + (uint32_t)per_row : 0u;
 }
 
 // cut the rows (natural order) into B ranges of equal cost
@@ -699,6 +701,8 @@ template <class T> static T *arena_take(char *&cur, size_t n)
     return p;
 }
 
+#include "prep_psum.inl"
+
 extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opts_in)
 {
     CHECK_ARG(s, "emsar_sample_prepare: NULL sample");
@@ -883,6 +887,28 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.smem_bytes = ctx->em_smem_bytes;
     m.theta = s->d_state;
     m.q = (double *)((char *)s->d_state + theta_bytes);
+    // ---- the class-owner-centric model (k_em_psum) whenever the sample is eligible; EMSAR_EM_MODE=legacy|barrier|pipe keeps the older kernels ----
+    {
+        const char *em_mode_ = getenv("EMSAR_EM_MODE");
+        const bool want_psum = !s->sharded && (!em_mode_ || !strcmp(em_mode_, "psum")) && !getenv("EMSAR_OWNER");
+        s->use_psum = false;
+        if (want_psum) {
+            PsPrepIn pin;
+            pin.T = T; pin.P = P; pin.nm = nm; pin.C_a = C_a; pin.n_kseg = n_kseg; pin.B = B; pin.d_cub = d_cub; pin.cub_bytes = cub_bytes;
+            pin.d_act = d_act; pin.d_newid = d_newid; pin.d_deg = d_deg; pin.d_rflag = d_rflag; pin.d_nat = d_nat; pin.d_pos = d_pos;
+            TRY(sample_build_psum(s, pin));
+            if (s->use_psum) {
+                CU(cudaEventRecord(e1, st));
+                CU(cudaStreamSynchronize(st));
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, e0, e1));
+                s->prep_ms = ms;
+                s->prepared = true;
+                s->n_iter = 0; s->final_delta = INFINITY; s->em_ms = 0;
+                return EMSAR_OK;
+            }
+        } else ps_free(s);
+    }
     // ---- arena part 1: everything whose size is known now ----
     // padding: a class is padded to steps*G members (< 1.25 k + 31), a cell to whole row blocks (< 32*steps ints per (CTA, cardinality) cell)
     const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)ix->nnz_multi / 4 + 32 * (size_t)nm + (size_t)n_cells * 32 * 64 + 64;
@@ -925,10 +951,10 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     LAUNCHED(ctx);
     if (nm > 0) {
         k_class_owner<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, d_act, d_deg, owner_rule, d_owner);
-        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_owner, d_act, d_nat, d_ecost, cost_class);
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_owner, d_act, d_nat, d_ecost, cost_class, 1);
         ctx->launches += 2;
     }
-    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost, cost_row);
+    k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost, cost_row, 1);
     LAUNCHED(ctx);
     CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cost, d_costp, P + 1, st));
     LAUNCHED(ctx);
