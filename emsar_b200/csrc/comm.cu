@@ -138,11 +138,13 @@ void comm_window_release(emsar_ctx *ctx)
     cudaGetLastError();
 }
 
-int comm_window_ensure(emsar_ctx *ctx, int64_t rows)
+// `min_bytes`: the window must hold at least this many bytes (k_em_psum lays its own slot arrays out in it); `rows`: capacity in rows of
+// the legacy fused kernel's layout. Collective: every rank passes the same numbers.
+int comm_window_ensure(emsar_ctx *ctx, int64_t rows, size_t min_bytes)
 {
     if (!ctx->nccl_comm) { emsar_set_err("no communicator: call emsar_comm_init first"); return EMSAR_ERR_STATE; }
     if (ctx->win_state == -1) return EMSAR_OK;
-    if (ctx->win_state == 1 && rows <= ctx->win_rows) return EMSAR_OK;
+    if (ctx->win_state == 1 && rows <= ctx->win_rows && min_bytes <= ctx->win_bytes) return EMSAR_OK;
     const char *mode = getenv("EMSAR_SHARD_MODE");
     if (mode && !strcmp(mode, "nccl")) { ctx->win_state = -1; return EMSAR_OK; }     // every rank reads the same environment
     const int R = ctx->nranks, me = ctx->rank;
@@ -152,7 +154,8 @@ int comm_window_ensure(emsar_ctx *ctx, int64_t rows)
     CU(cudaStreamSynchronize(st));
     comm_window_release(ctx);
     const int64_t cap = rows + (rows >> 3) + 1024;
-    const size_t bytes = WIN_HDR_BYTES + 32 * (size_t)cap + 16 * (size_t)(win_slice_rows(cap, R) * R + 64);       // dm | 2 x theta | xbuf
+    size_t bytes = WIN_HDR_BYTES + 32 * (size_t)cap + 16 * (size_t)(win_slice_rows(cap, R) * R + 64);       // dm | 2 x theta | xbuf
+    if (bytes < min_bytes + (min_bytes >> 3)) bytes = min_bytes + (min_bytes >> 3);
     ctx->win_bytes = bytes;
     WinInfo mine;
     memset(&mine, 0, sizeof(mine));

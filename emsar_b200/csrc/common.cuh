@@ -213,6 +213,7 @@ struct emsar_sample {
     unsigned long long *d_trace;   // tuning aid
     void *d_slots;         // barrier-free EM kernel: tagged 16-byte slots of theta [P+1] and q [C_a+1]
     size_t slots_bytes;
+    bool force_legacy;     // the psum model was not eligible for a sharded sample: pack the legacy one
     unsigned slot_tag;     // tags handed out so far (every launch takes a fresh range, so the slots are never cleared)
     double *d_qpart;       // sharded mode, NCCL path: [2*P] partial / reduced per-row sums in natural order
     bool sharded;
@@ -221,6 +222,7 @@ struct emsar_sample {
     bool use_psum;
     PsModel ps;
     std::vector<void *> ps_allocs;
+    int32_t ps_row_lo, ps_row_hi;  // class-sharded: the rows this rank's CTAs own
     emsar_model_stats stats;
     // solve bookkeeping
     int32_t n_iter;
@@ -255,7 +257,7 @@ int sample_finalize_device(emsar_sample *s, emsar_solve_out *out);
 int comm_allreduce_f64(emsar_ctx *ctx, const double *in, double *out, size_t n);
 int comm_allreduce_i32(emsar_ctx *ctx, int32_t *inout, size_t n);
 int comm_barrier(emsar_ctx *ctx);
-int comm_window_ensure(emsar_ctx *ctx, int64_t rows);      // collective; leaves ctx->win_state at 1 (peer memory) or -1
+int comm_window_ensure(emsar_ctx *ctx, int64_t rows, size_t min_bytes = 0);      // collective; leaves ctx->win_state at 1 (peer memory) or -1
 void comm_window_release(emsar_ctx *ctx);
 
 // ---- device helpers ------------------------------------------------------------------------------

@@ -108,7 +108,10 @@ __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const u
 __device__ __forceinline__ void ps_emit(const PsParams &p, const PsView &v, unsigned slot, double S, unsigned tag)
 {
     if ((int)slot < v.nrows) v.Q[slot] = S;
-    else ll_store(p.m.part_slots + 16 * (size_t)__ldg(p.m.halo_tgt + v.hr0 + ((int)slot - v.nrows)), S, tag);
+    else {
+        const unsigned tg = (unsigned)__ldg(p.m.halo_tgt + v.hr0 + ((int)slot - v.nrows));       // slot of the row's owner, in the owner's rank
+        ll_store(p.m.win[tg >> 28] + p.m.part_off + 16 * (size_t)(tg & 0x0fffffffu), S, tag);
+    }
 }
 
 template <bool RES>
@@ -227,11 +230,13 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     __syncthreads();
     const uint32_t *gR = p.m.e_R + cls0;
     const int Bt = p.m.Bt;
+    unsigned char *const my_win = p.m.win[p.m.rank];
+    const unsigned char *const th_slots = my_win + p.m.th_off, *const part_slots = my_win + p.m.part_off, *const dm_slots = my_win + p.m.dm_off;
     // the convergence measure of iteration j: the maximum over every CTA (slots alternate by iteration parity)
     auto read_dm = [&](int j) -> double {
         const unsigned tg = p.tag0 + (unsigned)j + 1u;
         double x = 0;
-        for (int i = threadIdx.x; i < Bt; i += EM_BLOCK) x = fmax(x, ll_load(p.m.dm_slots + 16 * (size_t)((j & 1) * Bt + i), tg, p.abort_flag));
+        for (int i = threadIdx.x; i < Bt; i += EM_BLOCK) x = fmax(x, ll_load(dm_slots + 16 * (size_t)((j & 1) * Bt + i), tg, p.abort_flag));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
         if (lane == 0) sm_red[warp] = x;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         const unsigned tag = p.tag0 + (unsigned)it + 1u;
         PS_TRACE(0);
         // theta of the halo rows, as their owners published it
-        for (int i = threadIdx.x; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(p.m.th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
+        for (int i = threadIdx.x; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
         if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
         __syncthreads();
         PS_TRACE(1);
@@ -278,23 +283,30 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) {
             double Q = v.Q[i];
             const int e0 = __ldg(p.m.inc_off + row0 + i), e1 = __ldg(p.m.inc_off + row0 + i + 1);
-            for (int e = e0; e < e1; e++) Q += ll_load(p.m.part_slots + 16 * (size_t)e, tag, p.abort_flag);
+            for (int e = e0; e < e1; e++) Q += ll_load(part_slots + 16 * (size_t)e, tag, p.abort_flag);
             const double2 ra = __ldg(p.m.row_RsA + row0 + i);
             const double th = v.theta[i];
             const double n = ra.x + th * Q;
             const double thn = fast_div(n, ra.y);
             v.theta[i] = thn;
-            if (e1 > e0) ll_store(p.m.th_slots + 16 * (size_t)(row0 + i), thn, tag + 1u);       // its readers are exactly its contributors
+            if (e1 > e0) {                                      // its readers are exactly its contributors: one store per rank that holds any
+                unsigned mk = (unsigned)__ldg(p.m.row_mask + row0 + i);
+                while (mk) {
+                    const int r = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    ll_store(p.m.win[r] + p.m.th_off + 16 * (size_t)(row0 + i), thn, tag + 1u);
+                }
+            }
             dm = fmax(dm, fast_div(fabs(thn - th) * ra.y, p.eps_abs + p.eps_rel * n));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if ((int)threadIdx.x < p.m.nranks) {                     // one store per rank: every CTA of every rank reads every CTA's measure
             double bm = 0;
             for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
-            ll_store(p.m.dm_slots + 16 * (size_t)((it & 1) * Bt + b), bm, tag);
+            ll_store(p.m.win[threadIdx.x] + p.m.dm_off + 16 * (size_t)((it & 1) * Bt + b), bm, tag);
         }
         __syncthreads();                                         // sm_red is reused by read_dm
         PS_TRACE(4);
@@ -322,6 +334,12 @@ int em_psum_attr(emsar_ctx *ctx)
     return EMSAR_OK;
 }
 
+__global__ void k_ps_zero_foreign(int32_t P, int32_t lo, int32_t hi, double *__restrict__ theta)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P && (p < lo || p >= hi)) theta[p] = 0.0;
+}
+
 int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_done, double *final_delta, double *ms_out)
 {
     emsar_ctx *ctx = s->ctx;
@@ -334,16 +352,32 @@ int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_d
     p.final_delta = (double *)(ctx->d_barrier + 10);
     p.abort_flag = (int *)(ctx->d_barrier + 14);
     p.trace = s->d_trace;
-    // scalars + the convergence slots (their tags restart with every sample, so they are cleared at every launch)
-    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256, st));
-    CU(cudaMemsetAsync(s->ps.dm_slots, 0, 2 * (size_t)s->ps.Bt * 16, st));
-    if ((unsigned)(s->slot_tag + (unsigned)max_iter + 4u) < s->slot_tag) {              // tag wrap: start over from clean slots
-        CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
-        s->slot_tag = 0;
+    const bool multi = s->ps.nranks > 1;
+    CU(cudaMemsetAsync(ctx->d_barrier, 0, 256, st));                                     // scalars, abort flag
+    const size_t slot_bytes = (size_t)p.m.dm_off + 2 * (size_t)s->ps.Bt * 16;
+    void *slot_base = nullptr;
+    if (multi) {
+        // one sample over several GPUs: the slot arrays live in this rank's peer-mapped window; every launch starts from clean tags
+        if (ctx->win_state != 1 || ctx->win_bytes < slot_bytes) { emsar_set_err("k_em_psum: the peer window is gone (call emsar_sample_prepare again)"); return EMSAR_ERR_STATE; }
+        for (int r = 0; r < s->ps.nranks; r++) p.m.win[r] = (unsigned char *)ctx->peer_win[r];
+        slot_base = ctx->win;
+        CU(cudaMemsetAsync(ctx->win, 0, slot_bytes, st));
+        p.tag0 = 0;
+    } else {
+        slot_base = s->d_slots;
+        p.m.win[0] = (unsigned char *)s->d_slots;
+        // the convergence slots are cleared at every launch (a launch that ended after 1-2 iterations leaves low tags behind); the
+        // theta / partial-sum slots never are: their tags only grow within a sample
+        CU(cudaMemsetAsync((unsigned char *)s->d_slots + p.m.dm_off, 0, 2 * (size_t)s->ps.Bt * 16, st));
+        if ((unsigned)(s->slot_tag + (unsigned)max_iter + 4u) < s->slot_tag) {              // tag wrap: start over from clean slots
+            CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
+            s->slot_tag = 0;
+        }
+        p.tag0 = s->slot_tag;
+        s->slot_tag += (unsigned)max_iter + 2u;
     }
-    p.tag0 = s->slot_tag;
-    s->slot_tag += (unsigned)max_iter + 2u;
-    if (s->ps.P > 0) { k_ps_theta_to_slots<<<(s->ps.P + 255) / 256, 256, 0, st>>>(s->ps.P, s->ps.theta, s->ps.th_slots, p.tag0 + 1u); LAUNCHED(ctx); }
+    if (s->ps.P > 0) { k_ps_theta_to_slots<<<(s->ps.P + 255) / 256, 256, 0, st>>>(s->ps.P, s->ps.theta, (unsigned char *)slot_base + p.m.th_off, p.tag0 + 1u); LAUNCHED(ctx); }
+    if (multi) TRY(comm_barrier(ctx));          // every window is reset and carries theta(0) before any rank's kernel writes into it
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)s->ps.B);
@@ -355,12 +389,12 @@ int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_d
     attrs[na].id = cudaLaunchAttributeCooperative;       // co-residency of all CTAs: they wait for each other's slots
     attrs[na].val.cooperative = 1;
     na++;
-    if (ctx->l2_persist_bytes > 0 && s->slots_bytes > 0) {
+    if (ctx->l2_persist_bytes > 0 && slot_bytes > 0) {
         // the exchange slots (theta of shared rows, partial sums) stay resident in L2 while the index streams through
-        size_t win = s->slots_bytes;
+        size_t win = slot_bytes;
         if (win > (size_t)ctx->prop.accessPolicyMaxWindowSize) win = (size_t)ctx->prop.accessPolicyMaxWindowSize;
         attrs[na].id = cudaLaunchAttributeAccessPolicyWindow;
-        attrs[na].val.accessPolicyWindow.base_ptr = s->d_slots;
+        attrs[na].val.accessPolicyWindow.base_ptr = slot_base;
         attrs[na].val.accessPolicyWindow.num_bytes = win;
         attrs[na].val.accessPolicyWindow.hitRatio = win <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)win;
         attrs[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -374,12 +408,21 @@ int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_d
     CU(cudaLaunchKernelEx(&cfg, k_em_psum, p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
+    if (multi && s->ps.P > 0) {
+        // every rank holds the final theta of its own rows: zero the others and add up (x + 0 is exact: all ranks end with the same bits)
+        k_ps_zero_foreign<<<(s->ps.P + 255) / 256, 256, 0, st>>>(s->ps.P, s->ps_row_lo, s->ps_row_hi, s->ps.theta);
+        LAUNCHED(ctx);
+        TRY(comm_allreduce_f64(ctx, s->ps.theta, s->ps.theta, (size_t)s->ps.P));
+    }
     int it = 0, aborted = 0; double fd = 0;
     CU(cudaMemcpyAsync(&it, p.iters_done, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&fd, p.final_delta, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&aborted, p.abort_flag, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (aborted) { emsar_set_err("k_em_psum: a wait on a tagged slot timed out (internal error)"); return EMSAR_ERR_STATE; }
+    if (aborted) {
+        emsar_set_err(multi ? "k_em_psum: a wait on peer memory timed out (a rank died or the ranks disagree on the call sequence)" : "k_em_psum: a wait on a tagged slot timed out (internal error)");
+        return multi ? EMSAR_ERR_COMM : EMSAR_ERR_STATE;
+    }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (iters_done) *iters_done = it;

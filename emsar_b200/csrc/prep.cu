@@ -834,7 +834,13 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     LAUNCHED(ctx);
     s->sharded = o.sharded != 0 && ctx->nranks > 1;
     if (o.sharded && !ctx->nccl_comm) { emsar_set_err("sharded solve without a communicator (emsar_comm_init)"); return EMSAR_ERR_STATE; }
-    if (s->sharded && nm > 0) {
+    // k_em_psum wherever the sample is eligible (EMSAR_EM_MODE=legacy|barrier|pipe keeps the older kernels). A class-sharded sample is then
+    // NOT cut by class range: every rank packs the whole model for nranks x B virtual CTAs and runs its own B of them.
+    const char *em_mode_ = getenv("EMSAR_EM_MODE");
+    const char *sh_mode_ = getenv("EMSAR_SHARD_MODE");
+    const bool want_psum = (!em_mode_ || !strcmp(em_mode_, "psum")) && !getenv("EMSAR_OWNER") && !s->force_legacy &&
+                           !(s->sharded && (ctx->win_state == -1 || (sh_mode_ && !strcmp(sh_mode_, "nccl"))));
+    if (s->sharded && nm > 0 && !want_psum) {
         uint32_t *d_w = (uint32_t *)d_newid2, *d_wpre = (uint32_t *)d_cellof;      // scratch reuse: both are written later
         k_shard_weights<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_act, d_w);
         CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_w, d_wpre, (int)(nm + 1), st));
@@ -887,28 +893,29 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
     m.T = T; m.P = P; m.B = B; m.C_a = C_a; m.smem_bytes = ctx->em_smem_bytes;
     m.theta = s->d_state;
     m.q = (double *)((char *)s->d_state + theta_bytes);
-    // ---- the class-owner-centric model (k_em_psum) whenever the sample is eligible; EMSAR_EM_MODE=legacy|barrier|pipe keeps the older kernels ----
-    {
-        const char *em_mode_ = getenv("EMSAR_EM_MODE");
-        const bool want_psum = !s->sharded && (!em_mode_ || !strcmp(em_mode_, "psum")) && !getenv("EMSAR_OWNER");
-        s->use_psum = false;
-        if (want_psum) {
-            PsPrepIn pin;
-            pin.T = T; pin.P = P; pin.nm = nm; pin.C_a = C_a; pin.n_kseg = n_kseg; pin.B = B; pin.d_cub = d_cub; pin.cub_bytes = cub_bytes;
-            pin.d_act = d_act; pin.d_newid = d_newid; pin.d_deg = d_deg; pin.d_rflag = d_rflag; pin.d_nat = d_nat; pin.d_pos = d_pos;
-            TRY(sample_build_psum(s, pin));
-            if (s->use_psum) {
-                CU(cudaEventRecord(e1, st));
-                CU(cudaStreamSynchronize(st));
-                float ms = 0;
-                CU(cudaEventElapsedTime(&ms, e0, e1));
-                s->prep_ms = ms;
-                s->prepared = true;
-                s->n_iter = 0; s->final_delta = INFINITY; s->em_ms = 0;
-                return EMSAR_OK;
-            }
-        } else ps_free(s);
-    }
+    // ---- the class-owner-centric model (k_em_psum) whenever the sample is eligible ----
+    s->use_psum = false;
+    if (want_psum) {
+        PsPrepIn pin;
+        pin.T = T; pin.P = P; pin.nm = nm; pin.C_a = C_a; pin.n_kseg = n_kseg; pin.d_cub = d_cub; pin.cub_bytes = cub_bytes;
+        pin.nranks = s->sharded ? ctx->nranks : 1; pin.rank = s->sharded ? ctx->rank : 0; pin.B_local = B; pin.B = B * pin.nranks;
+        pin.d_act = d_act; pin.d_newid = d_newid; pin.d_deg = d_deg; pin.d_rflag = d_rflag; pin.d_nat = d_nat; pin.d_pos = d_pos;
+        TRY(sample_build_psum(s, pin));
+        if (s->use_psum) {
+            CU(cudaEventRecord(e1, st));
+            CU(cudaStreamSynchronize(st));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            s->prep_ms = ms;
+            s->prepared = true;
+            s->n_iter = 0; s->final_delta = INFINITY; s->em_ms = 0;
+            return EMSAR_OK;
+        }
+        if (s->sharded) {            // not eligible: the legacy sharded kernel cuts the classes by range, which has to happen before the row statistics
+            s->force_legacy = true;
+            return emsar_sample_prepare(s, opts_in);
+        }
+    } else ps_free(s);
     // ---- arena part 1: everything whose size is known now ----
     // padding: a class is padded to steps*G members (< 1.25 k + 31), a cell to whole row blocks (< 32*steps ints per (CTA, cardinality) cell)
     const size_t e_ints_max = (size_t)ix->nnz_multi + (size_t)ix->nnz_multi / 4 + 32 * (size_t)nm + (size_t)n_cells * 32 * 64 + 64;

@@ -4,7 +4,8 @@
 struct PsPrepIn {
     int32_t T, P;
     int64_t nm, C_a;
-    int n_kseg, B;
+    int n_kseg, B;                 // B: virtual CTAs over all ranks (= B_local * nranks)
+    int B_local, rank, nranks;     // class-sharded sample: this device runs the CTAs rank * B_local ..; 1 rank otherwise
     void *d_cub;
     size_t cub_bytes;
     const int32_t *d_act, *d_newid, *d_deg;
@@ -242,10 +243,20 @@ __global__ void k_ps_inc_keys(unsigned int n, const unsigned long long *__restri
     key[i] = ((uniq_e[i] & 0xffffffffULL) << 32) | (uniq_e[i] >> 32);       // (row, CTA)
     val[i] = (int32_t)i;
 }
-__global__ void k_ps_inc_tgt(unsigned int n, const int32_t *__restrict__ sval, int32_t *__restrict__ tgt)
+// incidence e = (row p, contributing CTA b): the contributor's halo slot learns where its partial sum goes (slot e in the rank of p's
+// owner), and p learns which ranks read its theta
+__global__ void k_ps_inc_tgt(unsigned int n, const unsigned long long *__restrict__ skey, const int32_t *__restrict__ sval, const int32_t *__restrict__ row0, int B, int B_local,
+                             int32_t *__restrict__ tgt, int32_t *__restrict__ row_mask, unsigned long long *__restrict__ peer_stores, int my_rank)
 {
     unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) tgt[sval[e]] = (int32_t)e;
+    if (e >= n) return;
+    const int p = (int)(skey[e] >> 32), b = (int)(uint32_t)skey[e];
+    const int owner_rank = block_of_row(row0, B, p) / B_local, reader_rank = b / B_local;
+    tgt[sval[e]] = (int32_t)(e | ((unsigned)owner_rank << 28));
+    const int old = atomicOr(&row_mask[p], 1 << reader_rank);
+    // stores of THIS rank that cross NVLink per iteration: its partial sums for rows of other ranks, theta of its rows to every other reader rank
+    if (reader_rank == my_rank && owner_rank != my_rank) atomicAdd(peer_stores, 1ULL);
+    if (owner_rank == my_rank && reader_rank != my_rank && !(old & (1 << reader_rank))) atomicAdd(peer_stores, 1ULL);
 }
 __global__ void k_ps_inc_off(int32_t P, unsigned int n, const unsigned long long *__restrict__ skey, int32_t *__restrict__ inc_off)
 {
@@ -280,7 +291,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     ps_free(s);
     const int32_t T = in.T, P = in.P;
     const int64_t nm = in.nm, C_a = in.C_a;
-    const int B = in.B, n_kseg = in.n_kseg > 0 ? in.n_kseg : 1;
+    const int B = in.B, B_local = in.B_local, n_kseg = in.n_kseg > 0 ? in.n_kseg : 1;
     if (P <= 0 || C_a <= 0 || nm <= 0 || in.n_kseg <= 0) return EMSAR_OK;          // nothing to iterate on: the legacy path handles the degenerate cases
     const int n_cells = B * n_kseg;
     void *d_cub = in.d_cub; size_t cub_bytes = in.cub_bytes;
@@ -320,12 +331,14 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     // ---- model arrays that are sized now ----
     PsModel &m = s->ps;
     memset(&m, 0, sizeof(m));
-    m.P = P; m.B = B; m.Bt = B; m.block0 = 0; m.C_a = C_a; m.nnz_a = (int64_t)nnz_a; m.smem_bytes = ctx->em_smem_bytes;
+    m.P = P; m.B = B_local; m.Bt = B; m.block0 = in.rank * B_local; m.rank = in.rank; m.nranks = in.nranks;
+    m.C_a = C_a; m.nnz_a = (int64_t)nnz_a; m.smem_bytes = ctx->em_smem_bytes;
     m.theta = s->d_state;
     TRY(ps_alloc(s, &m.blk_row0, (size_t)B + 1)); TRY(ps_alloc(s, &m.blk_cls0, (size_t)B + 1)); TRY(ps_alloc(s, &m.blk_etile0, (size_t)B + 1));
     TRY(ps_alloc(s, &m.blk_mitem0, (size_t)B + 1)); TRY(ps_alloc(s, &m.blk_hr0, (size_t)B + 1)); TRY(ps_alloc(s, &m.blk_desc_smem, (size_t)B + 1));
     TRY(ps_alloc(s, &m.blk_res16, (size_t)B + 1));
-    TRY(ps_alloc(s, &m.row_RsA, (size_t)P + 1)); TRY(ps_alloc(s, &m.inc_off, (size_t)P + 2));
+    TRY(ps_alloc(s, &m.row_RsA, (size_t)P + 1)); TRY(ps_alloc(s, &m.inc_off, (size_t)P + 2)); TRY(ps_alloc(s, &m.row_mask, (size_t)P + 2));
+    CU(cudaMemsetAsync(m.row_mask, 0, ((size_t)P + 2) * 4, st));
     uint32_t *d_eR = nullptr;
     TRY(ps_alloc(s, &d_eR, (size_t)C_a + 1));
     m.e_R = d_eR;
@@ -336,8 +349,41 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     k_class_owner<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, in.d_act, in.d_deg, 2, d_owner);
     k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_owner, in.d_act, in.d_nat, d_ecost, cost_class, 2);
     k_row_cost<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, d_degn, d_ecost, d_cost, cost_row, 0);
-    CU(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cost, d_costp, P + 1, st));
-    k_block_bounds<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, P, d_costp, m.blk_row0);
+    {
+        // Row ranges on the host (P numbers each way): equal cost per CTA, but a range also ends where the state its CTA must hold in shared
+        // memory - theta and the partial sum of every row (16 bytes), q of every class a row owns (8 bytes) - reaches the budget; a region
+        // of many small classes would otherwise pile more q into one CTA than an SM can hold. The remaining cost is re-divided over the
+        // remaining CTAs after every cut.
+        CU(cudaMemsetAsync(d_costp, 0, ((size_t)P + 1) * 4, st));
+        k_class_cost<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(nm, T, ix->d_cls_off, d_owner, in.d_act, in.d_nat, (int32_t *)d_costp, 1, 0);      // classes owned per row
+        std::vector<uint32_t> h_cost((size_t)P + 1), h_ncls((size_t)P + 1);
+        CU(cudaMemcpyAsync(h_cost.data(), d_cost, ((size_t)P + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_ncls.data(), d_costp, ((size_t)P + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const long long cap = (long long)(getenv("EMSAR_PS_STATE_KB") ? atoi(getenv("EMSAR_PS_STATE_KB")) * 1024 : (ctx->em_smem_bytes * 6) / 10);   // the rest: halo theta, descriptors, index cache
+        unsigned long long left = 0;
+        for (int32_t i = 0; i < P; i++) left += h_cost[(size_t)i];
+        std::vector<int32_t> h_r0((size_t)B + 1, P);
+        h_r0[0] = 0;
+        int b = 0;
+        unsigned long long acc = 0, target = left / (unsigned long long)B;
+        long long state = 0;
+        for (int32_t i = 0; i < P && b < B - 1; i++) {
+            const long long sw = 16 + 8 * (long long)h_ncls[(size_t)i];
+            if (i > h_r0[(size_t)b] && (acc + h_cost[(size_t)i] / 2 > target || state + sw > cap)) {       // row i opens the next range
+                b++;
+                h_r0[(size_t)b] = i;
+                left -= acc;
+                acc = 0; state = 0;
+                target = left / (unsigned long long)(B - b);
+            }
+            acc += h_cost[(size_t)i];
+            state += sw;
+        }
+        for (int bb = b + 1; bb <= B; bb++) h_r0[(size_t)bb] = P;
+        CU(cudaMemcpyAsync(m.blk_row0, h_r0.data(), ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
     k_sort_keys<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, B, m.blk_row0, d_degn, d_key, d_val);
     CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_key, d_key2, d_val, d_perm, P, 0, 44, st));
     k_apply_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, d_perm, d_tn, d_degn, s->d_Rs, s->d_A, in.d_pos, d_degp, m.row_RsA, d_rown, d_rsan);
@@ -373,6 +419,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     }
     TRY(ps_alloc(s, &m.halo_rows, (size_t)n_ue + 1)); TRY(ps_alloc(s, &m.halo_tgt, (size_t)n_ue + 1));
     m.n_inc = (int32_t)n_ue;
+    if (n_ue >= (1u << 28)) { ps_free(s); return EMSAR_OK; }
     k_halo_ranges<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_ue, d_uniq_e, m.blk_hr0);
     if (n_ue) k_halo_list<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, m.halo_rows);
     ctx->launches += 2;
@@ -413,7 +460,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     char *tscr = nullptr;
     const size_t trb = rnd(((size_t)n_tr + 2) * 8);
     TRY(dev_alloc(&tscr, 8 * trb + 4096));
-    struct Guard2 { char *p; ~Guard2() { dev_free(p); } } guard2{tscr};
+    struct Guard2 { char *p, *q; ~Guard2() { dev_free(p); dev_free(q); } } guard2{tscr, nullptr};
     char *tc = tscr;
     unsigned long long *d_trkey = arena_take<unsigned long long>(tc, (size_t)n_tr + 2), *d_k2 = arena_take<unsigned long long>(tc, (size_t)n_tr + 2);
     unsigned long long *d_sk2 = arena_take<unsigned long long>(tc, (size_t)n_tr + 2);
@@ -422,6 +469,17 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     uint32_t *d_rowbase = arena_take<uint32_t>(tc, (size_t)n_tr + 2);
     int32_t *d_rowitem = arena_take<int32_t>(tc, (size_t)n_tr + 2), *d_rowidx = arena_take<int32_t>(tc, (size_t)n_tr + 2);
     uint32_t *d_size16 = arena_take<uint32_t>(tc, (size_t)n_tr + 2), *d_off16 = arena_take<uint32_t>(tc, (size_t)n_tr + 2);
+    {   // the CUB scratch of the caller is sized for the legacy packer's sorts: make sure the two sorts over touched rows / incidences fit
+        size_t need1 = 0, need2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need1, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)n_tr + 1, 0, 64);
+        cub::DeviceScan::ExclusiveSum(nullptr, need2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_tr + 2);
+        if (std::max(need1, need2) > cub_bytes) {
+            char *bigger = nullptr;
+            TRY(dev_alloc(&bigger, std::max(need1, need2) + 256));
+            guard2.q = bigger;
+            d_cub = bigger; cub_bytes = std::max(need1, need2);
+        }
+    }
     k_ps_touched<<<(unsigned)((nnz_a + 255) / 256), 256, 0, st>>>((int64_t)nnz_a, d_pb, d_flag, d_tidx, n_tr, d_trkey, d_trstart);
     k_ps_touched_keys<<<(n_tr + 255) / 256, 256, 0, st>>>(n_tr, d_trkey, d_trstart, d_k2, d_v2);
     CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_k2, d_sk2, d_v2, d_tperm, (int)n_tr, 0, 32 + cta_bits, st));
@@ -458,7 +516,8 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
         int32_t *d_iv = (int32_t *)d_k2, *d_isv = (int32_t *)d_sk2;                       // n_ue <= n_tr: every halo row is a touched row
         k_ps_inc_keys<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, d_ik, d_iv);
         CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_ik, d_isk, d_iv, d_isv, (int)n_ue, 0, 64, st));
-        k_ps_inc_tgt<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_isv, m.halo_tgt);
+        CU(cudaMemsetAsync(d_hcount + 4, 0, 8, st));
+        k_ps_inc_tgt<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_isk, d_isv, m.blk_row0, B, B_local, m.halo_tgt, m.row_mask, (unsigned long long *)(d_hcount + 4), in.rank);
         k_ps_inc_off<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, n_ue, d_isk, m.inc_off);
         ctx->launches += 6;
     } else CU(cudaMemsetAsync(m.inc_off, 0, ((size_t)P + 2) * 4, st));
@@ -519,21 +578,31 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     CU(cudaMemcpyAsync(m.blk_desc_smem, h_desc.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m.blk_res16, h_res16.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
     // ---- exchange slots: theta [P + 1] | partial sums [n_inc + 1] | convergence [2 * Bt] ----
+    unsigned long long peer_stores = 0;
     {
-        const size_t need = 16 * ((size_t)P + 1 + (size_t)n_ue + 1 + 2 * (size_t)B + 8);
-        if (need > s->slots_bytes) {
-            if (s->d_slots) dev_free(s->d_slots);
-            s->d_slots = nullptr;
-            char *psl = nullptr;
-            TRY(dev_alloc(&psl, need + (need >> 3)));
-            s->d_slots = psl;
-            s->slots_bytes = need + (need >> 3);
-            CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
-            s->slot_tag = 0;
+        m.th_off = 0;
+        m.part_off = 16 * ((long long)P + 1);
+        m.dm_off = m.part_off + 16 * ((long long)n_ue + 1);
+        const size_t need = (size_t)m.dm_off + 16 * (2 * (size_t)B + 8);
+        if (in.nranks > 1) {
+            // one sample over several GPUs: the slots live in a window every rank maps into the others (comm.cu); collective call
+            if (n_ue) CU(cudaMemcpyAsync(&peer_stores, d_hcount + 4, 8, cudaMemcpyDeviceToHost, st));
+            TRY(comm_window_ensure(ctx, 0, need));
+            if (ctx->win_state != 1) { ps_free(s); return EMSAR_OK; }          // no peer memory: the NCCL path of the legacy kernel
+            s->ps_row_lo = h_row0[in.rank * B_local]; s->ps_row_hi = h_row0[(in.rank + 1) * B_local];
+        } else {
+            if (need > s->slots_bytes) {
+                if (s->d_slots) dev_free(s->d_slots);
+                s->d_slots = nullptr;
+                char *psl = nullptr;
+                TRY(dev_alloc(&psl, need + (need >> 3)));
+                s->d_slots = psl;
+                s->slots_bytes = need + (need >> 3);
+                CU(cudaMemsetAsync(s->d_slots, 0, s->slots_bytes, st));
+                s->slot_tag = 0;
+            }
+            s->ps_row_lo = 0; s->ps_row_hi = P;
         }
-        m.th_slots = (unsigned char *)s->d_slots;
-        m.part_slots = m.th_slots + 16 * ((size_t)P + 1);
-        m.dm_slots = m.part_slots + 16 * ((size_t)n_ue + 1);
     }
     k_fill_double<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(m.theta, P, 1.0);
     LAUNCHED(ctx);
@@ -551,6 +620,6 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     ms_.stream_bytes_per_iter = ms_.index_bytes + 16 * (int64_t)P + 3 * 16 * (int64_t)n_ue;
     ms_.em_variant = 5; ms_.all_local = 1; ms_.halo_rows = n_ue; ms_.halo_classes = 0;
     ms_.resident_index_bytes = 16 * resident16;
-    ms_.peer_bytes_per_iter = 0;
+    ms_.peer_bytes_per_iter = in.nranks > 1 ? 16 * (int64_t)peer_stores + 16 * (int64_t)B_local * (in.nranks - 1) : 0;
     return EMSAR_OK;
 }

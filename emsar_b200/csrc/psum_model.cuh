@@ -15,13 +15,18 @@ struct PsModel {
     const unsigned char *e_data, *m_data;
     const uint32_t *e_R;           // [C_a] read counts in compact class order
     int32_t *halo_rows;            // [n_inc] global row of every halo slot, grouped by CTA (blk_hr0)
-    int32_t *halo_tgt;             // [n_inc] partial-sum slot the CTA's contribution to that row goes to
+    int32_t *halo_tgt;             // [n_inc] partial-sum slot the CTA's contribution to that row goes to | rank of the row's owner << 28
     int32_t *inc_off;              // [P + 1] partial-sum slots of row p: inc_off[p] .. inc_off[p + 1], ordered by contributing CTA
     double2 *row_RsA;              // [P] {Rs, A}
     double *theta;                 // [P]
-    unsigned char *th_slots;       // [P + 1] tagged slots: theta of every row that some other CTA reads
-    unsigned char *part_slots;     // [n_inc + 1] tagged slots: partial row sums
-    unsigned char *dm_slots;       // [2 * Bt] tagged slots: convergence measure per CTA, alternating by iteration parity
+    int32_t *row_mask;             // [P] ranks that hold a CTA contributing to (= reading theta of) row p, one bit per rank
+    // exchange slots (16 bytes, tagged): every rank holds the three arrays at the same offsets of its window; win[r] is rank r's window as
+    // mapped into this device (NVLink peer memory), win[rank] the local one. On a single GPU: one rank, the window is the sample's slot buffer.
+    unsigned char *win[8];
+    long long th_off;              // [P + 1]      theta of every row that some other CTA reads (written by the row's owner into every reader rank)
+    long long part_off;            // [n_inc + 1]  partial row sums (written by the contributor into the owner's rank)
+    long long dm_off;              // [2 * Bt]     convergence measure per CTA, alternating by iteration parity (written into every rank)
+    int32_t rank, nranks;
     int32_t Bt;                    // virtual CTAs over all devices (= B on a single GPU)
     int32_t n_inc;
     int32_t smem_bytes;

@@ -61,12 +61,16 @@ def main():
         ok, msg = False, "ranks disagree bitwise"
     tot = torch.tensor([float(st["nnz_a"])], device="cuda")
     dist.all_reduce(tot)
-    if int(tot.item()) != st1["nnz_a"]:
+    if st["em_variant"] == 5:
+        # k_em_psum: every rank packs the whole model and runs its own CTAs of it (the rows are cut over the ranks, not the classes)
+        if st["nnz_a"] != st1["nnz_a"] or (world > 1 and st["peer_bytes_per_iter"] <= 0):
+            ok, msg = False, f"psum sharding: nnz_a {st['nnz_a']} vs {st1['nnz_a']}, peer bytes {st['peer_bytes_per_iter']}"
+    elif int(tot.item()) != st1["nnz_a"]:
         ok, msg = False, f"shards do not partition the active classes: {int(tot.item())} vs {st1['nnz_a']}"
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MGPU {'OK' if flag.item() == 1.0 else 'FAIL'} mode={mode} peer_memory={pm} world={world} iters={r['n_iter']}/{r1['n_iter']} em_ms={r['em_ms']:.1f}/{r1['em_ms']:.1f} "
+        print(f"MGPU {'OK' if flag.item() == 1.0 else 'FAIL'} mode={mode} variant={st['em_variant']} peer_memory={pm} world={world} iters={r['n_iter']}/{r1['n_iter']} em_ms={r['em_ms']:.1f}/{r1['em_ms']:.1f} "
               f"max_rel={float(rel.max()):.2e} nnz_a/rank={st['nnz_a']} {msg}", flush=True)
     ix.close(); ctx.close()
     dist.destroy_process_group()

@@ -12,18 +12,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fused", "fused_overflow", "nccl"])
+@pytest.mark.parametrize("mode", ["fused", "fused_legacy", "fused_overflow", "nccl"])
 def test_class_sharded_sample_two_gpus(built, mode):
-    """fused: the all-reduce runs inside the persistent kernel over peer memory; nccl: ncclAllReduce per iteration."""
+    """fused: k_em_psum, the rows (and the classes of their median members) cut over the GPUs, shared rows exchanged over peer memory inside
+    the kernel; fused_legacy / fused_overflow: the class-range sharded k_em_persistent<2> with its in-kernel all-reduce; nccl: ncclAllReduce
+    per iteration."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    n = min(4, torch.cuda.device_count()) if mode == "fused" else 2
+    n = min(4, torch.cuda.device_count()) if mode in ("fused", "fused_legacy") else 2
     env = dict(os.environ)
     if mode == "nccl":
         env["EMSAR_SHARD_MODE"] = "nccl"
     if mode == "fused_overflow":
         env["EMSAR_EM_SMEM_KB"] = "12"
+    if mode == "fused_legacy":
+        env["EMSAR_EM_MODE"] = "legacy"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1", "--master-port", "29541",
            os.path.join(ROOT, "tests", "mgpu_worker.py"), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
