@@ -278,6 +278,143 @@ static int read_bowtie(const emsar_rsh *r, FILE *fp, const emsar_reader_opts *o,
 }
 
 
+/* ---- bowtie default output, SE, parsed by a pool of threads -------------------------------------------------
+ * The reference parses and groups on one thread (read_bowtie_SE :707-762). Splitting a line into fields, the transcript-name lookup and
+ * the mismatch string are independent per line; only the grouping by read id needs the file order. The reading thread cuts the file into
+ * blocks that end on a line break, `nthr` workers turn every line of a block into a small record, and the reading thread consumes the
+ * blocks in file order, feeding the records to the same grouper the single-threaded reader uses. Results are identical by construction
+ * (tests/test_host_ingest_cpu.py). */
+typedef struct { uint32_t id_off; int32_t tid, mm, fl, pos; int8_t status; } bt_rec;        /* status: 0 ok, 1 dropped by the strand filter, 2 malformed, 3 unknown transcript */
+typedef struct { char *buf; size_t len, cap; bt_rec *rec; size_t nrec, rec_cap; int state; } bt_job;   /* state: 0 free, 1 queued, 2 running, 3 done */
+typedef struct {
+    const emsar_rsh *r; char strand;
+    int nthr, njobs;
+    pthread_t *thr;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    bt_job *jobs;
+    unsigned long long n_read, n_taken;
+    int stop;
+} bt_mt;
+
+static void bt_parse_block(const emsar_rsh *r, char strand, bt_job *j)
+{
+    j->nrec = 0;
+    char *p = j->buf, *end = j->buf + j->len;
+    while (p < end) {
+        char *nl = (char *)memchr(p, '\n', (size_t)(end - p));
+        if (!nl) nl = end;
+        *nl = 0;
+        if (j->nrec == j->rec_cap) { j->rec_cap = j->rec_cap ? j->rec_cap * 2 : 65536; j->rec = (bt_rec *)realloc(j->rec, sizeof(bt_rec) * j->rec_cap); }
+        bt_rec *q = &j->rec[j->nrec++];
+        btline a;
+        bt_parse(p, &a);
+        q->id_off = (uint32_t)(a.id - j->buf);
+        q->status = 0; q->tid = -1; q->mm = 0; q->fl = 0; q->pos = 0;
+        if (strand != 0 && a.nfield > 1 && strand != a.strand) q->status = 1;
+        else if (a.nfield < 7) q->status = 2;
+        else {
+            q->tid = emsar_rsh_tid(r, a.tname);
+            if (q->tid < 0) q->status = 3;
+            else { q->mm = emsar_parse_mmstr(a.mm); q->fl = a.seqlen; q->pos = a.pos; }
+        }
+        p = nl + 1;
+    }
+}
+
+static void *bt_worker(void *arg)
+{
+    bt_mt *h = (bt_mt *)arg;
+    pthread_mutex_lock(&h->mu);
+    for (;;) {
+        while (!h->stop && h->n_taken == h->n_read) pthread_cond_wait(&h->cv_work, &h->mu);
+        if (h->stop) break;
+        bt_job *j = &h->jobs[h->n_taken % (unsigned long long)h->njobs];
+        h->n_taken++;
+        j->state = 2;
+        pthread_mutex_unlock(&h->mu);
+        bt_parse_block(h->r, h->strand, j);
+        pthread_mutex_lock(&h->mu);
+        j->state = 3;
+        pthread_cond_broadcast(&h->cv_done);
+    }
+    pthread_mutex_unlock(&h->mu);
+    return NULL;
+}
+
+static int bt_consume(bt_job *j, grouper *g, char *err)
+{
+    for (size_t i = 0; i < j->nrec; i++) {
+        const bt_rec *q = &j->rec[i];
+        if (q->status == 1) continue;
+        if (q->status == 2) return fail(err, "Error: input alignment file doesn't look like bowtieout file.");
+        if (q->status == 3) return fail(err, "error: unexisting tid in the bowtie output file. Check bowtieout file.");
+        g_alignment(g, j->buf + q->id_off, q->tid, q->mm, q->fl, q->pos);
+    }
+    return 0;
+}
+
+static int read_bowtie_se_mt(const emsar_rsh *r, FILE *fp, const emsar_reader_opts *o, grouper *g, char *err)
+{
+    enum { BLOCK = 4 << 20 };
+    bt_mt h;
+    memset(&h, 0, sizeof h);
+    h.r = r; h.strand = o->strand; h.nthr = o->io_threads; h.njobs = 2 * o->io_threads + 2;
+    h.jobs = (bt_job *)calloc((size_t)h.njobs, sizeof(bt_job));
+    h.thr = (pthread_t *)calloc((size_t)h.nthr, sizeof(pthread_t));
+    pthread_mutex_init(&h.mu, NULL); pthread_cond_init(&h.cv_work, NULL); pthread_cond_init(&h.cv_done, NULL);
+    for (int i = 0; i < h.nthr; i++) pthread_create(&h.thr[i], NULL, bt_worker, &h);
+    char *carry = NULL; size_t ncarry = 0, carry_cap = 0;
+    unsigned long long n_consumed = 0;
+    int rc = 0, eof = 0;
+    while (!rc && (!eof || n_consumed < h.n_read)) {
+        /* keep the ring full: read blocks ahead */
+        while (!eof && h.n_read - n_consumed < (unsigned long long)h.njobs) {
+            bt_job *j = &h.jobs[h.n_read % (unsigned long long)h.njobs];
+            if (j->cap < ncarry + BLOCK + 1) { j->cap = ncarry + BLOCK + 1; j->buf = (char *)realloc(j->buf, j->cap); }
+            if (ncarry) memcpy(j->buf, carry, ncarry);
+            size_t got = fread(j->buf + ncarry, 1, BLOCK, fp);
+            size_t len = ncarry + got;
+            ncarry = 0;
+            if (got < (size_t)BLOCK) eof = 1;
+            if (!eof) {                     /* cut at the last line break; the tail goes in front of the next block */
+                size_t cut = len;
+                while (cut > 0 && j->buf[cut - 1] != '\n') cut--;
+                if (cut == 0) { rc = fail(err, "bowtie file: a line longer than %d bytes", (int)BLOCK); break; }
+                ncarry = len - cut;
+                if (ncarry > carry_cap) { carry_cap = ncarry * 2; carry = (char *)realloc(carry, carry_cap); }
+                memcpy(carry, j->buf + cut, ncarry);
+                len = cut;
+            }
+            if (len > 0 && j->buf[len - 1] == '\n') len--;          /* the last line of the block needs no terminator */
+            j->len = len;
+            if (len == 0 && eof) break;
+            pthread_mutex_lock(&h.mu);
+            j->state = 1;
+            h.n_read++;
+            pthread_cond_signal(&h.cv_work);
+            pthread_mutex_unlock(&h.mu);
+        }
+        if (rc || n_consumed == h.n_read) continue;
+        bt_job *j = &h.jobs[n_consumed % (unsigned long long)h.njobs];
+        pthread_mutex_lock(&h.mu);
+        while (j->state != 3) pthread_cond_wait(&h.cv_done, &h.mu);
+        pthread_mutex_unlock(&h.mu);
+        rc = bt_consume(j, g, err);
+        j->state = 0;
+        n_consumed++;
+    }
+    pthread_mutex_lock(&h.mu);
+    h.stop = 1;
+    pthread_cond_broadcast(&h.cv_work);
+    pthread_mutex_unlock(&h.mu);
+    for (int i = 0; i < h.nthr; i++) pthread_join(h.thr[i], NULL);
+    for (int i = 0; i < h.njobs; i++) { free(h.jobs[i].buf); free(h.jobs[i].rec); }
+    free(h.jobs); free(h.thr); free(carry);
+    pthread_mutex_destroy(&h.mu); pthread_cond_destroy(&h.cv_work); pthread_cond_destroy(&h.cv_done);
+    return rc;
+}
+
 /* ---- BGZF with a pool of inflate threads ------------------------------------------------------
  * A BAM file is a sequence of independent gzip members of <= 64 KB (BGZF); the reference inflates them one at a time on
  * the thread that also parses (samtools 0.1.19 bgzf.c). Here the parsing thread only reads the compressed blocks ahead
@@ -767,7 +904,8 @@ int emsar_read_alignments(const emsar_rsh *r, const char *path, const emsar_read
     if (o->format == 0) {
         FILE *fp = (path[0] == 0) ? stdin : fopen(path, "r");
         if (!fp) { g_finish(&g); return fail(err, "can't open bowtie file."); }
-        rc = read_bowtie(r, fp, o, readlength, &g, err);
+        if (!o->pe && o->io_threads > 1) rc = read_bowtie_se_mt(r, fp, o, &g, err);
+        else rc = read_bowtie(r, fp, o, readlength, &g, err);
         if (fp != stdin) fclose(fp);
     } else {
         rc = read_sam(r, path, o, readlength, &g, err);

@@ -150,3 +150,37 @@ def test_malformed_bam_aux_is_an_error(pe_bam, tmp_path):
         with pytest.raises(host.HostError):
             host.read_alignments(rsh, str(p), pe=True, fmt="bam")
     rsh.close()
+
+
+def test_threaded_bowtie_parser_matches_single_thread(built, tmp_path):
+    """SE bowtie text parsed by a pool of threads (blocks cut at line breaks, grouping in file order) gives exactly the read groups of the
+    single-threaded reader, with and without the strand filter; malformed lines and unknown transcripts are still errors."""
+    idx = synth.make_index(T=300, n_multi=1500, kmax=12, seed=17, module_cap=40)
+    reads = synth.make_reads(idx, 120000, seed=17)
+    synth.write_rsh(idx, str(tmp_path / "in.rsh"))
+    p = str(tmp_path / "in.bowtie")
+    synth.write_bowtie_se(idx, reads, p)
+    lines = open(p).read().splitlines(True)
+    for i in range(0, len(lines), 7):                    # some reverse-strand alignments for the strand filter
+        f = lines[i].split("\t"); f[1] = "-"; lines[i] = "\t".join(f)
+    open(p, "w").writelines(lines)
+    rsh = host.Rsh(str(tmp_path / "in.rsh"))
+    for strand in ("ns", "ssf", "ssr"):
+        a, _ = host.read_alignments(rsh, p, fmt="bowtie", strand=strand, io_threads=0)
+        for thr in (2, 5):
+            b, _ = host.read_alignments(rsh, p, fmt="bowtie", strand=strand, io_threads=thr, nbuf=2, batch_reads=5000)
+            assert _same(a, b), (strand, thr)
+    fx = gu.FIXTURES["se"]
+    grsh = host.Rsh(gu.materialize(fx["rsh"], tmp_path))
+    galn = gu.materialize(fx["aln"], tmp_path)
+    a, _ = host.read_alignments(grsh, galn, fmt="bowtie", io_threads=0)
+    b, _ = host.read_alignments(grsh, galn, fmt="bowtie", io_threads=4)
+    assert _same(a, b)
+    bad = str(tmp_path / "bad.bowtie")
+    open(bad, "w").writelines(lines[:1000] + ["r\t+\tnot_a_transcript\t0\tAAAA\tAAAA\t0\t\n"] + lines[1000:2000])
+    with pytest.raises(host.HostError):
+        host.read_alignments(rsh, bad, fmt="bowtie", io_threads=3)
+    open(bad, "w").writelines(lines[:1000] + ["garbage line without tabs\n"])
+    with pytest.raises(host.HostError):
+        host.read_alignments(rsh, bad, fmt="bowtie", io_threads=3)
+    rsh.close(); grsh.close()
