@@ -50,39 +50,39 @@ __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const u
     const double *th = v.theta;
     if (lg == 0 && steps <= 4) {
         const uint4 w = ps_ld128<RES>(v.cache, gdat, off16 + lane);
-        // read counts: behind the 512 bytes of index data in a resident copy, in the compact class array otherwise
-        const int r4 = off16 * 4 + 128;
+        // read counts: behind the 512 bytes of index data in a resident copy, in the compact class array otherwise. They are fetched together
+        // with the members (one round trip to L2 for a tile that is not resident), for lanes beyond the tile's classes from a clamped index
+        const int r4 = off16 * 4 + 128, last = t.y - 1;
         if (steps == 2) {
+            uint32_t r[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) { const int c = min(g * 32 + lane, last); r[g] = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c) : __ldg(gR + t.x + c); }
             const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], b0 = th[w.y & 0xffffu], b1 = th[w.y >> 16];
             const double c0 = th[w.z & 0xffffu], c1 = th[w.z >> 16], d0 = th[w.w & 0xffffu], d1 = th[w.w >> 16];
             const double s[4] = {a0 + a1, b0 + b1, c0 + c1, d0 + d1};
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 const int c = g * 32 + lane;
-                if (c < t.y) {
-                    const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c) : __ldg(gR + t.x + c);
-                    v.q[t.x + c] = ps_q_of(r, s[g]);
-                }
+                if (c < t.y) v.q[t.x + c] = ps_q_of(r[g], s[g]);
             }
         } else {
+            const int c0i = min(lane, last), c1i = min(32 + lane, last);
+            const uint32_t r0 = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c0i) : __ldg(gR + t.x + c0i);
+            const uint32_t r1 = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c1i) : __ldg(gR + t.x + c1i);
             const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], a2 = th[w.y & 0xffffu], a3 = th[w.y >> 16];
             const double b0 = th[w.z & 0xffffu], b1 = th[w.z >> 16], b2 = th[w.w & 0xffffu], b3 = th[w.w >> 16];
             double s0 = a0; s0 += a1; s0 += a2; s0 += a3;           // sequential member order (the pad slot holds 0.0)
             double s1 = b0; s1 += b1; s1 += b2; s1 += b3;
-            if (lane < t.y) {
-                const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + lane) : __ldg(gR + t.x + lane);
-                v.q[t.x + lane] = ps_q_of(r, s0);
-            }
-            if (32 + lane < t.y) {
-                const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, r4 + 32 + lane) : __ldg(gR + t.x + 32 + lane);
-                v.q[t.x + 32 + lane] = ps_q_of(r, s1);
-            }
+            if (lane < t.y) v.q[t.x + lane] = ps_q_of(r0, s0);
+            if (32 + lane < t.y) v.q[t.x + 32 + lane] = ps_q_of(r1, s1);
         }
         return;
     }
     // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
     const int steps4 = (steps + 3) >> 2;
     const int o8 = off16 * 2 + lane;
+    const int G = 1 << lg, cls = lane >> lg;
+    const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + min(cls, t.y - 1)) : __ldg(gR + t.x + min(cls, t.y - 1));
     double s = 0;
     int c = 0;
     for (; c + 2 <= steps4; c += 2) {
@@ -96,22 +96,15 @@ __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const u
         const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
         s += x0; s += x1; s += x2; s += x3;
     }
-    const int G = 1 << lg, cls = lane >> lg;
     for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((lane & (G - 1)) == 0 && cls < t.y) {
-        const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + cls) : __ldg(gR + t.x + cls);
-        v.q[t.x + cls] = ps_q_of(r, s);
-    }
+    if ((lane & (G - 1)) == 0 && cls < t.y) v.q[t.x + cls] = ps_q_of(r, s);
 }
 
 // ---- M-phase: one item (partial row sums over the CTA's own classes) ------------------------------------------------------------------------
-__device__ __forceinline__ void ps_emit(const PsParams &p, const PsView &v, unsigned slot, double S, unsigned tag)
+__device__ __forceinline__ void ps_emit(const PsParams &p, const PsView &v, uint32_t dst, double S, unsigned tag)
 {
-    if ((int)slot < v.nrows) v.Q[slot] = S;
-    else {
-        const unsigned tg = (unsigned)__ldg(p.m.halo_tgt + v.hr0 + ((int)slot - v.nrows));       // slot of the row's owner, in the owner's rank
-        ll_store(p.m.win[tg >> 28] + p.m.part_off + 16 * (size_t)(tg & 0x0fffffffu), S, tag);
-    }
+    if (!(dst & PS_REMOTE)) v.Q[dst] = S;
+    else ll_store(p.m.win[(dst >> 28) & 7u] + p.m.part_off + 16 * (size_t)(dst & 0x0fffffffu), S, tag);     // the row's owner collects it, in its rank
 }
 
 template <bool RES>
@@ -121,10 +114,9 @@ __device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, co
     const int off16 = t.z;
     const double *q = v.q;
     if (((t.w >> 30) & 1) == 0) {
-        const uint32_t hw = ps_ld32<RES>(v.cache, gdat, off16 * 4 + (lane >> 1));
-        const unsigned slot = (lane & 1) ? (hw >> 16) : (hw & 0xffffu);
+        const uint32_t dst = ps_ld32<RES>(v.cache, gdat, off16 * 4 + lane);
         const int len4 = (len + 3) >> 2;
-        const int o8 = off16 * 2 + 8 + lane;
+        const int o8 = off16 * 2 + 16 + lane;
         double S = 0;
         int c = 0;
         for (; c + 2 <= len4; c += 2) {
@@ -138,16 +130,16 @@ __device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, co
             const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
             S += x0; S += x1; S += x2; S += x3;
         }
-        if (slot != 0xffffu) ps_emit(p, v, slot, S, tag);
+        if (dst != PS_NONE) ps_emit(p, v, dst, S, tag);
     } else {
         // a group of long rows: the warp reduces one row at a time (lane-strided partial sums, fixed shuffle tree), lane r keeps row r's sum
         const int n = t.y;
-        const uint32_t hw = lane < n ? ps_ld32<RES>(v.cache, gdat, off16 * 4 + lane) : 0u;
-        const int mywords = (int)(((hw >> 16) + 1) >> 1);
+        const uint2 hw = lane < n ? ps_ld64<RES>(v.cache, gdat, off16 * 2 + lane) : make_uint2(0u, PS_NONE);      // {length, destination}
+        const int mywords = (int)((hw.x + 1) >> 1);
         int start = mywords;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
-        start += ((n + 3) & ~3) - mywords;                 // exclusive prefix (32-bit words), behind the header
+        start += ((2 * n + 3) & ~3) - mywords;             // exclusive prefix (32-bit words), behind the header
         double mine = 0;
         for (int r = 0; r < n; r++) {
             const int a = off16 * 4 + __shfl_sync(0xffffffffu, start, r), W = __shfl_sync(0xffffffffu, mywords, r);
@@ -167,7 +159,7 @@ __device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, co
             for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
             if (lane == r) mine = s;
         }
-        if (lane < n) ps_emit(p, v, hw & 0xffffu, mine, tag);
+        if (lane < n) ps_emit(p, v, hw.y, mine, tag);
     }
 }
 
@@ -187,7 +179,9 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     const int mi0 = p.m.blk_mitem0[b], n_mi = p.m.blk_mitem0[b + 1] - mi0;
     const int hr0 = p.m.blk_hr0[b], nhr = p.m.blk_hr0[b + 1] - hr0;
     const int desc_smem = p.m.blk_desc_smem[b];
-    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls);
+    const int in0 = p.m.inc_off[row0], nin = p.m.inc_off[row0 + nrows] - in0;       // partial sums this CTA receives per iteration
+    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls, nin);
+    double *const s_in = (double *)(sm_dyn + pl.off_in);
     PsView v;
     v.theta = (double *)(sm_dyn + pl.off_theta);
     v.q = (double *)(sm_dyn + pl.off_q);
@@ -278,27 +272,35 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         }
         __syncthreads();
         PS_TRACE(3);
-        // owner update: own partial sum + the contributions of the other CTAs, in CTA order
+        // owner update: own partial sum + the contributions of the other CTAs, in CTA order. The constants of a thread's first two rows are
+        // requested first, then every incoming partial sum is fetched by its own thread (one round trip for all of them) and staged
         double dm = 0;
-        for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) {
+        const int i0 = threadIdx.x, i1 = threadIdx.x + EM_BLOCK;
+        double2 ra0 = make_double2(0.0, 1.0), ra1 = ra0;
+        int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+        unsigned mk0 = 0, mk1 = 0;
+        if (i0 < nrows) { ra0 = __ldg(p.m.row_RsA + row0 + i0); a0 = __ldg(p.m.inc_off + row0 + i0); b0 = __ldg(p.m.inc_off + row0 + i0 + 1); mk0 = (unsigned)__ldg(p.m.row_mask + row0 + i0); }
+        if (i1 < nrows) { ra1 = __ldg(p.m.row_RsA + row0 + i1); a1 = __ldg(p.m.inc_off + row0 + i1); b1 = __ldg(p.m.inc_off + row0 + i1 + 1); mk1 = (unsigned)__ldg(p.m.row_mask + row0 + i1); }
+        for (int e = threadIdx.x; e < nin; e += EM_BLOCK) s_in[e] = ll_load(part_slots + 16 * (size_t)(in0 + e), tag, p.abort_flag);
+        __syncthreads();
+        auto update = [&](int i, double2 ra, int e0, int e1, unsigned mk) {
             double Q = v.Q[i];
-            const int e0 = __ldg(p.m.inc_off + row0 + i), e1 = __ldg(p.m.inc_off + row0 + i + 1);
-            for (int e = e0; e < e1; e++) Q += ll_load(part_slots + 16 * (size_t)e, tag, p.abort_flag);
-            const double2 ra = __ldg(p.m.row_RsA + row0 + i);
+            for (int e = e0; e < e1; e++) Q += s_in[e - in0];
             const double th = v.theta[i];
             const double n = ra.x + th * Q;
             const double thn = fast_div(n, ra.y);
             v.theta[i] = thn;
-            if (e1 > e0) {                                      // its readers are exactly its contributors: one store per rank that holds any
-                unsigned mk = (unsigned)__ldg(p.m.row_mask + row0 + i);
-                while (mk) {
-                    const int r = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    ll_store(p.m.win[r] + p.m.th_off + 16 * (size_t)(row0 + i), thn, tag + 1u);
-                }
+            while (mk) {                                        // its readers are exactly its contributors: one store per rank that holds any
+                const int r = __ffs(mk) - 1;
+                mk &= mk - 1;
+                ll_store(p.m.win[r] + p.m.th_off + 16 * (size_t)(row0 + i), thn, tag + 1u);
             }
             dm = fmax(dm, fast_div(fabs(thn - th) * ra.y, p.eps_abs + p.eps_rel * n));
-        }
+        };
+        if (i0 < nrows) update(i0, ra0, a0, b0, mk0);
+        if (i1 < nrows) update(i1, ra1, a1, b1, mk1);
+        for (int i = threadIdx.x + 2 * EM_BLOCK; i < nrows; i += EM_BLOCK)
+            update(i, __ldg(p.m.row_RsA + row0 + i), __ldg(p.m.inc_off + row0 + i), __ldg(p.m.inc_off + row0 + i + 1), (unsigned)__ldg(p.m.row_mask + row0 + i));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) sm_red[warp] = dm;

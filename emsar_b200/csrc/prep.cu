@@ -7,6 +7,7 @@
 // The deterministic fp64 pre-steps use the reference's summation order and no FMA contraction (-fmad=false), so
 // Wf, adjEUMA, EUMAps and iEUMA are bit-identical to the CPU reference.
 #include <algorithm>
+#include <stdarg.h>
 #include <cub/cub.cuh>
 #include <numeric>
 

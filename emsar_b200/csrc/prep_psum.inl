@@ -202,7 +202,7 @@ __global__ void k_ps_item_init(int n_items, int B, const int32_t *__restrict__ i
     uint16_t *d = m_data + (size_t)it.z * 8;
     const int n = it.x * 8;
     if ((it.w >> 30) & 1) { for (int j = lane; j < n; j += 32) d[j] = zq; for (int j = lane; j < ps_group_hdr_u16(it.y); j += 32) d[j] = 0; }
-    else for (int j = lane; j < n; j += 32) d[j] = j < 32 ? (uint16_t)0xFFFF : zq;
+    else for (int j = lane; j < n; j += 32) d[j] = j < 64 ? (uint16_t)0xFFFF : zq;            // 32 destinations = PS_NONE
 }
 // one warp per touched row (in the CTA's sorted order): its local classes, ascending, into its slice column or group row
 __global__ void k_ps_scatter_rows(uint32_t n_tr, int B, const unsigned long long *__restrict__ skey, const int32_t *__restrict__ tperm,
@@ -210,6 +210,7 @@ __global__ void k_ps_scatter_rows(uint32_t n_tr, int B, const unsigned long long
                                   const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ tr0, const int32_t *__restrict__ nlong,
                                   const int32_t *__restrict__ ngroups, const int32_t *__restrict__ item0, const uint32_t *__restrict__ rowbase,
                                   const int32_t *__restrict__ rowitem, const int32_t *__restrict__ rowidx, const int4 *__restrict__ items,
+                                  const int32_t *__restrict__ row0, const int32_t *__restrict__ hr0, const int32_t *__restrict__ halo_tgt,
                                   uint16_t *__restrict__ m_data)
 {
     const int lane = threadIdx.x & 31;
@@ -218,20 +219,22 @@ __global__ void k_ps_scatter_rows(uint32_t n_tr, int B, const unsigned long long
     const int b = (int)(skey[j] >> 32);
     const int ti = tperm[j];
     const uint32_t s0 = tr_start[ti], deg = tr_start[ti + 1] - s0;
-    const uint16_t slot = (uint16_t)(tr_key[ti] & 0xffffu);
+    const int slot = (int)(tr_key[ti] & 0xffffu), nrows = row0[b + 1] - row0[b];
+    // where the row's partial sum goes: the CTA's own array, or the slot its owner reads (in the owner's rank)
+    const uint32_t dst = slot < nrows ? (uint32_t)slot : (PS_REMOTE | (uint32_t)halo_tgt[hr0[b] + (slot - nrows)]);
     const int jj = (int)j - tr0[b], nl = nlong[b];
     if (jj < nl) {
         const int4 it = items[rowitem[j]];
         uint16_t *d = m_data + (size_t)it.z * 8;
-        if (lane == 0) ((uint32_t *)d)[rowidx[j]] = (uint32_t)slot | (deg << 16);
+        if (lane == 0) { ((uint32_t *)d)[2 * rowidx[j]] = deg; ((uint32_t *)d)[2 * rowidx[j] + 1] = dst; }
         uint16_t *ent = d + ps_group_hdr_u16(it.y) + rowbase[j];
         for (uint32_t e = lane; e < deg; e += 32) ent[e] = (uint16_t)(pairs[s0 + e] & 0xffffu);
     } else {
         const int4 it = items[item0[b] + ngroups[b] + ((jj - nl) >> 5)];
         const int l = (jj - nl) & 31;
         uint16_t *d = m_data + (size_t)it.z * 8;
-        if (lane == 0) d[l] = slot;
-        for (uint32_t e = lane; e < deg; e += 32) d[32 + (e >> 2) * 128 + l * 4 + (e & 3)] = (uint16_t)(pairs[s0 + e] & 0xffffu);
+        if (lane == 0) ((uint32_t *)d)[l] = dst;
+        for (uint32_t e = lane; e < deg; e += 32) d[64 + (e >> 2) * 128 + l * 4 + (e & 3)] = (uint16_t)(pairs[s0 + e] & 0xffffu);
     }
 }
 
@@ -268,6 +271,18 @@ __global__ void k_ps_inc_off(int32_t P, unsigned int n, const unsigned long long
     inc_off[p] = (int32_t)lo;
 }
 
+// why a sample did not get the psum model (EMSAR_VERBOSE=1)
+static void ps_note(const char *fmt, ...)
+{
+    if (!getenv("EMSAR_VERBOSE")) return;
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "emsar_cuda: k_em_psum not used: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+}
+
 static void ps_free(emsar_sample *s)
 {
     for (void *p : s->ps_allocs) dev_free(p);
@@ -292,7 +307,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     const int32_t T = in.T, P = in.P;
     const int64_t nm = in.nm, C_a = in.C_a;
     const int B = in.B, B_local = in.B_local, n_kseg = in.n_kseg > 0 ? in.n_kseg : 1;
-    if (P <= 0 || C_a <= 0 || nm <= 0 || in.n_kseg <= 0) return EMSAR_OK;          // nothing to iterate on: the legacy path handles the degenerate cases
+    if (P <= 0 || C_a <= 0 || nm <= 0 || in.n_kseg <= 0) { ps_note("empty model"); return EMSAR_OK; }         // nothing to iterate on: the legacy path handles the degenerate cases
     const int n_cells = B * n_kseg;
     void *d_cub = in.d_cub; size_t cub_bytes = in.cub_bytes;
     auto rnd = [](size_t b) { return ((b + 255) / 256) * 256; };
@@ -419,7 +434,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     }
     TRY(ps_alloc(s, &m.halo_rows, (size_t)n_ue + 1)); TRY(ps_alloc(s, &m.halo_tgt, (size_t)n_ue + 1));
     m.n_inc = (int32_t)n_ue;
-    if (n_ue >= (1u << 28)) { ps_free(s); return EMSAR_OK; }
+    if (n_ue >= (1u << 28)) { ps_note("%u shared rows", n_ue); ps_free(s); return EMSAR_OK; }
     k_halo_ranges<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_ue, d_uniq_e, m.blk_hr0);
     if (n_ue) k_halo_list<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, m.halo_rows);
     ctx->launches += 2;
@@ -431,9 +446,27 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     CU(cudaStreamSynchronize(st));
     for (int b = 0; b < B; b++) {
         const int nrows = h_row0[b + 1] - h_row0[b], nhr = h_hr0[b + 1] - h_hr0[b], ncls = h_cls0[b + 1] - h_cls0[b];
-        if (nrows + nhr + 1 > PS_MAX_SLOT || ncls + 1 > PS_MAX_SLOT) { ps_free(s); return EMSAR_OK; }       // 16-bit slots do not reach: legacy layout
-        if (ps_smem_plan(0, 0, 0, nrows, nhr, ncls).total + 1024 > ctx->em_smem_bytes) { ps_free(s); return EMSAR_OK; }
+        if (nrows + nhr + 1 > PS_MAX_SLOT || ncls + 1 > PS_MAX_SLOT) {       // 16-bit slots do not reach: legacy layout
+            ps_note("CTA %d: %d rows + %d halo rows, %d classes exceed 16-bit slots", b, nrows, nhr, ncls);
+            ps_free(s); return EMSAR_OK;
+        }
+        if (ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr).total + 1024 > ctx->em_smem_bytes) {
+            ps_note("CTA %d: state of %d rows + %d halo rows, %d classes = %d bytes does not fit in %d bytes of shared memory", b, nrows, nhr, ncls,
+                    ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr).total, ctx->em_smem_bytes);
+            ps_free(s); return EMSAR_OK;
+        }
     }
+    // ---- incidences: partial-sum slots per row, and where every halo slot sends its contribution ----
+    if (n_ue > 0) {
+        unsigned long long *d_ik = d_pa, *d_isk = d_pb;                                   // both free here: the halo keys have been reduced to d_uniq_e
+        int32_t *d_iv = (int32_t *)d_pc, *d_isv = (int32_t *)d_pc + (nnz_a + 2);          // n_ue <= nnz_a
+        k_ps_inc_keys<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, d_ik, d_iv);
+        CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_ik, d_isk, d_iv, d_isv, (int)n_ue, 0, 64, st));
+        CU(cudaMemsetAsync(d_hcount + 4, 0, 8, st));
+        k_ps_inc_tgt<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_isk, d_isv, m.blk_row0, B, B_local, m.halo_tgt, m.row_mask, (unsigned long long *)(d_hcount + 4), in.rank);
+        k_ps_inc_off<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, n_ue, d_isk, m.inc_off);
+        ctx->launches += 6;
+    } else CU(cudaMemsetAsync(m.inc_off, 0, ((size_t)P + 2) * 4, st));
     // ---- E side: tile descriptors, member slots, read counts; one key per member for the M side ----
     uint16_t *d_edata = nullptr;
     TRY(ps_alloc(s, &d_edata, (size_t)e_u16 + 64));
@@ -506,24 +539,13 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     if (n_mitems > 0) {
         k_ps_item_init<<<(unsigned)(((int64_t)n_mitems * 32 + 255) / 256), 256, 0, st>>>(n_mitems, B, m.blk_mitem0, m.blk_cls0, m.m_items, d_mdata);
         k_ps_scatter_rows<<<(unsigned)(((int64_t)n_tr * 32 + 255) / 256), 256, 0, st>>>(n_tr, B, d_sk2, d_tperm, d_trkey, d_trstart, d_pb, d_tr0, d_nlong, d_ngroups, m.blk_mitem0,
-                                                                                     d_rowbase, d_rowitem, d_rowidx, m.m_items, d_mdata);
+                                                                                     d_rowbase, d_rowitem, d_rowidx, m.m_items, m.blk_row0, m.blk_hr0, m.halo_tgt, d_mdata);
         ctx->launches += 2;
     }
-    // ---- incidences: partial-sum slots per row, and where every halo slot sends its contribution ----
-    if (n_ue > 0) {
-        unsigned long long *d_ik = d_pa, *d_isk = d_pa + (n_ue + 2);                      // n_ue <= nnz_a / 2 is not guaranteed: use d_pc for the values
-        if (2 * ((size_t)n_ue + 2) > nnz_a + 2) { d_isk = d_pc; }
-        int32_t *d_iv = (int32_t *)d_k2, *d_isv = (int32_t *)d_sk2;                       // n_ue <= n_tr: every halo row is a touched row
-        k_ps_inc_keys<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_uniq_e, d_ik, d_iv);
-        CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_ik, d_isk, d_iv, d_isv, (int)n_ue, 0, 64, st));
-        CU(cudaMemsetAsync(d_hcount + 4, 0, 8, st));
-        k_ps_inc_tgt<<<(n_ue + 255) / 256, 256, 0, st>>>(n_ue, d_isk, d_isv, m.blk_row0, B, B_local, m.halo_tgt, m.row_mask, (unsigned long long *)(d_hcount + 4), in.rank);
-        k_ps_inc_off<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(P, n_ue, d_isk, m.inc_off);
-        ctx->launches += 6;
-    } else CU(cudaMemsetAsync(m.inc_off, 0, ((size_t)P + 2) * 4, st));
     // ---- host: shared-memory plan of every CTA, resident index cache ----
     std::vector<int4> h_et((size_t)n_etiles), h_mi((size_t)n_mitems);
-    std::vector<int32_t> h_mi0(B + 1);
+    std::vector<int32_t> h_mi0(B + 1), h_inc((size_t)P + 2);
+    CU(cudaMemcpyAsync(h_inc.data(), m.inc_off, ((size_t)P + 1) * 4, cudaMemcpyDeviceToHost, st));
     if (n_etiles) CU(cudaMemcpyAsync(h_et.data(), m.e_tiles, (size_t)n_etiles * 16, cudaMemcpyDeviceToHost, st));
     if (n_mitems) CU(cudaMemcpyAsync(h_mi.data(), m.m_items, (size_t)n_mitems * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_mi0.data(), m.blk_mitem0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, st));
@@ -536,13 +558,14 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     for (int b = 0; b < B && fits; b++) {
         const int nrows = h_row0[b + 1] - h_row0[b], nhr = h_hr0[b + 1] - h_hr0[b], ncls = h_cls0[b + 1] - h_cls0[b];
         const int n_et = h_et0[b + 1] - h_et0[b], n_mi = h_mi0[b + 1] - h_mi0[b];
+        const int nin = h_inc[(size_t)h_row0[b + 1]] - h_inc[(size_t)h_row0[b]];        // partial sums it receives per iteration (staged in shared memory)
         int desc = 1;
-        int left = ctx->em_smem_bytes - ps_smem_plan(1, n_et, n_mi, nrows, nhr, ncls).total - 256;
+        int left = ctx->em_smem_bytes - ps_smem_plan(1, n_et, n_mi, nrows, nhr, ncls, nin).total - 256;
         if (left < 16 * 1024) {         // many tiles (high cardinalities): descriptors stay in global memory, the space goes to the state
             desc = 0;
-            left = ctx->em_smem_bytes - ps_smem_plan(0, n_et, n_mi, nrows, nhr, ncls).total - 256;
+            left = ctx->em_smem_bytes - ps_smem_plan(0, n_et, n_mi, nrows, nhr, ncls, nin).total - 256;
         }
-        if (left < 0) { fits = false; break; }
+        if (left < 0) { ps_note("CTA %d: %d rows + %d halo rows, %d classes, %d incoming partial sums, %d tiles, %d items: %d bytes short", b, nrows, nhr, ncls, nin, n_et, n_mi, -left); fits = false; break; }
         h_desc[b] = desc;
         // resident index cache: the data of the items with the longest dependent chains stays in shared memory for the whole kernel
         struct Cand { int prio, n16, idx; bool e; };
@@ -588,7 +611,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
             // one sample over several GPUs: the slots live in a window every rank maps into the others (comm.cu); collective call
             if (n_ue) CU(cudaMemcpyAsync(&peer_stores, d_hcount + 4, 8, cudaMemcpyDeviceToHost, st));
             TRY(comm_window_ensure(ctx, 0, need));
-            if (ctx->win_state != 1) { ps_free(s); return EMSAR_OK; }          // no peer memory: the NCCL path of the legacy kernel
+            if (ctx->win_state != 1) { ps_note("no peer memory between the ranks"); ps_free(s); return EMSAR_OK; }          // the NCCL path of the legacy kernel
             s->ps_row_lo = h_row0[in.rank * B_local]; s->ps_row_hi = h_row0[(in.rank + 1) * B_local];
         } else {
             if (need > s->slots_bytes) {

@@ -26,15 +26,19 @@ __host__ __device__ __forceinline__ int ps_tile_u16(int k) { return k <= 4 ? 256
 
 // ---- M side -------------------------------------------------------------------------------------------------------------------------
 // The rows a CTA's classes touch (own rows and halo rows), sorted by their number of local entries, longest first.
-// rows with more than M_LONG entries: groups of <= M_GROUP_ROWS rows, one warp per group: header = one 32-bit word {slot, length} per row
-// (padded to 16 bytes), then the rows' entries back to back, each row padded to an even number of entries;
-// the rest: slices of 32 rows: header = 32 u16 row slots (0xFFFF = unused lane), then chunks of 4 entries per lane (chunk c of all lanes = 256
+// A row's destination is one 32-bit word: its slot in the CTA's partial-sum array when the CTA owns the row, or PS_REMOTE | the
+// partial-sum slot of the row's owner | the owner's rank << 28 for a halo row; PS_NONE = unused lane.
+// rows with more than M_LONG entries: groups of <= M_GROUP_ROWS rows, one warp per group: header = two 32-bit words {length, destination}
+// per row (padded to 16 bytes), then the rows' entries back to back, each row padded to an even number of entries;
+// the rest: slices of 32 rows: header = 32 destinations (128 bytes), then chunks of 4 entries per lane (chunk c of all lanes = 256
 // bytes), padded with the zero-q slot up to the longest row of the slice.
-__host__ __device__ __forceinline__ int ps_slice_u16(int len) { return 32 + 128 * ((len + 3) >> 2); }
-__host__ __device__ __forceinline__ int ps_group_hdr_u16(int rows) { return ((rows + 3) & ~3) * 2; }
+constexpr uint32_t PS_REMOTE = 0x80000000u, PS_NONE = 0xFFFFFFFFu;
+__host__ __device__ __forceinline__ int ps_slice_u16(int len) { return 64 + 128 * ((len + 3) >> 2); }
+__host__ __device__ __forceinline__ int ps_group_hdr_u16(int rows) { return ((2 * rows + 3) & ~3) * 2; }
 
-struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_cache, total; };
-__host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls)
+struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_in, off_cache, total; };
+// nin: partial sums the CTA receives per iteration (staged in shared memory before its rows are updated)
+__host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls, int nin)
 {
     PsPlan p;
     p.off_et = 0;
@@ -42,7 +46,8 @@ __host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et,
     p.off_theta = p.off_mi + (desc_smem ? n_mi * 16 : 0);
     p.off_q = p.off_theta + (((nrows + nhr + 1) * 8 + 15) & ~15);
     p.off_Q = p.off_q + (((ncls + 1) * 8 + 15) & ~15);
-    p.off_cache = p.off_Q + ((nrows * 8 + 15) & ~15);
+    p.off_in = p.off_Q + ((nrows * 8 + 15) & ~15);
+    p.off_cache = p.off_in + ((nin * 8 + 15) & ~15);
     p.total = p.off_cache;
     return p;
 }
