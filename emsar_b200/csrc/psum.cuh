@@ -36,7 +36,8 @@ constexpr uint32_t PS_REMOTE = 0x80000000u, PS_NONE = 0xFFFFFFFFu;
 __host__ __device__ __forceinline__ int ps_slice_u16(int len) { return 64 + 128 * ((len + 3) >> 2); }
 __host__ __device__ __forceinline__ int ps_group_hdr_u16(int rows) { return ((2 * rows + 3) & ~3) * 2; }
 
-struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_in, off_cache, total; };
+constexpr int PS_STG_BYTES = 1152 * EM_WARPS;     // one staging buffer per warp (em_psum.cu)
+struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_in, off_stg, off_cache, total; };
 // nin: partial sums the CTA receives per iteration (staged in shared memory before its rows are updated)
 __host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls, int nin)
 {
@@ -47,7 +48,8 @@ __host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et,
     p.off_q = p.off_theta + (((nrows + nhr + 1) * 8 + 15) & ~15);
     p.off_Q = p.off_q + (((ncls + 1) * 8 + 15) & ~15);
     p.off_in = p.off_Q + ((nrows * 8 + 15) & ~15);
-    p.off_cache = p.off_in + ((nin * 8 + 15) & ~15);
+    p.off_stg = p.off_in + ((nin * 8 + 15) & ~15);
+    p.off_cache = p.off_stg + PS_STG_BYTES;
     p.total = p.off_cache;
     return p;
 }

@@ -18,6 +18,7 @@
  */
 #define _GNU_SOURCE
 #include <getopt.h>
+#include <sys/stat.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdarg.h>
@@ -105,6 +106,7 @@ typedef struct {
     int by_class;                      /* EMSAR_SHARD=classes */
     uint8_t *comm_id;                  /* shared: NCCL unique id made by worker 0 */
     pthread_barrier_t *bar;
+    int *next; const int *order; int serial;      /* -M work queue: shared ticket, files sorted by size (largest first) */
 } worker_arg;
 
 static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsar_index *ix, int i, double *eumacut, int shard_rank, int shard_n)
@@ -230,7 +232,16 @@ static void *worker(void *p)
         for (int i = 0; i < o->naln; i++) run_file(o, r, ctx, ix, i, &eumacut, w->worker, w->nworker);      /* every file on all GPUs */
         emsar_comm_destroy(ctx);
     } else {
-        for (int i = w->worker; i < o->naln; i += w->nworker) run_file(o, r, ctx, ix, i, &eumacut, 0, 1);
+        /* shared work queue, largest file first (LPT): a GPU takes the next file the moment it is free, so a list of uneven samples
+         * finishes together. Output file numbers are the positions in the list, whoever computes them. One GPU: list order, and EUMAcut
+         * carries over from file to file as in the reference (emsar.h:94 is never reset); several GPUs: every file starts from the
+         * initial EUMAcut, so that the result does not depend on which GPU took which file. */
+        for (;;) {
+            const int k = w->nworker > 1 ? __atomic_fetch_add(w->next, 1, __ATOMIC_RELAXED) : w->serial++;
+            if (k >= o->naln) break;
+            if (w->nworker > 1) eumacut = 0;
+            run_file(o, r, ctx, ix, w->nworker > 1 ? w->order[k] : k, &eumacut, 0, 1);
+        }
     }
     emsar_index_destroy(ix);
     emsar_cuda_close(ctx);
@@ -366,15 +377,30 @@ int main(int argc, char *argv[])
     pthread_t th[64];
     worker_arg wa[64];
     uint8_t comm_id[128];
+    /* the -M work queue: files by decreasing size (a proxy for the number of reads), ties in list order */
+    int queue_next = 0;
+    int *order = (int *)malloc(sizeof(int) * (size_t)(o.naln > 0 ? o.naln : 1));
+    {
+        long long *sz = (long long *)malloc(sizeof(long long) * (size_t)(o.naln > 0 ? o.naln : 1));
+        for (int i = 0; i < o.naln; i++) { struct stat sb; sz[i] = stat(o.aln[i], &sb) == 0 ? (long long)sb.st_size : 0; order[i] = i; }
+        for (int i = 1; i < o.naln; i++) {          /* insertion sort: stable, the list is short */
+            const int x = order[i]; int j = i - 1;
+            while (j >= 0 && sz[order[j]] < sz[x]) { order[j + 1] = order[j]; j--; }
+            order[j + 1] = x;
+        }
+        free(sz);
+    }
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, NULL, (unsigned)ndev);
     for (int w = 0; w < ndev; w++) {
         wa[w].o = &o; wa[w].rsh = rsh; wa[w].device = devs[w]; wa[w].worker = w; wa[w].nworker = ndev; wa[w].rc = 0;
+        wa[w].next = &queue_next; wa[w].order = order; wa[w].serial = 0;
         wa[w].by_class = by_class; wa[w].comm_id = comm_id; wa[w].bar = &bar;
     }
     for (int w = 1; w < ndev; w++) pthread_create(&th[w], NULL, worker, &wa[w]);
     worker(&wa[0]);
     for (int w = 1; w < ndev; w++) pthread_join(th[w], NULL);
+    free(order);
     stamp(&o, "freeing rsh array ...");
     emsar_rsh_free(rsh);
     return 0;
