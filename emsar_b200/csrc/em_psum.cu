@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     const int hr0 = p.m.blk_hr0[b], nhr = p.m.blk_hr0[b + 1] - hr0;
     const int desc_smem = p.m.blk_desc_smem[b];
     const int in0 = p.m.inc_off[row0], nin = p.m.inc_off[row0 + nrows] - in0;       // partial sums this CTA receives per iteration
-    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls, nin);
+    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls, nin, p.m.stage);
+    const bool stage_e = p.m.stage & 1, stage_m = p.m.stage & 2;
     double *const s_in = (double *)(sm_dyn + pl.off_in);
     unsigned char *const stg = sm_dyn + pl.off_stg + PS_STG * warp;          // this warp's staging buffer
     PsView v;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             auto e_stage = [&](const int4 &t) {
                 const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf, s4 = (steps + 3) >> 2;
                 const bool small = lg == 0 && steps <= 4;
-                if (((t.w >> 30) & 1) || (!small && s4 > 4)) return;            // resident, or too long for the buffer (read directly)
+                if (!stage_e || ((t.w >> 30) & 1) || (!small && s4 > 4)) return;            // resident, or too long for the buffer (read directly)
                 const int n16 = small ? 32 : 16 * s4;
                 const uint4 *src = (const uint4 *)p.m.e_data + t.z;
                 for (int j = lane; j < n16; j += 32) ps_cp16(stg + 16 * j, src + j);
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             int4 tB = e_desc(tkB);
             while (tkA < n_et) {
                 const int steps = tA.w & 0xfff, lg = (tA.w >> 12) & 0xf, s4 = (steps + 3) >> 2;
-                const bool small = lg == 0 && steps <= 4, res = (tA.w >> 30) & 1, staged = !res && (small || s4 <= 4);
+                const bool small = lg == 0 && steps <= 4, res = (tA.w >> 30) & 1, staged = stage_e && !res && (small || s4 <= 4);
                 const unsigned char *dsm = res ? v.cache + 16 * (size_t)tA.z : stg;     // where the tile's words are when they are in shared memory
                 int tkC = n_et;
                 int4 tC = make_int4(0, 0, 0, 0);
@@ -247,12 +248,13 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
                 const double *th = v.theta;
                 const int last = tA.y - 1;
                 if (small) {
-                    const uint4 w = *(const uint4 *)(dsm + 16 * lane);
-                    const uint32_t *rr = (const uint32_t *)(dsm + 512);
+                    const bool insm = res || staged;
+                    const uint4 w = insm ? *(const uint4 *)(dsm + 16 * lane) : __ldg((const uint4 *)p.m.e_data + tA.z + lane);
+                    const uint32_t *rr = insm ? (const uint32_t *)(dsm + 512) : gR + tA.x;      // read counts: behind the index data in shared memory, else the compact class array
                     if (steps == 2) {
                         uint32_t r[4];
 #pragma unroll
-                        for (int g = 0; g < 4; g++) r[g] = rr[min(g * 32 + lane, last)];
+                        for (int g = 0; g < 4; g++) r[g] = insm ? rr[min(g * 32 + lane, last)] : __ldg(rr + min(g * 32 + lane, last));
                         advance();
                         const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], b0 = th[w.y & 0xffffu], b1 = th[w.y >> 16];
                         const double c0 = th[w.z & 0xffffu], c1 = th[w.z >> 16], d0 = th[w.w & 0xffffu], d1 = th[w.w >> 16];
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
                             if (c < tA.y) v.q[tA.x + c] = ps_q_of(r[g], sum[g]);
                         }
                     } else {
-                        const uint32_t r0 = rr[min(lane, last)], r1 = rr[min(32 + lane, last)];
+                        const uint32_t r0 = insm ? rr[min(lane, last)] : __ldg(rr + min(lane, last)), r1 = insm ? rr[min(32 + lane, last)] : __ldg(rr + min(32 + lane, last));
                         advance();
                         const double s0 = ps_gather4(th, make_uint2(w.x, w.y), 0.0), s1 = ps_gather4(th, make_uint2(w.z, w.w), 0.0);     // the pad slot of a 3-member class holds 0.0
                         if (lane < tA.y) v.q[tA.x + lane] = ps_q_of(r0, s0);
@@ -289,9 +291,9 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
                         r = ((const uint32_t *)(dsm + 256 * s4))[min(cls, last)];
                         sum = ps_sum_chunks<true>(th, v.cache, nullptr, tA.z * 2 + lane, s4);
                     } else {
-                        advance();
                         r = __ldg(gR + tA.x + min(cls, last));
-                        sum = ps_sum_chunks<false>(th, nullptr, p.m.e_data, tA.z * 2 + lane, s4);
+                        advance();
+                        sum = ps_sum_chunks<false>(th, nullptr, p.m.e_data, tA.z * 2 + lane, s4);       // four chunk loads in flight from the start
                     }
                     for (int dd = G >> 1; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
                     if ((lane & (G - 1)) == 0 && cls < tA.y) v.q[tA.x + cls] = ps_q_of(r, sum);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             auto m_desc = [&](int tk) -> int4 { return tk < n_mi ? mi[tk] : make_int4(0, 0, 0, 0); };
             auto m_stage = [&](const int4 &t) {
                 const int len4 = ((t.w & 0x1fffffff) + 3) >> 2;
-                if (((t.w >> 29) & 1) || ((t.w >> 30) & 1) || len4 > 4) return;   // resident, a group of long rows, or a slice too long for the buffer
+                if (!stage_m || ((t.w >> 29) & 1) || ((t.w >> 30) & 1) || len4 > 4) return;   // resident, a group of long rows, or a slice too long for the buffer
                 const int n16 = 8 + 16 * len4;
                 const uint4 *src = (const uint4 *)p.m.m_data + t.z;
                 for (int j = lane; j < n16; j += 32) ps_cp16(stg + 16 * j, src + j);
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             int4 tB = m_desc(tkB);
             while (tkA < n_mi) {
                 const int len4 = ((tA.w & 0x1fffffff) + 3) >> 2;
-                const bool res = (tA.w >> 29) & 1, group = (tA.w >> 30) & 1, staged = !res && !group && len4 <= 4;
+                const bool res = (tA.w >> 29) & 1, group = (tA.w >> 30) & 1, staged = stage_m && !res && !group && len4 <= 4;
                 const unsigned char *dsm = res ? v.cache + 16 * (size_t)tA.z : stg;
                 int tkC = n_mi;
                 int4 tC = make_int4(0, 0, 0, 0);
@@ -355,8 +357,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
                         dst = ((const uint32_t *)dsm)[lane];
                         S = ps_sum_chunks<true>(q, v.cache, nullptr, tA.z * 2 + 16 + lane, len4);
                     } else {
-                        advance();
                         dst = __ldg((const uint32_t *)p.m.m_data + (size_t)tA.z * 4 + lane);
+                        advance();
                         S = ps_sum_chunks<false>(q, nullptr, p.m.m_data, tA.z * 2 + 16 + lane, len4);
                     }
                     if (dst != PS_NONE) ps_emit(p, v, dst, S, tag);

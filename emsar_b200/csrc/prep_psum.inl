@@ -450,9 +450,9 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
             ps_note("CTA %d: %d rows + %d halo rows, %d classes exceed 16-bit slots", b, nrows, nhr, ncls);
             ps_free(s); return EMSAR_OK;
         }
-        if (ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr).total + 1024 > ctx->em_smem_bytes) {
+        if (ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr, 0).total + 1024 > ctx->em_smem_bytes) {
             ps_note("CTA %d: state of %d rows + %d halo rows, %d classes = %d bytes does not fit in %d bytes of shared memory", b, nrows, nhr, ncls,
-                    ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr).total, ctx->em_smem_bytes);
+                    ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nhr, 0).total, ctx->em_smem_bytes);
             ps_free(s); return EMSAR_OK;
         }
     }
@@ -554,16 +554,30 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     int64_t resident16 = 0, rows_long = 0;
     for (int i = 0; i < n_etiles; i++) h_esrc[(size_t)i] = h_et[(size_t)i].z;
     for (int i = 0; i < n_mitems; i++) { h_msrc[(size_t)i] = h_mi[(size_t)i].z; if ((h_mi[(size_t)i].w >> 30) & 1) rows_long += h_mi[(size_t)i].y; }
+    // look-ahead staging of the items that are not resident (E tiles: bit 0, M items: bit 1; EMSAR_PS_STAGE overrides). It costs 36 KB of
+    // shared memory per CTA, so it is dropped when the state would not fit beside it.
+    int stage = getenv("EMSAR_PS_STAGE") ? atoi(getenv("EMSAR_PS_STAGE")) & 3 : 2;
+    for (int pass = 0; pass < 2; pass++) {
+        bool ok = true;
+        for (int b = 0; b < B && ok; b++) {
+            const int nrows = h_row0[b + 1] - h_row0[b], nhr = h_hr0[b + 1] - h_hr0[b], ncls = h_cls0[b + 1] - h_cls0[b];
+            const int nin = h_inc[(size_t)h_row0[b + 1]] - h_inc[(size_t)h_row0[b]];
+            if (ctx->em_smem_bytes - ps_smem_plan(0, 0, 0, nrows, nhr, ncls, nin, stage).total - 256 < 8 * 1024) ok = false;
+        }
+        if (ok || stage == 0) break;
+        stage = 0;
+    }
+    m.stage = stage;
     bool fits = true;
     for (int b = 0; b < B && fits; b++) {
         const int nrows = h_row0[b + 1] - h_row0[b], nhr = h_hr0[b + 1] - h_hr0[b], ncls = h_cls0[b + 1] - h_cls0[b];
         const int n_et = h_et0[b + 1] - h_et0[b], n_mi = h_mi0[b + 1] - h_mi0[b];
         const int nin = h_inc[(size_t)h_row0[b + 1]] - h_inc[(size_t)h_row0[b]];        // partial sums it receives per iteration (staged in shared memory)
         int desc = 1;
-        int left = ctx->em_smem_bytes - ps_smem_plan(1, n_et, n_mi, nrows, nhr, ncls, nin).total - 256;
+        int left = ctx->em_smem_bytes - ps_smem_plan(1, n_et, n_mi, nrows, nhr, ncls, nin, stage).total - 256;
         if (left < 16 * 1024) {         // many tiles (high cardinalities): descriptors stay in global memory, the space goes to the state
             desc = 0;
-            left = ctx->em_smem_bytes - ps_smem_plan(0, n_et, n_mi, nrows, nhr, ncls, nin).total - 256;
+            left = ctx->em_smem_bytes - ps_smem_plan(0, n_et, n_mi, nrows, nhr, ncls, nin, stage).total - 256;
         }
         if (left < 0) { ps_note("CTA %d: %d rows + %d halo rows, %d classes, %d incoming partial sums, %d tiles, %d items: %d bytes short", b, nrows, nhr, ncls, nin, n_et, n_mi, -left); fits = false; break; }
         h_desc[b] = desc;

@@ -39,7 +39,7 @@ __host__ __device__ __forceinline__ int ps_group_hdr_u16(int rows) { return ((2 
 constexpr int PS_STG_BYTES = 1152 * EM_WARPS;     // one staging buffer per warp (em_psum.cu)
 struct PsPlan { int off_et, off_mi, off_theta, off_q, off_Q, off_in, off_stg, off_cache, total; };
 // nin: partial sums the CTA receives per iteration (staged in shared memory before its rows are updated)
-__host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls, int nin)
+__host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et, int n_mi, int nrows, int nhr, int ncls, int nin, int stage)
 {
     PsPlan p;
     p.off_et = 0;
@@ -49,7 +49,7 @@ __host__ __device__ __forceinline__ PsPlan ps_smem_plan(int desc_smem, int n_et,
     p.off_Q = p.off_q + (((ncls + 1) * 8 + 15) & ~15);
     p.off_in = p.off_Q + ((nrows * 8 + 15) & ~15);
     p.off_stg = p.off_in + ((nin * 8 + 15) & ~15);
-    p.off_cache = p.off_stg + PS_STG_BYTES;
+    p.off_cache = p.off_stg + (stage ? PS_STG_BYTES : 0);
     p.total = p.off_cache;
     return p;
 }

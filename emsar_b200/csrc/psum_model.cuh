@@ -27,6 +27,7 @@ struct PsModel {
     long long part_off;            // [n_inc + 1]  partial row sums (written by the contributor into the owner's rank)
     long long dm_off;              // [2 * Bt]     convergence measure per CTA, alternating by iteration parity (written into every rank)
     int32_t rank, nranks;
+    int32_t stage;                 // bit 0: E tiles, bit 1: M items that are not resident travel through the per-warp staging buffers (cp.async look-ahead)
     int32_t Bt;                    // virtual CTAs over all devices (= B on a single GPU)
     int32_t n_inc;
     int32_t smem_bytes;

@@ -208,10 +208,77 @@ def fixture_eumacut(tmp):
     keep(tmp, "eumacut", ["in.rsh", "in.bowtie"])
 
 
+def fixture_bigmod(tmp):
+    """Two sequence-sharing sets of ~700 transcripts each (gene families tied together by classes across a paralog family): the size at
+    which the reference's randomized search is slow (minutes per round) and its rounds visibly disagree, so the 6 sd term of the
+    tolerance policy is exercised. -n 8 rounds, two sets on two threads."""
+    idx = synth.make_index_v2(T=1400, n_multi=9000, alpha=2.0, kmax=24, seed=11, module_cap=700, p_cross=0.25, scatter=True)
+    idx.names = [f"T{t:05d}" for t in range(idx.T)]
+    reads = synth.make_reads(idx, 60000, seed=11)
+    synth.write_rsh(idx, f"{tmp}/in.rsh")
+    synth.write_bowtie_se(idx, reads, f"{tmp}/in.bowtie")
+    run([REF, "-q", "-g", "-p", "2", "-n", "8", "-I", f"{tmp}/in.rsh", f"{tmp}/out", "p", f"{tmp}/in.bowtie"])
+    keep(tmp, "bigmod", ["in.rsh", "in.bowtie", "out/p.0.fpkm", "out/p.0.segments", "out/p.0.fraglength_effect"])
+
+
+def fixture_config1(tmp):
+    """Substitute of BASELINE.json configs[0] (the bundled Vicugna PE sample is missing from the reference checkout, .MISSING_LARGE_BLOBS):
+    a PE index built by the reference's own emsar-build -P (L = 40, fragments 60..90) from a generated 2K-transcript fasta (gene families
+    sharing exons), 100K simulated PE fragments written as SAM with their true multi-mapping alignments, quantified by the reference."""
+    rng = np.random.default_rng(21)
+    L, fmin, fmax = 40, 60, 90
+    exons = ["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(80, 260, size=2600)]
+    tx = []
+    while len(tx) < 2000:
+        pool = list(rng.choice(len(exons), size=8, replace=False))
+        for _ in range(int(rng.integers(2, 7))):
+            ks = sorted(rng.choice(8, size=int(rng.integers(2, 6)), replace=False))
+            tx.append("".join(exons[pool[k]] for k in ks))
+    tx = tx[:2000]
+    names = [f"TX{i:04d}" for i in range(len(tx))]
+    with open(f"{tmp}/tx.fa", "w") as f:
+        for n, s_ in zip(names, tx):
+            f.write(f">{n}\n{s_}\n")
+    run([REFB, "-p", "4", "-P", "-f", str(fmin), "-F", str(fmax), f"{tmp}/tx.fa", str(L), f"{tmp}/idx", "c1"])
+    rsh = [p for p in os.listdir(f"{tmp}/idx") if p.endswith(".rsh")][0]
+    shutil.copy(f"{tmp}/idx/{rsh}", f"{tmp}/in.rsh")
+    # fragments: position + length on a transcript drawn by expression; every (mate1 L-mer, mate2 L-mer, fragment length) occurrence in
+    # any transcript is an alignment of the pair (dictionary of fragment end pairs)
+    theta = rng.lognormal(0, 1.5, size=len(tx)) * (rng.random(len(tx)) > 0.2)
+    w = theta * np.array([max(len(s_) - fmin + 1, 0) for s_ in tx])
+    pick = rng.choice(len(tx), size=100000, p=w / w.sum())
+    occ = {}
+    for t, s_ in enumerate(tx):
+        for fl in range(fmin, fmax + 1):
+            for p0 in range(0, len(s_) - fl + 1):
+                occ.setdefault((s_[p0:p0 + L], s_[p0 + fl - L:p0 + fl], fl), []).append((t, p0))
+    seq = "A" * L
+    with open(f"{tmp}/in.sam", "w") as f:
+        f.write("@HD\tVN:1.0\tSO:unsorted\n")
+        for n, s_ in zip(names, tx):
+            f.write(f"@SQ\tSN:{n}\tLN:{len(s_)}\n")
+        for r, t in enumerate(pick):
+            s_ = tx[t]
+            fl = int(rng.integers(fmin, min(fmax, len(s_)) + 1))
+            p0 = int(rng.integers(0, len(s_) - fl + 1))
+            for (tt, pp) in occ[(s_[p0:p0 + L], s_[p0 + fl - L:p0 + fl], fl)]:
+                p1, p2 = pp + 1, pp + fl - L + 1
+                f.write(f"r{r}\t{0x1 | 0x2 | 0x20 | 0x40}\t{names[tt]}\t{p1}\t255\t{L}M\t=\t{p2}\t{fl}\t{seq}\t{seq}\tMD:Z:{L}\n")
+                f.write(f"r{r}\t{0x1 | 0x2 | 0x10 | 0x80}\t{names[tt]}\t{p2}\t255\t{L}M\t=\t{p1}\t{-fl}\t{seq}\t{seq}\tMD:Z:{L}\n")
+    run([REF, "-q", "-g", "-p", "4", "-n", "8", "-P", "-S", "-I", f"{tmp}/in.rsh", f"{tmp}/out", "p", f"{tmp}/in.sam"])
+    keep(tmp, "config1", ["in.rsh", "in.sam", "out/p.0.fpkm", "out/p.0.segments", "out/p.0.fraglength_effect"])
+
+
 def main():
+    if len(sys.argv) > 1:          # python make_golden.py bigmod config1: only those
+        for n in sys.argv[1:]:
+            with tempfile.TemporaryDirectory() as tmp:
+                globals()["fixture_" + n](tmp)
+                print("ok", n)
+        return
     if not (os.path.exists(REF) and os.path.exists(REFB)):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    for fx in (fixture_se, fixture_pe, fixture_crafted, fixture_bowtie_pe, fixture_built, fixture_eumacut):
+    for fx in (fixture_se, fixture_pe, fixture_crafted, fixture_bowtie_pe, fixture_built, fixture_eumacut, fixture_bigmod, fixture_config1):
         with tempfile.TemporaryDirectory() as tmp:
             fx(tmp)
             print("ok", fx.__name__)

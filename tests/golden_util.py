@@ -67,10 +67,27 @@ def parse_out_file(path):
         return [l.rstrip("\n").split("\t") for l in f][1:]
 
 
-def fpkm_tolerance(gold_fpkm, efflen, N, rounds):
-    """|x - m| <= max(1e-6 |m|, 1e-3 reads-equivalent, 6 s_t) (+ the file's print precision)."""
+PRINT_EPS = 5e-7          # the reference's files carry 6 decimals (%lf): a printed value is within 5e-7 of the number behind it
+
+
+def fpkm_tolerance(gold_fpkm, efflen, N, rounds, from_files=False):
+    """SURVEY.md §8(c) item 3 / north star: |x - m| <= max(1e-6 |m|, 1e-3 reads-equivalent, 6 s_t), nothing else - except that m (and s_t) are
+    read from a file with 6 decimals, so the rounding of the printed numbers (5e-7 each; twice that when x is read from a file too) is added."""
     m = gold_fpkm["fpkm"]
     s_t = gold_fpkm["sd"] * rounds            # the file stores sd / NUM_ROUND (:3200)
-    s_t = np.where(np.isfinite(s_t), s_t, 0.0)
+    s_t = np.where(np.isfinite(s_t), s_t + PRINT_EPS * rounds, 0.0)
     per_read = np.where(efflen > 0, 1e-3 / np.maximum(efflen / 1e3 * N / 1e6, 1e-300), np.inf)
-    return np.maximum(np.maximum(1e-6 * np.abs(m), 6 * s_t), per_read) + 2e-6
+    return np.maximum(np.maximum(1e-6 * np.abs(m), 6 * s_t), per_read) + PRINT_EPS * (2 if from_files else 1)
+
+
+def ireadcount_tolerance(tol_fpkm, efflen, N, from_files=False):
+    """iReadcount_t = iEUMA_t / 1e3 * FPKM_t * N / 1e6 (print_FPKMfinal :3203): the FPKM tolerance carried through that product."""
+    return np.where(efflen > 0, np.where(np.isfinite(tol_fpkm), tol_fpkm, 0.0) * (efflen / 1e3 * N / 1e6), 0.0) + PRINT_EPS * (2 if from_files else 1)
+
+
+def expected_tolerance(tol_fpkm, class_ptr, class_tid, adjEUMA, N, from_files=False):
+    """expected_Readcount_c = sum_{t in c} FPKM_t * adjEUMA_c / 1e3 * N / 1e6 (print_aEUMA_3 :2289-2296): the FPKM tolerances of the members
+    carried through that sum. Transcripts without a finite tolerance (no effective length) contribute through the class's own 1e-3 reads."""
+    t = np.where(np.isfinite(tol_fpkm), tol_fpkm, 0.0)
+    seg = np.add.reduceat(t[class_tid], np.asarray(class_ptr[:-1], dtype=np.int64))
+    return np.maximum(seg * (adjEUMA / 1e3 * N / 1e6), 1e-3) + PRINT_EPS * (2 if from_files else 1)
