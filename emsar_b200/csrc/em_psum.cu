@@ -41,84 +41,126 @@ template <bool RES> __device__ __forceinline__ uint32_t ps_ld32(const unsigned c
 
 __device__ __forceinline__ double ps_q_of(uint32_t r, double s) { return s > 0 ? fast_div((double)r, s) : 0.0; }
 
-// ---- staging: the index data of the NEXT tile / item of a warp travels from L2 / HBM into the warp's private staging buffer (cp.async)
-// while the warp works on the current one, so that a tile that is not resident costs no exposed round trip. One buffer per warp is enough:
-// a tile's words are pulled into registers first, then the buffer is handed to the next copy.
-constexpr int PS_STG = 1152;            // bytes per warp: 1 KB of index data + 128 bytes of read counts / destinations (small tiles: 512 + 512)
-__device__ __forceinline__ uint32_t ps_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ps_cp16(void *dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ps_smem_u32(dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void ps_cp4(void *dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ps_smem_u32(dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void ps_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ps_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ double ps_gather4(const double *a, uint2 w, double s)
-{
-    const double x0 = a[w.x & 0xffffu], x1 = a[w.x >> 16], x2 = a[w.y & 0xffffu], x3 = a[w.y >> 16];
-    s += x0; s += x1; s += x2; s += x3;            // member order
-    return s;
-}
-
-// members of a long tile / slice (more than 4 chunks per lane): chunk c of all lanes = 256 bytes; four loads kept in flight
+// ---- E-phase: one tile ----------------------------------------------------------------------------------------------------------------
 template <bool RES>
-__device__ __forceinline__ double ps_sum_chunks(const double *a, const unsigned char *sm, const unsigned char *g, int o8, int n4)
+__device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const unsigned char *gdat, const uint32_t *gR, int lane)
 {
-    uint2 w[4];
+    const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf;
+    const int off16 = t.z;
+    const double *th = v.theta;
+    if (lg == 0 && steps <= 4) {
+        const uint4 w = ps_ld128<RES>(v.cache, gdat, off16 + lane);
+        // read counts: behind the 512 bytes of index data in a resident copy, in the compact class array otherwise. They are fetched together
+        // with the members (one round trip to L2 for a tile that is not resident), for lanes beyond the tile's classes from a clamped index
+        const int r4 = off16 * 4 + 128, last = t.y - 1;
+        if (steps == 2) {
+            uint32_t r[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) w[u] = ps_ld64<RES>(sm, g, o8 + min(u, n4 - 1) * 32);
-    double s = 0;
-    for (int c = 0; c < n4; c += 4) {
+            for (int g = 0; g < 4; g++) { const int c = min(g * 32 + lane, last); r[g] = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c) : __ldg(gR + t.x + c); }
+            const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], b0 = th[w.y & 0xffffu], b1 = th[w.y >> 16];
+            const double c0 = th[w.z & 0xffffu], c1 = th[w.z >> 16], d0 = th[w.w & 0xffffu], d1 = th[w.w >> 16];
+            const double s[4] = {a0 + a1, b0 + b1, c0 + c1, d0 + d1};
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (c + u < n4) {
-                const uint2 cur = w[u];
-                if (c + u + 4 < n4) w[u] = ps_ld64<RES>(sm, g, o8 + (c + u + 4) * 32);
-                s = ps_gather4(a, cur, s);
+            for (int g = 0; g < 4; g++) {
+                const int c = g * 32 + lane;
+                if (c < t.y) v.q[t.x + c] = ps_q_of(r[g], s[g]);
             }
+        } else {
+            const int c0i = min(lane, last), c1i = min(32 + lane, last);
+            const uint32_t r0 = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c0i) : __ldg(gR + t.x + c0i);
+            const uint32_t r1 = RES ? ps_ld32<true>(v.cache, nullptr, r4 + c1i) : __ldg(gR + t.x + c1i);
+            const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], a2 = th[w.y & 0xffffu], a3 = th[w.y >> 16];
+            const double b0 = th[w.z & 0xffffu], b1 = th[w.z >> 16], b2 = th[w.w & 0xffffu], b3 = th[w.w >> 16];
+            double s0 = a0; s0 += a1; s0 += a2; s0 += a3;           // sequential member order (the pad slot holds 0.0)
+            double s1 = b0; s1 += b1; s1 += b2; s1 += b3;
+            if (lane < t.y) v.q[t.x + lane] = ps_q_of(r0, s0);
+            if (32 + lane < t.y) v.q[t.x + 32 + lane] = ps_q_of(r1, s1);
         }
+        return;
     }
-    return s;
+    // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
+    const int steps4 = (steps + 3) >> 2;
+    const int o8 = off16 * 2 + lane;
+    const int G = 1 << lg, cls = lane >> lg;
+    const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + min(cls, t.y - 1)) : __ldg(gR + t.x + min(cls, t.y - 1));
+    double s = 0;
+    int c = 0;
+    for (; c + 2 <= steps4; c += 2) {
+        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
+        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
+        const double x4 = th[w1.x & 0xffffu], x5 = th[w1.x >> 16], x6 = th[w1.y & 0xffffu], x7 = th[w1.y >> 16];
+        s += x0; s += x1; s += x2; s += x3; s += x4; s += x5; s += x6; s += x7;
+    }
+    if (c < steps4) {
+        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
+        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
+        s += x0; s += x1; s += x2; s += x3;
+    }
+    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((lane & (G - 1)) == 0 && cls < t.y) v.q[t.x + cls] = ps_q_of(r, s);
 }
 
+// ---- M-phase: one item (partial row sums over the CTA's own classes) ------------------------------------------------------------------------
 __device__ __forceinline__ void ps_emit(const PsParams &p, const PsView &v, uint32_t dst, double S, unsigned tag)
 {
     if (!(dst & PS_REMOTE)) v.Q[dst] = S;
     else ll_store(p.m.win[(dst >> 28) & 7u] + p.m.part_off + 16 * (size_t)(dst & 0x0fffffffu), S, tag);     // the row's owner collects it, in its rank
 }
 
-// a group of long rows: the warp reduces one row at a time (lane-strided partial sums, four loads in flight, fixed shuffle tree)
 template <bool RES>
-__device__ __forceinline__ void ps_m_group(const PsParams &p, const PsView &v, const int4 t, const unsigned char *gdat, int lane, unsigned tag)
+__device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, const int4 t, const unsigned char *gdat, int lane, unsigned tag)
 {
-    const int off16 = t.z, n = t.y;
+    const int len = t.w & 0x1fffffff;
+    const int off16 = t.z;
     const double *q = v.q;
-    const uint2 hw = lane < n ? ps_ld64<RES>(v.cache, gdat, off16 * 2 + lane) : make_uint2(0u, PS_NONE);      // {length, destination}
-    const int mywords = (int)((hw.x + 1) >> 1);
-    int start = mywords;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
-    start += ((2 * n + 3) & ~3) - mywords;             // exclusive prefix (32-bit words), behind the header
-    double mine = 0;
-    for (int r = 0; r < n; r++) {
-        const int a = off16 * 4 + __shfl_sync(0xffffffffu, start, r), W = __shfl_sync(0xffffffffu, mywords, r);
-        double s = 0;
-        int e = lane;
-        for (; e + 96 < W; e += 128) {
-            const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e), w1 = ps_ld32<RES>(v.cache, gdat, a + e + 32);
-            const uint32_t w2 = ps_ld32<RES>(v.cache, gdat, a + e + 64), w3 = ps_ld32<RES>(v.cache, gdat, a + e + 96);
-            const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16], x2 = q[w1 & 0xffffu], x3 = q[w1 >> 16];
-            const double x4 = q[w2 & 0xffffu], x5 = q[w2 >> 16], x6 = q[w3 & 0xffffu], x7 = q[w3 >> 16];
-            s += x0; s += x1; s += x2; s += x3; s += x4; s += x5; s += x6; s += x7;
+    if (((t.w >> 30) & 1) == 0) {
+        const uint32_t dst = ps_ld32<RES>(v.cache, gdat, off16 * 4 + lane);
+        const int len4 = (len + 3) >> 2;
+        const int o8 = off16 * 2 + 16 + lane;
+        double S = 0;
+        int c = 0;
+        for (; c + 2 <= len4; c += 2) {
+            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
+            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
+            const double x4 = q[w1.x & 0xffffu], x5 = q[w1.x >> 16], x6 = q[w1.y & 0xffffu], x7 = q[w1.y >> 16];
+            S += x0; S += x1; S += x2; S += x3; S += x4; S += x5; S += x6; S += x7;      // ascending class order
         }
-        for (; e < W; e += 32) {
-            const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e);
-            const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16];
-            s += x0; s += x1;
+        if (c < len4) {
+            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
+            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
+            S += x0; S += x1; S += x2; S += x3;
         }
+        if (dst != PS_NONE) ps_emit(p, v, dst, S, tag);
+    } else {
+        // a group of long rows: the warp reduces one row at a time (lane-strided partial sums, fixed shuffle tree), lane r keeps row r's sum
+        const int n = t.y;
+        const uint2 hw = lane < n ? ps_ld64<RES>(v.cache, gdat, off16 * 2 + lane) : make_uint2(0u, PS_NONE);      // {length, destination}
+        const int mywords = (int)((hw.x + 1) >> 1);
+        int start = mywords;
 #pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
-        if (lane == r) mine = s;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
+        start += ((2 * n + 3) & ~3) - mywords;             // exclusive prefix (32-bit words), behind the header
+        double mine = 0;
+        for (int r = 0; r < n; r++) {
+            const int a = off16 * 4 + __shfl_sync(0xffffffffu, start, r), W = __shfl_sync(0xffffffffu, mywords, r);
+            double s = 0;
+            int e = lane;
+            for (; e + 32 < W; e += 64) {
+                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e), w1 = ps_ld32<RES>(v.cache, gdat, a + e + 32);
+                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16], x2 = q[w1 & 0xffffu], x3 = q[w1 >> 16];
+                s += x0; s += x1; s += x2; s += x3;
+            }
+            if (e < W) {
+                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e);
+                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16];
+                s += x0; s += x1;
+            }
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
+            if (lane == r) mine = s;
+        }
+        if (lane < n) ps_emit(p, v, hw.y, mine, tag);
     }
-    if (lane < n) ps_emit(p, v, hw.y, mine, tag);
 }
 
 #define PS_TRACE(slot) do { if (p.trace && it == p.max_iter - 1 && threadIdx.x == 0) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
@@ -138,10 +180,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     const int hr0 = p.m.blk_hr0[b], nhr = p.m.blk_hr0[b + 1] - hr0;
     const int desc_smem = p.m.blk_desc_smem[b];
     const int in0 = p.m.inc_off[row0], nin = p.m.inc_off[row0 + nrows] - in0;       // partial sums this CTA receives per iteration
-    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls, nin, p.m.stage);
-    const bool stage_e = p.m.stage & 1, stage_m = p.m.stage & 2;
+    const PsPlan pl = ps_smem_plan(desc_smem, n_et, n_mi, nrows, nhr, ncls, nin, 0);
     double *const s_in = (double *)(sm_dyn + pl.off_in);
-    unsigned char *const stg = sm_dyn + pl.off_stg + PS_STG * warp;          // this warp's staging buffer
     PsView v;
     v.theta = (double *)(sm_dyn + pl.off_theta);
     v.q = (double *)(sm_dyn + pl.off_q);
@@ -215,156 +255,20 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
         __syncthreads();
         PS_TRACE(1);
-        {
-            // ---- E-phase: q_c = R_c / sum of theta over the members. Tiles come from the CTA's queue, heaviest first; a warp keeps the copy of
-            // its next tile and the descriptor of the one after in flight while it computes ----
-            auto e_desc = [&](int tk) -> int4 { return tk < n_et ? et[n_et - 1 - tk] : make_int4(0, 0, 0, 0); };
-            auto e_stage = [&](const int4 &t) {
-                const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf, s4 = (steps + 3) >> 2;
-                const bool small = lg == 0 && steps <= 4;
-                if (!stage_e || ((t.w >> 30) & 1) || (!small && s4 > 4)) return;            // resident, or too long for the buffer (read directly)
-                const int n16 = small ? 32 : 16 * s4;
-                const uint4 *src = (const uint4 *)p.m.e_data + t.z;
-                for (int j = lane; j < n16; j += 32) ps_cp16(stg + 16 * j, src + j);
-                for (int j = lane; j < t.y; j += 32) ps_cp4(stg + 16 * n16 + 4 * j, gR + t.x + j);
-                ps_cp_commit();
-            };
-            int tkA = next_item(&sm_ctr[0], lane);
-            int4 tA = e_desc(tkA);
-            if (tkA < n_et) e_stage(tA);
-            int tkB = tkA < n_et ? next_item(&sm_ctr[0], lane) : n_et;
-            int4 tB = e_desc(tkB);
-            while (tkA < n_et) {
-                const int steps = tA.w & 0xfff, lg = (tA.w >> 12) & 0xf, s4 = (steps + 3) >> 2;
-                const bool small = lg == 0 && steps <= 4, res = (tA.w >> 30) & 1, staged = stage_e && !res && (small || s4 <= 4);
-                const unsigned char *dsm = res ? v.cache + 16 * (size_t)tA.z : stg;     // where the tile's words are when they are in shared memory
-                int tkC = n_et;
-                int4 tC = make_int4(0, 0, 0, 0);
-                auto advance = [&]() {          // tile A's words sit in registers (or it does not use the buffer): start the copy of tile B, ask for C
-                    if (staged) __syncwarp();
-                    if (tkB < n_et) { e_stage(tB); tkC = next_item(&sm_ctr[0], lane); tC = e_desc(tkC); }
-                };
-                if (staged) { ps_cp_wait(); __syncwarp(); }
-                const double *th = v.theta;
-                const int last = tA.y - 1;
-                if (small) {
-                    const bool insm = res || staged;
-                    const uint4 w = insm ? *(const uint4 *)(dsm + 16 * lane) : __ldg((const uint4 *)p.m.e_data + tA.z + lane);
-                    const uint32_t *rr = insm ? (const uint32_t *)(dsm + 512) : gR + tA.x;      // read counts: behind the index data in shared memory, else the compact class array
-                    if (steps == 2) {
-                        uint32_t r[4];
-#pragma unroll
-                        for (int g = 0; g < 4; g++) r[g] = insm ? rr[min(g * 32 + lane, last)] : __ldg(rr + min(g * 32 + lane, last));
-                        advance();
-                        const double a0 = th[w.x & 0xffffu], a1 = th[w.x >> 16], b0 = th[w.y & 0xffffu], b1 = th[w.y >> 16];
-                        const double c0 = th[w.z & 0xffffu], c1 = th[w.z >> 16], d0 = th[w.w & 0xffffu], d1 = th[w.w >> 16];
-                        const double sum[4] = {a0 + a1, b0 + b1, c0 + c1, d0 + d1};
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const int c = g * 32 + lane;
-                            if (c < tA.y) v.q[tA.x + c] = ps_q_of(r[g], sum[g]);
-                        }
-                    } else {
-                        const uint32_t r0 = insm ? rr[min(lane, last)] : __ldg(rr + min(lane, last)), r1 = insm ? rr[min(32 + lane, last)] : __ldg(rr + min(32 + lane, last));
-                        advance();
-                        const double s0 = ps_gather4(th, make_uint2(w.x, w.y), 0.0), s1 = ps_gather4(th, make_uint2(w.z, w.w), 0.0);     // the pad slot of a 3-member class holds 0.0
-                        if (lane < tA.y) v.q[tA.x + lane] = ps_q_of(r0, s0);
-                        if (32 + lane < tA.y) v.q[tA.x + 32 + lane] = ps_q_of(r1, s1);
-                    }
-                } else {
-                    // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
-                    const int G = 1 << lg, cls = lane >> lg;
-                    double sum;
-                    uint32_t r;
-                    if (s4 <= 4 && (res || staged)) {
-                        uint2 w[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) w[u] = *(const uint2 *)(dsm + 256 * min(u, s4 - 1) + 8 * lane);
-                        r = ((const uint32_t *)(dsm + 256 * s4))[min(cls, last)];
-                        advance();
-                        sum = ps_gather4(th, w[0], 0.0);
-                        if (s4 > 1) sum = ps_gather4(th, w[1], sum);
-                        if (s4 > 2) sum = ps_gather4(th, w[2], sum);
-                        if (s4 > 3) sum = ps_gather4(th, w[3], sum);
-                    } else if (res) {
-                        advance();
-                        r = ((const uint32_t *)(dsm + 256 * s4))[min(cls, last)];
-                        sum = ps_sum_chunks<true>(th, v.cache, nullptr, tA.z * 2 + lane, s4);
-                    } else {
-                        r = __ldg(gR + tA.x + min(cls, last));
-                        advance();
-                        sum = ps_sum_chunks<false>(th, nullptr, p.m.e_data, tA.z * 2 + lane, s4);       // four chunk loads in flight from the start
-                    }
-                    for (int dd = G >> 1; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
-                    if ((lane & (G - 1)) == 0 && cls < tA.y) v.q[tA.x + cls] = ps_q_of(r, sum);
-                }
-                tkA = tkB; tA = tB; tkB = tkC; tB = tC;
-            }
+        for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+            const int4 t = et[n_et - 1 - tk];                   // tiles are ordered by cardinality: heaviest first
+            if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
+            else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
         }
         PS_TRACE(2);
         if (it > 0) {
             d = read_dm(it - 1);
             if (*((volatile int *)p.abort_flag) != 0 || (p.stop_on_conv && d <= 1.0)) { stopped = true; break; }
         } else __syncthreads();
-        {
-            // ---- M-phase: partial row sums over the CTA's own classes; items longest first, same look-ahead as the E-phase ----
-            auto m_desc = [&](int tk) -> int4 { return tk < n_mi ? mi[tk] : make_int4(0, 0, 0, 0); };
-            auto m_stage = [&](const int4 &t) {
-                const int len4 = ((t.w & 0x1fffffff) + 3) >> 2;
-                if (!stage_m || ((t.w >> 29) & 1) || ((t.w >> 30) & 1) || len4 > 4) return;   // resident, a group of long rows, or a slice too long for the buffer
-                const int n16 = 8 + 16 * len4;
-                const uint4 *src = (const uint4 *)p.m.m_data + t.z;
-                for (int j = lane; j < n16; j += 32) ps_cp16(stg + 16 * j, src + j);
-                ps_cp_commit();
-            };
-            int tkA = next_item(&sm_ctr[1], lane);
-            int4 tA = m_desc(tkA);
-            if (tkA < n_mi) m_stage(tA);
-            int tkB = tkA < n_mi ? next_item(&sm_ctr[1], lane) : n_mi;
-            int4 tB = m_desc(tkB);
-            while (tkA < n_mi) {
-                const int len4 = ((tA.w & 0x1fffffff) + 3) >> 2;
-                const bool res = (tA.w >> 29) & 1, group = (tA.w >> 30) & 1, staged = stage_m && !res && !group && len4 <= 4;
-                const unsigned char *dsm = res ? v.cache + 16 * (size_t)tA.z : stg;
-                int tkC = n_mi;
-                int4 tC = make_int4(0, 0, 0, 0);
-                auto advance = [&]() {
-                    if (staged) __syncwarp();
-                    if (tkB < n_mi) { m_stage(tB); tkC = next_item(&sm_ctr[1], lane); tC = m_desc(tkC); }
-                };
-                if (staged) { ps_cp_wait(); __syncwarp(); }
-                if (group) {
-                    advance();
-                    if (res) ps_m_group<true>(p, v, tA, nullptr, lane, tag);
-                    else ps_m_group<false>(p, v, tA, p.m.m_data, lane, tag);
-                } else {
-                    // a slice of 32 rows: 32 destinations, then chunks of 4 entries per lane
-                    const double *q = v.q;
-                    uint32_t dst;
-                    double S;
-                    if (len4 <= 4 && (res || staged)) {
-                        uint2 w[4];
-                        dst = ((const uint32_t *)dsm)[lane];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) w[u] = *(const uint2 *)(dsm + 128 + 256 * min(u, len4 - 1) + 8 * lane);
-                        advance();
-                        S = ps_gather4(q, w[0], 0.0);                  // ascending class order
-                        if (len4 > 1) S = ps_gather4(q, w[1], S);
-                        if (len4 > 2) S = ps_gather4(q, w[2], S);
-                        if (len4 > 3) S = ps_gather4(q, w[3], S);
-                    } else if (res) {
-                        advance();
-                        dst = ((const uint32_t *)dsm)[lane];
-                        S = ps_sum_chunks<true>(q, v.cache, nullptr, tA.z * 2 + 16 + lane, len4);
-                    } else {
-                        dst = __ldg((const uint32_t *)p.m.m_data + (size_t)tA.z * 4 + lane);
-                        advance();
-                        S = ps_sum_chunks<false>(q, nullptr, p.m.m_data, tA.z * 2 + 16 + lane, len4);
-                    }
-                    if (dst != PS_NONE) ps_emit(p, v, dst, S, tag);
-                }
-                tkA = tkB; tA = tB; tkB = tkC; tB = tC;
-            }
+        for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+            const int4 t = mi[tk];                              // items are ordered longest first
+            if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
+            else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
         }
         __syncthreads();
         PS_TRACE(3);

@@ -556,7 +556,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
     for (int i = 0; i < n_mitems; i++) { h_msrc[(size_t)i] = h_mi[(size_t)i].z; if ((h_mi[(size_t)i].w >> 30) & 1) rows_long += h_mi[(size_t)i].y; }
     // look-ahead staging of the items that are not resident (E tiles: bit 0, M items: bit 1; EMSAR_PS_STAGE overrides). It costs 36 KB of
     // shared memory per CTA, so it is dropped when the state would not fit beside it.
-    int stage = getenv("EMSAR_PS_STAGE") ? atoi(getenv("EMSAR_PS_STAGE")) & 3 : 2;
+    int stage = 0;      // measured (profiles/r2h): routing the index words through shared memory costs more LSU work than the hidden latency is worth
     for (int pass = 0; pass < 2; pass++) {
         bool ok = true;
         for (int b = 0; b < B && ok; b++) {
