@@ -41,6 +41,35 @@ template <bool RES> __device__ __forceinline__ uint32_t ps_ld32(const unsigned c
 
 __device__ __forceinline__ double ps_q_of(uint32_t r, double s) { return s > 0 ? fast_div((double)r, s) : 0.0; }
 
+__device__ __forceinline__ double ps_gather4(const double *a, uint2 w, double s)
+{
+    const double x0 = a[w.x & 0xffffu], x1 = a[w.x >> 16], x2 = a[w.y & 0xffffu], x3 = a[w.y >> 16];
+    s += x0; s += x1; s += x2; s += x3;            // member order
+    return s;
+}
+
+// the chunks of one lane (chunk c of all lanes = 256 bytes), four loads kept in flight: index data that is not resident comes from L2 or,
+// for a model larger than L2, from HBM, and a lane that waits for every chunk in turn leaves the memory system idle
+template <bool RES>
+__device__ __forceinline__ double ps_sum_chunks(const double *a, const unsigned char *sm, const unsigned char *g, int o8, int n4)
+{
+    uint2 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) w[u] = ps_ld64<RES>(sm, g, o8 + min(u, n4 - 1) * 32);
+    double s = 0;
+    for (int c = 0; c < n4; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (c + u < n4) {
+                const uint2 cur = w[u];
+                if (c + u + 4 < n4) w[u] = ps_ld64<RES>(sm, g, o8 + (c + u + 4) * 32);
+                s = ps_gather4(a, cur, s);
+            }
+        }
+    }
+    return s;
+}
+
 // ---- E-phase: one tile ----------------------------------------------------------------------------------------------------------------
 template <bool RES>
 __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const unsigned char *gdat, const uint32_t *gR, int lane)
@@ -80,22 +109,9 @@ __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const u
     }
     // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
     const int steps4 = (steps + 3) >> 2;
-    const int o8 = off16 * 2 + lane;
     const int G = 1 << lg, cls = lane >> lg;
     const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + min(cls, t.y - 1)) : __ldg(gR + t.x + min(cls, t.y - 1));
-    double s = 0;
-    int c = 0;
-    for (; c + 2 <= steps4; c += 2) {
-        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
-        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
-        const double x4 = th[w1.x & 0xffffu], x5 = th[w1.x >> 16], x6 = th[w1.y & 0xffffu], x7 = th[w1.y >> 16];
-        s += x0; s += x1; s += x2; s += x3; s += x4; s += x5; s += x6; s += x7;
-    }
-    if (c < steps4) {
-        const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
-        const double x0 = th[w0.x & 0xffffu], x1 = th[w0.x >> 16], x2 = th[w0.y & 0xffffu], x3 = th[w0.y >> 16];
-        s += x0; s += x1; s += x2; s += x3;
-    }
+    double s = ps_sum_chunks<RES>(th, v.cache, gdat, off16 * 2 + lane, steps4);
     for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if ((lane & (G - 1)) == 0 && cls < t.y) v.q[t.x + cls] = ps_q_of(r, s);
 }
@@ -115,49 +131,50 @@ __device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, co
     const double *q = v.q;
     if (((t.w >> 30) & 1) == 0) {
         const uint32_t dst = ps_ld32<RES>(v.cache, gdat, off16 * 4 + lane);
-        const int len4 = (len + 3) >> 2;
-        const int o8 = off16 * 2 + 16 + lane;
-        double S = 0;
-        int c = 0;
-        for (; c + 2 <= len4; c += 2) {
-            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32), w1 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32 + 32);
-            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
-            const double x4 = q[w1.x & 0xffffu], x5 = q[w1.x >> 16], x6 = q[w1.y & 0xffffu], x7 = q[w1.y >> 16];
-            S += x0; S += x1; S += x2; S += x3; S += x4; S += x5; S += x6; S += x7;      // ascending class order
-        }
-        if (c < len4) {
-            const uint2 w0 = ps_ld64<RES>(v.cache, gdat, o8 + c * 32);
-            const double x0 = q[w0.x & 0xffffu], x1 = q[w0.x >> 16], x2 = q[w0.y & 0xffffu], x3 = q[w0.y >> 16];
-            S += x0; S += x1; S += x2; S += x3;
-        }
+        const double S = ps_sum_chunks<RES>(q, v.cache, gdat, off16 * 2 + 16 + lane, (len + 3) >> 2);      // ascending class order
         if (dst != PS_NONE) ps_emit(p, v, dst, S, tag);
     } else {
-        // a group of long rows: the warp reduces one row at a time (lane-strided partial sums, fixed shuffle tree), lane r keeps row r's sum
-        const int n = t.y;
+        // a group of long rows, stored back to back: the warp streams the group's 32-bit words (two entries each) with eight loads per lane in
+        // flight - header and first words are requested together - and closes a row where it ends: lane-strided partial sums, fixed shuffle
+        // tree, lane r keeps row r's sum. A long row has more than 32 words, so at most one row ends inside a block of 32 words.
+        const int n = t.y, hdr = (2 * n + 3) & ~3;
+        const int base4 = off16 * 4 + hdr, Wt = t.x * 4 - hdr;           // the tail of the last 16 bytes is padded with zero-q pairs
+        const int nch = (Wt + 31) >> 5;
+        const uint32_t zz = (uint32_t)v.ncls | ((uint32_t)v.ncls << 16);
         const uint2 hw = lane < n ? ps_ld64<RES>(v.cache, gdat, off16 * 2 + lane) : make_uint2(0u, PS_NONE);      // {length, destination}
+        uint32_t ring[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) ring[u] = (u * 32 + lane < Wt) ? ps_ld32<RES>(v.cache, gdat, base4 + u * 32 + lane) : zz;
         const int mywords = (int)((hw.x + 1) >> 1);
         int start = mywords;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, start, o); if (lane >= o) start += y; }
-        start += ((2 * n + 3) & ~3) - mywords;             // exclusive prefix (32-bit words), behind the header
-        double mine = 0;
-        for (int r = 0; r < n; r++) {
-            const int a = off16 * 4 + __shfl_sync(0xffffffffu, start, r), W = __shfl_sync(0xffffffffu, mywords, r);
-            double s = 0;
-            int e = lane;
-            for (; e + 32 < W; e += 64) {
-                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e), w1 = ps_ld32<RES>(v.cache, gdat, a + e + 32);
-                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16], x2 = q[w1 & 0xffffu], x3 = q[w1 >> 16];
-                s += x0; s += x1; s += x2; s += x3;
-            }
-            if (e < W) {
-                const uint32_t w0 = ps_ld32<RES>(v.cache, gdat, a + e);
-                const double x0 = q[w0 & 0xffffu], x1 = q[w0 >> 16];
-                s += x0; s += x1;
-            }
+        start -= mywords;                                  // exclusive prefix: first word of the lane's row
+        int r = 0, end_r = __shfl_sync(0xffffffffu, start, 0) + __shfl_sync(0xffffffffu, mywords, 0);
+        double acc = 0, mine = 0;
+        for (int c = 0; c < nch; c += 8) {
 #pragma unroll
-            for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
-            if (lane == r) mine = s;
+            for (int u = 0; u < 8; u++) {
+                if (c + u < nch) {
+                    const uint32_t cur = ring[u];
+                    const int nx = (c + u + 8) * 32 + lane;
+                    if (c + u + 8 < nch) ring[u] = nx < Wt ? ps_ld32<RES>(v.cache, gdat, base4 + nx) : zz;
+                    const double x0 = q[cur & 0xffffu], x1 = q[cur >> 16];
+                    if (r < n && end_r <= (c + u) * 32 + 32) {             // row r ends inside this block of words (warp-uniform)
+                        const bool in_r = (c + u) * 32 + lane < end_r;
+                        double sum = acc;
+                        if (in_r) { sum += x0; sum += x1; }
+#pragma unroll
+                        for (int dd = 16; dd > 0; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+                        if (lane == r) mine = sum;
+                        acc = 0;
+                        if (!in_r) { acc += x0; acc += x1; }
+                        r++;
+                        const int rr = min(r, n - 1);
+                        end_r = __shfl_sync(0xffffffffu, start, rr) + __shfl_sync(0xffffffffu, mywords, rr);
+                    } else { acc += x0; acc += x1; }
+                }
+            }
         }
         if (lane < n) ps_emit(p, v, hw.y, mine, tag);
     }
@@ -255,20 +272,45 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
         __syncthreads();
         PS_TRACE(1);
-        for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
-            const int4 t = et[n_et - 1 - tk];                   // tiles are ordered by cardinality: heaviest first
-            if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
-            else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
+        if (desc_smem) {
+            for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
+                const int4 t = et[n_et - 1 - tk];               // tiles are ordered by cardinality: heaviest first
+                if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
+                else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
+            }
+        } else {
+            // descriptors in global memory (many tiles): the next ticket's descriptor is requested before the current tile is processed
+            int tk = next_item(&sm_ctr[0], lane);
+            int4 t = tk < n_et ? __ldg(et + (n_et - 1 - tk)) : make_int4(0, 0, 0, 0);
+            while (tk < n_et) {
+                const int tk2 = next_item(&sm_ctr[0], lane);
+                const int4 t2 = tk2 < n_et ? __ldg(et + (n_et - 1 - tk2)) : make_int4(0, 0, 0, 0);
+                if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
+                else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
+                tk = tk2; t = t2;
+            }
         }
         PS_TRACE(2);
         if (it > 0) {
             d = read_dm(it - 1);
             if (*((volatile int *)p.abort_flag) != 0 || (p.stop_on_conv && d <= 1.0)) { stopped = true; break; }
         } else __syncthreads();
-        for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
-            const int4 t = mi[tk];                              // items are ordered longest first
-            if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
-            else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
+        if (desc_smem) {
+            for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
+                const int4 t = mi[tk];                          // items are ordered longest first
+                if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
+                else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
+            }
+        } else {
+            int tk = next_item(&sm_ctr[1], lane);
+            int4 t = tk < n_mi ? __ldg(mi + tk) : make_int4(0, 0, 0, 0);
+            while (tk < n_mi) {
+                const int tk2 = next_item(&sm_ctr[1], lane);
+                const int4 t2 = tk2 < n_mi ? __ldg(mi + tk2) : make_int4(0, 0, 0, 0);
+                if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
+                else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
+                tk = tk2; t = t2;
+            }
         }
         __syncthreads();
         PS_TRACE(3);

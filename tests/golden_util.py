@@ -17,6 +17,9 @@ FIXTURES = {
     "built": dict(aln="built.in.sam", rsh="built.in.rsh", fmt="sam", pe=False, strand="ssf", k=100, out="built", rounds=8),
     # two sequence-sharing sets of ~700 transcripts: the reference's rounds visibly disagree here (the 6 sd term of the tolerance policy)
     "bigmod": dict(aln="bigmod.in.bowtie", rsh="bigmod.in.rsh", fmt="bowtie", pe=False, strand="ns", k=100, out="bigmod", rounds=8),
+    # substitute of BASELINE configs[0] (the bundled Vicugna PE sample is absent): index by the reference's emsar-build -P on a generated
+    # 2K-transcript fasta, 100K simulated PE fragments as SAM
+    "config1": dict(aln="config1.in.sam", rsh="config1.in.rsh", fmt="sam", pe=True, strand="ns", k=100, out="config1", rounds=8),
     "bowtie_pe_ns": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ns", k=100, out="bowtie_pe_ns", rounds=2),
     "bowtie_pe_ssfr": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ssfr", k=100, out="bowtie_pe_ssfr", rounds=2),
     "bowtie_pe_ssrf": dict(aln="bowtie_pe.in.bowtie", rsh="bowtie_pe.in.rsh", fmt="bowtie", pe=True, strand="ssrf", k=100, out="bowtie_pe_ssrf", rounds=2),
@@ -29,6 +32,10 @@ def materialize(name, tmpdir):
     dst = os.path.join(str(tmpdir), name)
     if os.path.exists(src):
         shutil.copy(src, dst)
+    elif os.path.exists(src + ".xz"):
+        import lzma
+        with lzma.open(src + ".xz", "rb") as f, open(dst, "wb") as g:
+            shutil.copyfileobj(f, g)
     else:
         with gzip.open(src + ".gz", "rb") as f, open(dst, "wb") as g:
             shutil.copyfileobj(f, g)
