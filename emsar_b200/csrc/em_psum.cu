@@ -55,7 +55,7 @@ __device__ __forceinline__ double ps_sum_chunks(const double *a, const unsigned 
 {
     uint2 w[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) w[u] = ps_ld64<RES>(sm, g, o8 + min(u, n4 - 1) * 32);
+    for (int u = 0; u < 4; u++) w[u] = u < n4 ? ps_ld64<RES>(sm, g, o8 + u * 32) : make_uint2(0u, 0u);
     double s = 0;
     for (int c = 0; c < n4; c += 4) {
 #pragma unroll
@@ -110,10 +110,39 @@ __device__ __forceinline__ void ps_e_tile(const PsView &v, const int4 t, const u
     // G = 1 << lg lanes per class; a lane's members come in chunks of 4 (chunk c of all lanes = 256 bytes)
     const int steps4 = (steps + 3) >> 2;
     const int G = 1 << lg, cls = lane >> lg;
-    const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + min(cls, t.y - 1)) : __ldg(gR + t.x + min(cls, t.y - 1));
-    double s = ps_sum_chunks<RES>(th, v.cache, gdat, off16 * 2 + lane, steps4);
-    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((lane & (G - 1)) == 0 && cls < t.y) v.q[t.x + cls] = ps_q_of(r, s);
+    if (lg == 0) {
+        const uint32_t r = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + steps4 * 64 + min(cls, t.y - 1)) : __ldg(gR + t.x + min(cls, t.y - 1));
+        const double s = ps_sum_chunks<RES>(th, v.cache, gdat, off16 * 2 + lane, steps4);
+        if (cls < t.y) v.q[t.x + cls] = ps_q_of(r, s);
+        return;
+    }
+    // several lanes per class: the tile covers nb consecutive row blocks (32 / G classes each, at most 64 classes in all), streamed as one run of
+    // chunks with four loads in flight. Lane l fetches the read counts of classes l and 32 + l up front; a block's heads get theirs by shuffle.
+    const int nb = max(1, (t.w >> 16) & 0xff), n4 = nb * steps4, cpb = 32 >> lg, o8 = off16 * 2 + lane;
+    const uint32_t ra = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + n4 * 64 + min(lane, t.y - 1)) : __ldg(gR + t.x + min(lane, t.y - 1));
+    const uint32_t rb = RES ? ps_ld32<true>(v.cache, nullptr, off16 * 4 + n4 * 64 + min(32 + lane, t.y - 1)) : __ldg(gR + t.x + min(32 + lane, t.y - 1));
+    uint2 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) w[u] = ps_ld64<RES>(v.cache, gdat, o8 + min(u, n4 - 1) * 32);
+    double s = 0;
+    int left = steps4, blk = 0;                // chunks left in the current block
+    for (int c = 0; c < n4; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (c + u < n4) {
+                const uint2 cur = w[u];
+                if (c + u + 4 < n4) w[u] = ps_ld64<RES>(v.cache, gdat, o8 + (c + u + 4) * 32);
+                s = ps_gather4(th, cur, s);
+                if (--left == 0) {              // the block is complete: one class per group of G lanes
+                    for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                    const int ci = blk * cpb + cls;
+                    const uint32_t r = __shfl_sync(0xffffffffu, ci < 32 ? ra : rb, ci & 31);
+                    if ((lane & (G - 1)) == 0 && ci < t.y) v.q[t.x + ci] = ps_q_of(r, s);
+                    s = 0; left = steps4; blk++;
+                }
+            }
+        }
+    }
 }
 
 // ---- M-phase: one item (partial row sums over the CTA's own classes) ------------------------------------------------------------------------
@@ -222,7 +251,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             const int4 t = p.m.e_tiles[et0 + i];
             if (!((t.w >> 30) & 1)) continue;
             const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf;
-            const int n16 = (lg == 0 && steps <= 4) ? 32 : 16 * ((steps + 3) >> 2);
+            const int n16 = (lg == 0 && steps <= 4) ? 32 : 16 * ((steps + 3) >> 2) * max(1, (t.w >> 16) & 0xff);
             const uint4 *src = (const uint4 *)p.m.e_data + p.m.e_src[et0 + i];
             uint4 *dst = (uint4 *)cache + t.z;
             for (int j = lane; j < n16; j += 32) dst[j] = __ldg(src + j);

@@ -19,10 +19,10 @@ __global__ void k_ps_cell_sizes(int n_cells, int n_kseg, const int32_t *__restri
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_cells) return;
     if (c == n_cells) { cell_u16[c] = 0; cell_tiles[c] = 0; return; }
-    const int k = kseg_k[c % n_kseg], cnt = cell_cnt[c], cpt = e_cls_per_tile(k);
-    const int nt = (cnt + cpt - 1) / cpt;
-    cell_tiles[c] = nt;
-    cell_u16[c] = (uint32_t)nt * (uint32_t)ps_tile_u16(k);
+    const int k = kseg_k[c % n_kseg], cnt = cell_cnt[c], cpt = e_cls_per_tile(k), nbt = ps_blocks_per_tile(k);
+    const int nblk = (cnt + cpt - 1) / cpt;                 // row blocks (for cardinality <= 4: tiles of 128 / 64 classes)
+    cell_tiles[c] = (nblk + nbt - 1) / nbt;
+    cell_u16[c] = (uint32_t)nblk * (uint32_t)ps_tile_u16(k);
 }
 
 __global__ void k_ps_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t *__restrict__ kseg_k, const int32_t *__restrict__ tilebase,
@@ -33,12 +33,13 @@ __global__ void k_ps_etiles(int n_tiles, int n_cells, int n_kseg, const int32_t 
     if (g >= n_tiles) return;
     int lo = 0, hi = n_cells - 1;      // largest cell with tilebase[cell] <= g (non-empty by construction)
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tilebase[mid] <= g) lo = mid; else hi = mid - 1; }
-    const int c = lo, k = kseg_k[c % n_kseg], cpt = e_cls_per_tile(k), lt = g - tilebase[c], b = c / n_kseg;
+    const int c = lo, k = kseg_k[c % n_kseg], cpt = e_cls_per_tile(k), nbt = ps_blocks_per_tile(k), lt = g - tilebase[c], b = c / n_kseg;
+    const int nblk = (cell_cnt[c] + cpt - 1) / cpt, nb = min(nbt, nblk - lt * nbt);
     int4 t;
-    t.x = clsbase[c] + lt * cpt - cls0[b];                    // local class id
-    t.y = min(cpt, cell_cnt[c] - lt * cpt);
-    t.z = (int)((u16base[c] + (uint32_t)lt * (uint32_t)ps_tile_u16(k)) >> 3);      // 16-byte units
-    t.w = e_steps(k) | (e_lgG(k) << 12);
+    t.x = clsbase[c] + lt * nbt * cpt - cls0[b];              // local class id
+    t.y = min(nb * cpt, cell_cnt[c] - lt * nbt * cpt);
+    t.z = (int)((u16base[c] + (uint32_t)(lt * nbt) * (uint32_t)ps_tile_u16(k)) >> 3);      // 16-byte units
+    t.w = e_steps(k) | (e_lgG(k) << 12) | (nb << 16);
     tiles[g] = t;
 }
 
@@ -587,7 +588,7 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
         for (int i = h_et0[b]; i < h_et0[b + 1]; i++) {
             const int4 t = h_et[(size_t)i];
             const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf;
-            const int d16 = (lg == 0 && steps <= 4) ? 32 : 16 * ((steps + 3) >> 2);
+            const int d16 = (lg == 0 && steps <= 4) ? 32 : 16 * ((steps + 3) >> 2) * max(1, (t.w >> 16) & 0xff);
             cand.push_back({(lg == 0 && steps <= 4) ? 2 : steps, d16 + (t.y * 4 + 15) / 16, i, true});       // index data + read counts
         }
         for (int i = h_mi0[b]; i < h_mi0[b + 1]; i++) {

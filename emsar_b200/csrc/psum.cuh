@@ -22,6 +22,10 @@ constexpr int PS_MAX_SLOT = 65534;         // 0xFFFF marks an unused lane of an 
 // chunk c of all 32 lanes is one 256-byte block. Entries beyond the cardinality point at the zero-theta slot.
 __host__ __device__ __forceinline__ int ps_steps4(int k) { return (e_steps(k) + 3) >> 2; }
 __host__ __device__ __forceinline__ int ps_tile_u16(int k) { return k <= 4 ? 256 : 128 * ps_steps4(k); }      // 16-bit words of index data per tile
+// Tiles of classes that share lanes (cardinality > 16) cover up to PS_NB consecutive row blocks of their cell, which the warp streams as one
+// run of chunks: the latency of the first load is paid once per tile, not once per 1 - 8 classes.
+constexpr int PS_NB = 8;
+__host__ __device__ __forceinline__ int ps_blocks_per_tile(int k) { return e_lgG(k) > 0 ? PS_NB : 1; }
 // a resident copy of a tile (shared memory) carries its read counts right behind the index data
 
 // ---- M side -------------------------------------------------------------------------------------------------------------------------
