@@ -360,20 +360,21 @@ def m64_leg(ctx, ix, idx, workload, rank, world, torch, dist, per_gpu):
     bufs = []
     for j in mine:
         rd = make_reads(workload, idx, seed=1000 + j, n_reads=int(sizes[j]))
-        bufs.append((j, torch.from_numpy(rd.read_ptr).pin_memory(), torch.from_numpy(rd.read_tid).pin_memory(), torch.from_numpy(rd.read_fraglen).pin_memory()))
+        bufs.append((j, torch.from_numpy(np.diff(rd.read_ptr).astype(np.uint16)).pin_memory(), torch.from_numpy(rd.read_tid).pin_memory(),
+                     None if idx.nF == 1 else torch.from_numpy(rd.read_fraglen.astype(np.uint16)).pin_memory(), int(rd.read_fraglen[0])))
         del rd
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     iters, h2d, chk = 0, 0, 0.0
-    for j, p, t, f in bufs:
+    for j, p, t, f, f0 in bufs:
         s = ix.sample()
-        s.count(p, t, f)
+        s.count_compact(p, t, f, f0)                     # the compact wire form: uint16 lengths, tids, uint16 / no fragment lengths
         r = s.solve()
         s.close()
         iters += int(r["n_iter"])
-        h2d += p.numel() * 8 + t.numel() * 4 + f.numel() * 4
+        h2d += p.numel() * 2 + t.numel() * 4 + (0 if f is None else f.numel() * 2)
         chk += float(r["tpm"].sum())
         assert r["final_delta"] <= 1.0
     ctx.synchronize()
@@ -507,13 +508,19 @@ def main():
     ctx = Context(local)
     ix = Index(ctx, idx)
     # pinned host copies of this rank's read lists (the e2e leg copies them every step)
-    h_ptr = torch.from_numpy(reads.read_ptr).pin_memory()
+    # the compact wire form of the C ABI (emsar_sample_count_compact): uint16 lengths, int32 tids, uint16 fragment lengths (none for one length)
+    one_fl = idx.nF == 1
+    h_len = torch.from_numpy(np.diff(reads.read_ptr).astype(np.uint16)).pin_memory()
     h_tid = torch.from_numpy(reads.read_tid).pin_memory()
-    h_fl = torch.from_numpy(reads.read_fraglen).pin_memory()
-    h2d_bytes = h_ptr.numel() * 8 + h_tid.numel() * 4 + h_fl.numel() * 4
+    h_fl = None if one_fl else torch.from_numpy(reads.read_fraglen.astype(np.uint16)).pin_memory()
+    fl0 = int(reads.read_fraglen[0])
+    h2d_bytes = h_len.numel() * 2 + h_tid.numel() * 4 + (0 if one_fl else h_fl.numel() * 2)
+
+    def count(s_):
+        s_.count_compact(h_len, h_tid, h_fl, fl0)
 
     def load(s_):
-        s_.count(h_ptr, h_tid, h_fl)
+        count(s_)
         s_.prepare()
 
     smp = ix.sample()            # resident sample for the device-timed leg
@@ -584,7 +591,7 @@ def main():
         barrier()
         c0 = time.perf_counter()
         s = ix.sample()
-        s.count(h_ptr, h_tid, h_fl)
+        count(s)
         r = s.solve()
         s.close()
         c1 = time.perf_counter()
@@ -635,7 +642,7 @@ def main():
     n_reads_sample = len(reads.read_fraglen)
     smp.close()
     ix.close()
-    del h_ptr, h_tid, h_fl
+    del h_len, h_tid, h_fl
     if not args.no_extras and world > 1:
         ctx.comm_init_torch()
         extras["class_sharded"] = []

@@ -153,6 +153,20 @@ class Sample:
         rp, rt, fl = _np(read_ptr, np.int64), _np(read_tid, np.int32), _np(read_fraglen, np.int32)
         L.check(L.lib().emsar_sample_count(self._h, C.c_int64(len(rp) - 1), _ptr(rp), _ptr(rt), _ptr(fl)), "emsar_sample_count")
 
+    def count_compact(self, read_len, read_tid, read_fraglen=None, const_fraglen=0):
+        """The compact wire form: uint16 lengths, int32 tids, uint16 fragment lengths or None (every group has `const_fraglen`).
+        numpy arrays or pinned torch CPU tensors."""
+        def ptr(a):
+            return C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else _ptr(a)
+        n = int(read_len.numel()) if hasattr(read_len, "numel") else len(read_len)
+        if not hasattr(read_len, "data_ptr"):
+            read_len, read_tid = _np(read_len, np.uint16), _np(read_tid, np.int32)
+            read_fraglen = _np(read_fraglen, np.uint16) if read_fraglen is not None else None
+        nt = int(read_tid.numel()) if hasattr(read_tid, "numel") else len(read_tid)
+        L.check(L.lib().emsar_sample_count_compact(self._h, C.c_int64(n), C.c_int64(nt), ptr(read_len), ptr(read_tid),
+                                                   ptr(read_fraglen) if read_fraglen is not None else None, C.c_int32(int(const_fraglen))),
+                "emsar_sample_count_compact")
+
     def set_counts(self, ReadCount, FraglengthCounts):
         R, F = _np(ReadCount, np.int32), _np(FraglengthCounts, np.int32)
         assert len(R) == self.index.C and len(F) == self.index.max_fraglength + 1

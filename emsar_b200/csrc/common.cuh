@@ -182,8 +182,8 @@ struct emsar_sample {
     int32_t *d_flags;      // [0] error flags raised by kernels
     bool have_counts;
     // staging for host read batches (grow-only)
-    void *d_rd_ptr, *d_rd_tid, *d_rd_fl;
-    size_t cap_rd_ptr, cap_rd_tid, cap_rd_fl;
+    void *d_rd_ptr, *d_rd_tid, *d_rd_fl, *d_rd_aux;
+    size_t cap_rd_ptr, cap_rd_tid, cap_rd_fl, cap_rd_aux;
     cudaEvent_t count_ev[4];   // "host arrays of batch k are free again" (emsar_sample_count_wait)
     unsigned count_seq;
     // model

@@ -3,6 +3,7 @@
 // update_rshbucket_single 'r' (:1528-1536) and update_rshbucket 'r' (:1597-1624, cmptarr :1677-1684),
 // clear_readcounts_in_rshbucket (:1726-1752) and the FraglengthCounts / TotalReadCount bookkeeping (:940-941).
 #include <limits.h>
+#include <cub/cub.cuh>
 
 #include "common.cuh"
 
@@ -26,6 +27,7 @@ struct CountParams {
     int32_t *R;
     int32_t *hist;
     int32_t *flags;
+    int64_t n_tids;          // size of rd_tid when the caller states it (compact form: offsets are rebuilt from lengths), else INT64_MAX
 };
 
 #define CE(a, b) { int lo_ = min(v[a], v[b]); int hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(CNT_BLOCK) k_count(CountParams p)
             int64_t k64 = p.rd_ptr[r + 1] - off;
             fl = p.rd_fl[r];
             if (k64 > EMSAR_MAX_READ_TIDS) { atomicOr(p.flags, 1); k64 = 0; }
+            if (off + k64 > p.n_tids) { atomicOr(p.flags, 4); k64 = 0; }          // lengths and tid count of a compact batch disagree
             k = (int)k64;
             ok = k > 0 && fl <= p.max_fl && fl >= p.min_fl;          // :849
         }
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(CNT_BLOCK) k_count(CountParams p)
     }
 }
 
-static int launch_count(emsar_sample *s, int64_t n_reads, const int64_t *d_ptr, const int32_t *d_tid, const int32_t *d_fl)
+static int launch_count(emsar_sample *s, int64_t n_reads, const int64_t *d_ptr, const int32_t *d_tid, const int32_t *d_fl, int64_t n_tids = INT64_MAX)
 {
     emsar_index *ix = s->index;
     emsar_ctx *ctx = s->ctx;
@@ -182,7 +185,7 @@ static int launch_count(emsar_sample *s, int64_t n_reads, const int64_t *d_ptr, 
     p.n_reads = n_reads; p.rd_ptr = d_ptr; p.rd_tid = d_tid; p.rd_fl = d_fl;
     p.T = ix->T; p.cls_off = ix->d_cls_off; p.cls_tid = ix->d_cls_tid; p.has_node = ix->d_has_node;
     p.hash = ix->d_hash; p.hash_mask = ix->hash_mask; p.max_t_size = ix->max_t_size; p.min_fl = ix->min_fl; p.max_fl = ix->max_fl;
-    p.R = s->d_R; p.hist = s->d_hist; p.flags = s->d_flags;
+    p.R = s->d_R; p.hist = s->d_hist; p.flags = s->d_flags; p.n_tids = n_tids;
     int64_t chunks = (n_reads + 31) / 32;
     int64_t blocks = (chunks + CNT_WARPS - 1) / CNT_WARPS;
     int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;        // grid-stride: 8 CTAs (of 8 resident) per SM
@@ -254,6 +257,59 @@ extern "C" int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_
     return launch_count(s, n_reads, (const int64_t *)s->d_rd_ptr, d_tid0, (const int32_t *)s->d_rd_fl);
 }
 
+// ---- compact wire form: lengths instead of offsets, 16-bit fragment lengths or none ----
+__global__ void k_len_widen(int64_t n, const uint16_t *__restrict__ len, uint32_t *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i < n ? len[i] : 0u;
+}
+__global__ void k_fl_widen(int64_t n, const uint16_t *__restrict__ fl, int32_t cfl, int32_t *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fl ? (int32_t)fl[i] : cfl;
+}
+struct U32ToI64 { __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; } };
+
+extern "C" int emsar_sample_count_compact(emsar_sample *s, int64_t n_reads, int64_t n_tids, const uint16_t *read_len, const int32_t *read_tid,
+                                          const uint16_t *read_fraglen, int32_t const_fraglen)
+{
+    CHECK_ARG(s && n_reads >= 0, "emsar_sample_count_compact: bad argument");
+    if (n_reads == 0) { s->have_counts = true; return EMSAR_OK; }
+    CHECK_ARG(read_len && read_tid, "emsar_sample_count_compact: NULL read arrays");
+    CHECK_ARG(n_reads < ((int64_t)1 << 31), "emsar_sample_count_compact: more than 2^31 read groups in one batch");
+    emsar_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    TRY(ctx_use(ctx));
+    CHECK_ARG(n_tids >= 0, "emsar_sample_count_compact: negative tid count");
+    const int64_t ntid = n_tids;            // must be the sum of read_len; the counting kernel checks every list against it
+    // staging: [int64 offsets n+1] [tids] [int32 fragment lengths n] as for the wide form, plus the 16-bit arrays and the scan scratch
+    TRY(grow(&s->d_rd_ptr, &s->cap_rd_ptr, (size_t)(n_reads + 1) * 8, ctx));
+    TRY(grow(&s->d_rd_tid, &s->cap_rd_tid, (size_t)(ntid > 0 ? ntid : 1) * 4, ctx));
+    TRY(grow(&s->d_rd_fl, &s->cap_rd_fl, (size_t)n_reads * 4, ctx));
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (int64_t *)nullptr, (int)(n_reads + 1));
+    const size_t need = (size_t)(n_reads + 1) * 2 * 2 + (size_t)(n_reads + 1) * 4 + scan_bytes + 1024;
+    TRY(grow(&s->d_rd_aux, &s->cap_rd_aux, need, ctx));
+    if (!s->count_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&s->count_ev[i], cudaEventDisableTiming));
+    char *aux = (char *)s->d_rd_aux;
+    uint16_t *d_len = (uint16_t *)aux;                                   aux += (((size_t)(n_reads + 1) * 2 + 255) / 256) * 256;
+    uint16_t *d_fl16 = (uint16_t *)aux;                                  aux += (((size_t)(n_reads + 1) * 2 + 255) / 256) * 256;
+    uint32_t *d_len32 = (uint32_t *)aux;                                 aux += (((size_t)(n_reads + 1) * 4 + 255) / 256) * 256;
+    void *d_scan = aux;
+    CU(cudaMemcpyAsync(d_len, read_len, (size_t)n_reads * 2, cudaMemcpyHostToDevice, st));
+    if (ntid > 0) CU(cudaMemcpyAsync(s->d_rd_tid, read_tid, (size_t)ntid * 4, cudaMemcpyHostToDevice, st));
+    if (read_fraglen) CU(cudaMemcpyAsync(d_fl16, read_fraglen, (size_t)n_reads * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(s->count_ev[s->count_seq & 3], st));           // the host arrays are free once the copies are done
+    s->count_seq++;
+    const unsigned nb = (unsigned)((n_reads + 1 + 255) / 256);
+    k_len_widen<<<nb, 256, 0, st>>>(n_reads, d_len, d_len32);
+    CU(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cub::TransformInputIterator<int64_t, U32ToI64, const uint32_t *>(d_len32, U32ToI64()), (int64_t *)s->d_rd_ptr,
+                                     (int)(n_reads + 1), st));
+    k_fl_widen<<<nb, 256, 0, st>>>(n_reads, read_fraglen ? d_fl16 : nullptr, const_fraglen, (int32_t *)s->d_rd_fl);
+    ctx->launches += 3;
+    return launch_count(s, n_reads, (const int64_t *)s->d_rd_ptr, (const int32_t *)s->d_rd_tid, (const int32_t *)s->d_rd_fl, ntid);
+}
+
 extern "C" int emsar_sample_count_wait(emsar_sample *s, int32_t lag)
 {
     CHECK_ARG(s && lag >= 0 && lag < 4, "emsar_sample_count_wait: lag must be 0..3");
@@ -317,6 +373,7 @@ static int check_flags(emsar_sample *s)
     CU(cudaStreamSynchronize(s->ctx->stream));
     if (f & 1) { emsar_set_err("a read group carried more than %d alignments (use -k <= %d)", EMSAR_MAX_READ_TIDS, EMSAR_MAX_READ_TIDS); return EMSAR_ERR_UNSUPPORTED; }
     if (f & 2) { emsar_set_err("a read carried a transcript id outside 0..T-1"); return EMSAR_ERR_BAD_ARG; }
+    if (f & 4) { emsar_set_err("emsar_sample_count_compact: the lengths add up to more tids than the caller passed"); return EMSAR_ERR_BAD_ARG; }
     return EMSAR_OK;
 }
 int sample_check_flags(emsar_sample *s) { return check_flags(s); }

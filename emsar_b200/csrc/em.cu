@@ -1449,7 +1449,7 @@ extern "C" int emsar_sample_end(emsar_sample *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (int i = 0; i < 4; i++) if (s->count_ev[i]) cudaEventDestroy(s->count_ev[i]);
     dev_free(s->d_R); dev_free(s->d_hist); dev_free(s->d_flags);
-    dev_free(s->d_rd_ptr); dev_free(s->d_rd_tid); dev_free(s->d_rd_fl);
+    dev_free(s->d_rd_ptr); dev_free(s->d_rd_tid); dev_free(s->d_rd_fl); dev_free(s->d_rd_aux);
     dev_free(s->d_Wf); dev_free(s->d_adj); dev_free(s->d_amodel); dev_free(s->d_in_model);
     dev_free(s->d_A); dev_free(s->d_Rs); dev_free(s->d_iE); dev_free(s->d_lone); dev_free(s->d_pos);
     for (void *q : s->ps_allocs) dev_free(q);

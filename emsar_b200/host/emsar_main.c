@@ -84,11 +84,30 @@ static void usage(const char *p)
 
 /* Ingestion pipeline: BGZF blocks are inflated by -p worker threads, the parser fills one of two page-locked batch buffers
  * while the device still copies / counts the other one (emsar_sample_count is asynchronous on page-locked arrays). */
-typedef struct { emsar_sample *s; emsar_ctx *ctx; int rc; int64_t batches, groups; } count_ctx;
+typedef struct { emsar_sample *s; emsar_ctx *ctx; int rc; int64_t batches, groups; uint16_t *len16[2], *fl16[2]; int64_t cap16; } count_ctx;
 static int on_batch(void *user, int64_t n, const int64_t *ptr, const int32_t *tid, const int32_t *fl)
 {
+    /* the batch goes to the device in its compact wire form (emsar_sample_count_compact): 16-bit lengths instead of 64-bit offsets, 16-bit
+     * fragment lengths or none when the whole batch has one - 40 % fewer bytes over PCIe, which is what eight GPUs on one host contend for */
     count_ctx *c = (count_ctx *)user;
-    c->rc = emsar_sample_count(c->s, n, ptr, tid, fl);
+    const int k = (int)(c->batches & 1);
+    if (n > c->cap16) {
+        if (c->batches > 0 && (c->rc = emsar_sample_count_wait(c->s, 0))) return c->rc;       /* nothing in flight reads the old arrays */
+        for (int b = 0; b < 2; b++) { emsar_host_free(c->ctx, c->len16[b]); emsar_host_free(c->ctx, c->fl16[b]); c->len16[b] = c->fl16[b] = NULL; }
+        c->cap16 = n + (n >> 2) + 1024;
+        for (int b = 0; b < 2; b++)
+            if (emsar_host_alloc(c->ctx, sizeof(uint16_t) * (size_t)c->cap16, (void **)&c->len16[b]) || emsar_host_alloc(c->ctx, sizeof(uint16_t) * (size_t)c->cap16, (void **)&c->fl16[b]))
+                return c->rc = EMSAR_ERR_NOMEM;
+    }
+    int wide = 0, same = 1;
+    for (int64_t r = 0; r < n; r++) {
+        const int64_t l = ptr[r + 1] - ptr[r];
+        if (l > 65535 || fl[r] < 0 || fl[r] > 65535) { wide = 1; break; }
+        c->len16[k][r] = (uint16_t)l; c->fl16[k][r] = (uint16_t)fl[r];
+        same &= fl[r] == fl[0];
+    }
+    if (wide) c->rc = emsar_sample_count(c->s, n, ptr, tid, fl);
+    else c->rc = emsar_sample_count_compact(c->s, n, ptr[n] - ptr[0], c->len16[k], tid + ptr[0], same ? NULL : c->fl16[k], n > 0 ? fl[0] : 0);
     if (!c->rc) c->rc = emsar_sample_count_wait(c->s, 1);      /* the other buffer set (batch k-1) is free again */
     c->batches++; c->groups += n;
     return c->rc;
@@ -125,7 +144,9 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
     ro.io_threads = o->nthread > 0 ? o->nthread : 4;            /* -p: BGZF inflate threads (the reference's -p sizes its MLE thread team) */
     ro.nbuf = 2; ro.buf_alloc = pinned_alloc; ro.buf_free = pinned_free; ro.hook_user = ctx;
     int readlength = rsh->readlength;
-    count_ctx cc = {s, ctx, 0, 0, 0};
+    count_ctx cc;
+    memset(&cc, 0, sizeof cc);
+    cc.s = s; cc.ctx = ctx;
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     if (lead) {
@@ -135,6 +156,7 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
         }
         if ((rc = emsar_sample_count_wait(s, 0))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
     } else if ((rc = emsar_sample_count(s, 0, NULL, NULL, NULL))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    for (int b = 0; b < 2; b++) { emsar_host_free(ctx, cc.len16[b]); emsar_host_free(ctx, cc.fl16[b]); }
     if (sharded && (rc = emsar_sample_counts_allreduce(s))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());   /* everybody gets rank 0's counts */
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (o->verbose > 0 && lead) {

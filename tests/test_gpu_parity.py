@@ -225,3 +225,32 @@ def test_short_launch_then_normal_sample_same_context(built):
         ix.close()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("name", ["se_longk", "pe_nf21"])
+def test_count_compact_wire_form(ctx, name):
+    """emsar_sample_count_compact (uint16 lengths, uint16 or no fragment lengths) counts exactly what the wide form counts; a batch
+    whose lengths and tid count disagree is an error."""
+    from emsar_b200._lib import EmsarError
+    idx, reads = _make(name)
+    R0, F0, N0 = _oracle().count(idx, reads)
+    ix = Index(ctx, idx)
+    s = ix.sample()
+    ln = np.diff(reads.read_ptr).astype(np.uint16)
+    n = len(ln)
+    h = n // 2
+    cut = int(reads.read_ptr[h])
+    if idx.nF == 1:
+        s.count_compact(ln[:h], reads.read_tid[:cut], None, int(reads.read_fraglen[0]))
+        s.count_compact(ln[h:], reads.read_tid[cut:], None, int(reads.read_fraglen[0]))
+    else:
+        s.count_compact(ln[:h], reads.read_tid[:cut], reads.read_fraglen[:h].astype(np.uint16))
+        s.count_compact(ln[h:], reads.read_tid[cut:], reads.read_fraglen[h:].astype(np.uint16))
+    R, F, N = s.counts()
+    s.close()
+    assert N == N0 and np.array_equal(F, F0) and np.array_equal(R, R0)
+    s = ix.sample()
+    s.count_compact(ln, reads.read_tid[:len(reads.read_tid) - 5], None, int(reads.read_fraglen[0]))
+    with pytest.raises(EmsarError):
+        s.counts()
+    s.close(); ix.close()
