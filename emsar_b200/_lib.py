@@ -61,7 +61,7 @@ SYMBOLS = [
     "emsar_cuda_synchronize", "emsar_cuda_device_info", "emsar_index_create", "emsar_index_info_get", "emsar_index_destroy",
     "emsar_sample_begin", "emsar_sample_count", "emsar_sample_count_compact", "emsar_sample_count_device", "emsar_sample_counts_set", "emsar_sample_counts_get",
     "emsar_sample_solve", "emsar_sample_segments_get", "emsar_sample_wf_get", "emsar_sample_end", "emsar_sample_prepare",
-    "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_finalize",
+    "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_theta_randomize", "emsar_sample_finalize",
     "emsar_host_alloc", "emsar_host_free", "emsar_sample_count_wait", "emsar_comm_unique_id", "emsar_comm_init", "emsar_comm_destroy", "emsar_comm_info", "emsar_sample_counts_allreduce", "emsar_shard_ranges", "emsar_locality_order", "emsar_cuda_timer_start", "emsar_cuda_timer_stop", "emsar_sample_time_adjeuma",
 ]
 

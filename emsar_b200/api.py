@@ -240,6 +240,9 @@ class Sample:
         L.check(L.lib().emsar_sample_theta_get(self._h, _ptr(th)), "emsar_sample_theta_get")
         return th
 
+    def theta_randomize(self, seed: int):
+        L.check(L.lib().emsar_sample_theta_randomize(self._h, C.c_uint64(int(seed))), "emsar_sample_theta_randomize")
+
     def finalize(self) -> dict:
         o, bufs = self._out()
         L.check(L.lib().emsar_sample_finalize(self._h, C.byref(o)), "emsar_sample_finalize")

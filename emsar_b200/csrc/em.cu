@@ -1414,6 +1414,31 @@ extern "C" int emsar_sample_theta_get(emsar_sample *s, double *theta)
     return EMSAR_OK;
 }
 
+__global__ void k_theta_random(int32_t T, const int32_t *__restrict__ pos, unsigned long long seed, double *__restrict__ theta)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int p = pos[t];
+    if (p < 0) return;
+    // keyed by the transcript id, not by the row: the start does not depend on how the rows are laid out (one GPU or several)
+    const uint64_t h = mix64(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)t + 1);
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+    theta[p] = exp((2.0 * u - 1.0) * 2.302585092994046);                        // 0.1 .. 10
+}
+
+extern "C" int emsar_sample_theta_randomize(emsar_sample *s, uint64_t seed)
+{
+    CHECK_ARG(s, "emsar_sample_theta_randomize: NULL sample");
+    if (!s->prepared) { emsar_set_err("emsar_sample_theta_randomize: sample not prepared"); return EMSAR_ERR_STATE; }
+    TRY(ctx_use(s->ctx));
+    const int32_t T = s->index->T;
+    k_theta_random<<<(T + 255) / 256, 256, 0, s->ctx->stream>>>(T, s->d_pos, (unsigned long long)seed, s->m.theta);
+    LAUNCHED(s->ctx);
+    CU(cudaGetLastError());
+    s->n_iter = 0; s->final_delta = INFINITY;
+    return EMSAR_OK;
+}
+
 extern "C" int emsar_sample_segments_get(emsar_sample *s, double *adjEUMA, double *expected, int32_t *set_id)
 {
     CHECK_ARG(s, "emsar_sample_segments_get: NULL sample");

@@ -36,7 +36,7 @@
 typedef struct {
     char rshfile[FILENAMEMAX], fasta[FILENAMEMAX], strand_str[8];
     int pe, multisample, print_segments, print_rsh, verbose, max_repeat, nthread, max_iter;
-    int min_fl, max_fl, num_round;
+    int min_fl, max_fl, num_round, rounds_set;
     char bamflag, strand, fasta_header;
     double eps_abs, eps_rel, delta;
     const char *outdir, *outprefix;
@@ -212,9 +212,7 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
     snprintf(p1, sizeof p1, "%s/%s.%d.fpkm", o->outdir, o->outprefix, i);
     snprintf(p2, sizeof p2, "%s/%s.%d.fraglength_effect", o->outdir, o->outprefix, i);
     snprintf(p3, sizeof p3, "%s/%s.%d.segments", o->outdir, o->outprefix, i);
-    if (emsar_write_fpkm(p1, rsh, out.fpkm, NULL, out.efflen, out.ireadcount, out.ireadcount_int, out.tpm, err)) die("%s", err);
-    if (o->verbose > 0) fprintf(stdout, "Total inferred readcount=%lld\n", (long long)out.total_ireadcount);
-    if (emsar_write_fraglength(p2, rsh, F, Wf, err)) die("%s", err);
+    /* the .segments file (expected counts per class) comes from the standard run, before any restart round moves theta */
     if (o->print_segments) {
         double *adj = (double *)malloc(sizeof(double) * (size_t)rsh->C), *ex = (double *)malloc(sizeof(double) * (size_t)rsh->C);
         int32_t *cs = (int32_t *)malloc(sizeof(int32_t) * (size_t)rsh->C);
@@ -222,6 +220,52 @@ static int run_file(const options *o, const emsar_rsh *rsh, emsar_ctx *ctx, emsa
         if (emsar_write_segments(p3, rsh, cs, adj, R, ex, err)) die("%s", err);
         free(adj); free(ex); free(cs);
     }
+    double *sd = NULL;
+    if (o->rounds_set && o->num_round > 1 && !sharded) {
+        /* -n R given explicitly: R - 1 restart rounds from seeded random starting points next to the standard run (reference emsar_main.c:444-450);
+         * the file then carries the mean over the rounds and sd.of.FPKM = sqrt(sum (x - m)^2 / (R - 1)) / R as print_FPKMfinal (:3186-3208) does.
+         * Without -n there is one deterministic run and the column prints 0. */
+        const int R_ = o->num_round;
+        double *sum = (double *)calloc((size_t)T, sizeof(double)), *sq = (double *)calloc((size_t)T, sizeof(double)), *fr = (double *)malloc(sizeof(double) * (size_t)T);
+        double **all = (double **)malloc(sizeof(double *) * (size_t)R_);
+        all[0] = (double *)malloc(sizeof(double) * (size_t)T);
+        memcpy(all[0], out.fpkm, sizeof(double) * (size_t)T);
+        for (int rd = 1; rd < R_; rd++) {
+            emsar_solve_out o2;
+            memset(&o2, 0, sizeof o2);
+            all[rd] = (double *)malloc(sizeof(double) * (size_t)T);
+            o2.fpkm = all[rd];
+            int32_t it2 = 0; double fd2 = 0, ms2 = 0;
+            if ((rc = emsar_sample_theta_randomize(s, (uint64_t)rd)) || (rc = emsar_sample_em_run(s, 0, 1, 0, &it2, &fd2, &ms2)) || (rc = emsar_sample_finalize(s, &o2)))
+                die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+            if (o->verbose > 0) fprintf(stdout, "round %d/%d: %d iterations, delta %.3g, logL %.10g\n", rd + 1, R_, o2.n_iter, o2.final_delta, o2.loglik);
+        }
+        sd = (double *)malloc(sizeof(double) * (size_t)T);
+        double tot = 0;
+        for (int32_t t = 0; t < T; t++) {
+            double m = 0;
+            for (int rd = 0; rd < R_; rd++) m += all[rd][t];
+            m /= R_;
+            double v = 0;
+            for (int rd = 0; rd < R_; rd++) v += (all[rd][t] - m) * (all[rd][t] - m);
+            sd[t] = sqrt(v / (R_ - 1)) / R_;
+            out.fpkm[t] = m;
+            tot += m;
+        }
+        const double nscale = (double)out.total_readcount / 1E6;
+        for (int32_t t = 0; t < T; t++) {
+            const double ir = (out.efflen[t] / 1E3) * out.fpkm[t] * nscale;                  /* print_FPKMfinal :3203 */
+            out.ireadcount[t] = ir;
+            out.ireadcount_int[t] = (ir - (int)ir >= 0.5) ? (int)ir + 1 : (int)ir;           /* Round_off :3215-3217 */
+            out.tpm[t] = out.fpkm[t] * 1E6 / tot;
+        }
+        for (int rd = 0; rd < R_; rd++) free(all[rd]);
+        free(all); free(sum); free(sq); free(fr);
+    }
+    if (emsar_write_fpkm(p1, rsh, out.fpkm, sd, out.efflen, out.ireadcount, out.ireadcount_int, out.tpm, err)) die("%s", err);
+    free(sd);
+    if (o->verbose > 0) fprintf(stdout, "Total inferred readcount=%lld\n", (long long)out.total_ireadcount);
+    if (emsar_write_fraglength(p2, rsh, F, Wf, err)) die("%s", err);
     fprintf(stdout, "Complete: Output file :\n  %s\n  %s\n", p1, p2);
     if (o->print_segments) fprintf(stdout, "  %s\n", p3);
     fflush(stdout);
@@ -302,7 +346,7 @@ int main(int argc, char *argv[])
         case 'F': o.max_fl = atoi(optarg); break;
         case 'f': o.min_fl = atoi(optarg); break;
         case 'k': o.max_repeat = atoi(optarg); break;
-        case 'n': o.num_round = atoi(optarg); if (o.num_round <= 0) { fprintf(stderr, "option -n must be a natural number.\n"); return 0; } break;
+        case 'n': o.rounds_set = 1; o.num_round = atoi(optarg); if (o.num_round <= 0) { fprintf(stderr, "option -n must be a natural number.\n"); return 0; } break;
         case 'e': o.eps_abs = atof(optarg); if (o.eps_abs <= 0) { fprintf(stderr, "option -e must be positive.\n"); return 0; } break;
         case 'r': o.eps_rel = atof(optarg); if (o.eps_rel <= 0) { fprintf(stderr, "option -p must be positive.\n"); return 0; } break;
         case 'i': o.max_iter = atoi(optarg); if (o.max_iter <= 0) { fprintf(stderr, "option -i must be positive.\n"); return 0; } break;

@@ -229,6 +229,12 @@ int emsar_sample_model_stats(emsar_sample *s, emsar_model_stats *st);
 int emsar_sample_em_run(emsar_sample *s, int32_t max_iter, int32_t stop_on_conv, int32_t reset_theta,
                         int32_t *iters_done, double *final_delta, double *elapsed_ms);
 int emsar_sample_theta_get(emsar_sample *s, double *theta);
+/* Restart rounds (reference -n, NUM_ROUND: emsar_main.c:444-450 runs the estimator from rand() starting points and prints mean and sd):
+ * sets theta of every participating transcript to a seeded pseudo-random positive value (log-uniform over two decades around 1; the
+ * same seed gives the same start on every device) and resets the iteration count. emsar_sample_em_run + emsar_sample_finalize then give
+ * that round's estimate. EM reaches the same optimum from any positive start where the optimum is unique; rounds differ (sd > 0) exactly
+ * on transcripts that the data cannot tell apart. */
+int emsar_sample_theta_randomize(emsar_sample *s, uint64_t seed);
 /* Measurement helpers (bench.py): CUDA events on the context's own stream around whatever the caller enqueues in between
  * (torch.cuda.Event only sees torch's stream). emsar_cuda_timer_stop synchronizes and returns the milliseconds since _start. */
 int emsar_cuda_timer_start(emsar_ctx *ctx);

@@ -144,3 +144,29 @@ def test_live_reference_binary_if_present(built, tmp_path):
     eff = np.array([float(r[3]) for r in fr])
     tol = gu.fpkm_tolerance(g, eff, 15000, 6)
     assert (np.abs(np.array([float(r[1]) for r in fm]) - g["fpkm"]) <= tol).all()
+
+
+def test_cli_restart_rounds_sd_column(built, tmp_path):
+    """-n R: R - 1 restart rounds from seeded random starts. Where the optimum is unique every round lands on it (sd.of.FPKM ~ 0, same
+    FPKM as the single run); the duplicated transcripts of the `built` fixture (no private k-mer) are what the data cannot tell apart:
+    their sd is large while their SUM is the same in every round."""
+    fx = gu.FIXTURES["built"]
+    rsh, aln = gu.materialize(fx["rsh"], tmp_path), gu.materialize(fx["aln"], tmp_path)
+    outs = {}
+    for tag, extra in (("one", []), ("n4", ["-n", "4"])):
+        out = os.path.join(str(tmp_path), tag)
+        r = subprocess.run([EMSAR, "-q", "-g", "-S", "-s", fx["strand"]] + extra + ["-I", rsh, out, "p", aln], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = gu.parse_out_file(os.path.join(out, "p.0.fpkm"))
+    one, n4 = outs["one"], outs["n4"]
+    seg = gu.read_segments(fx["out"])
+    f1, f4 = np.array([float(r[1]) for r in one]), np.array([float(r[1]) for r in n4])
+    sd1, sd4 = np.array([float(r[2]) for r in one]), np.array([float(r[2]) for r in n4])
+    ident = seg["adjEUMA"][:len(f1)] > 0
+    assert (sd1 == 0).all()
+    # every round stops within the EM tolerance of the same optimum: the spread is orders of magnitude below the estimates
+    assert np.allclose(f1[ident], f4[ident], rtol=1e-3, atol=1e-3) and (sd4[ident] <= 1e-3 * np.maximum(f4[ident], 1.0)).all()
+    amb = ~ident
+    assert amb.sum() >= 2 and abs(f1[amb].sum() - f4[amb].sum()) <= 1e-3 * max(f1[amb].sum(), 1.0) + 1e-3
+    assert sd4[amb].max() > 100 * max(sd4[ident].max(), 1e-9)            # the split between indistinguishable transcripts depends on the start
+    assert open(os.path.join(str(tmp_path), "one", "p.0.segments")).read() == open(os.path.join(str(tmp_path), "n4", "p.0.segments")).read()
