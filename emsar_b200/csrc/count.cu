@@ -258,17 +258,16 @@ extern "C" int emsar_sample_count(emsar_sample *s, int64_t n_reads, const int64_
 }
 
 // ---- compact wire form: lengths instead of offsets, 16-bit fragment lengths or none ----
-__global__ void k_len_widen(int64_t n, const uint16_t *__restrict__ len, uint32_t *__restrict__ out)
+__global__ void k_len_widen(int64_t n, const uint16_t *__restrict__ len, int64_t *__restrict__ out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n) out[i] = i < n ? len[i] : 0u;
+    if (i <= n) out[i] = i < n ? (int64_t)len[i] : 0;
 }
 __global__ void k_fl_widen(int64_t n, const uint16_t *__restrict__ fl, int32_t cfl, int32_t *__restrict__ out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fl ? (int32_t)fl[i] : cfl;
 }
-struct U32ToI64 { __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; } };
 
 extern "C" int emsar_sample_count_compact(emsar_sample *s, int64_t n_reads, int64_t n_tids, const uint16_t *read_len, const int32_t *read_tid,
                                           const uint16_t *read_fraglen, int32_t const_fraglen)
@@ -287,14 +286,14 @@ extern "C" int emsar_sample_count_compact(emsar_sample *s, int64_t n_reads, int6
     TRY(grow(&s->d_rd_tid, &s->cap_rd_tid, (size_t)(ntid > 0 ? ntid : 1) * 4, ctx));
     TRY(grow(&s->d_rd_fl, &s->cap_rd_fl, (size_t)n_reads * 4, ctx));
     size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (int64_t *)nullptr, (int)(n_reads + 1));
-    const size_t need = (size_t)(n_reads + 1) * 2 * 2 + (size_t)(n_reads + 1) * 4 + scan_bytes + 1024;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int64_t *)nullptr, (int64_t *)nullptr, (int)(n_reads + 1));
+    const size_t need = (size_t)(n_reads + 1) * 2 * 2 + (size_t)(n_reads + 1) * 8 + scan_bytes + 2048;
     TRY(grow(&s->d_rd_aux, &s->cap_rd_aux, need, ctx));
     if (!s->count_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&s->count_ev[i], cudaEventDisableTiming));
     char *aux = (char *)s->d_rd_aux;
     uint16_t *d_len = (uint16_t *)aux;                                   aux += (((size_t)(n_reads + 1) * 2 + 255) / 256) * 256;
     uint16_t *d_fl16 = (uint16_t *)aux;                                  aux += (((size_t)(n_reads + 1) * 2 + 255) / 256) * 256;
-    uint32_t *d_len32 = (uint32_t *)aux;                                 aux += (((size_t)(n_reads + 1) * 4 + 255) / 256) * 256;
+    int64_t *d_len64 = (int64_t *)aux;                                   aux += (((size_t)(n_reads + 1) * 8 + 255) / 256) * 256;
     void *d_scan = aux;
     CU(cudaMemcpyAsync(d_len, read_len, (size_t)n_reads * 2, cudaMemcpyHostToDevice, st));
     if (ntid > 0) CU(cudaMemcpyAsync(s->d_rd_tid, read_tid, (size_t)ntid * 4, cudaMemcpyHostToDevice, st));
@@ -302,9 +301,8 @@ extern "C" int emsar_sample_count_compact(emsar_sample *s, int64_t n_reads, int6
     CU(cudaEventRecord(s->count_ev[s->count_seq & 3], st));           // the host arrays are free once the copies are done
     s->count_seq++;
     const unsigned nb = (unsigned)((n_reads + 1 + 255) / 256);
-    k_len_widen<<<nb, 256, 0, st>>>(n_reads, d_len, d_len32);
-    CU(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cub::TransformInputIterator<int64_t, U32ToI64, const uint32_t *>(d_len32, U32ToI64()), (int64_t *)s->d_rd_ptr,
-                                     (int)(n_reads + 1), st));
+    k_len_widen<<<nb, 256, 0, st>>>(n_reads, d_len, d_len64);
+    CU(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_len64, (int64_t *)s->d_rd_ptr, (int)(n_reads + 1), st));
     k_fl_widen<<<nb, 256, 0, st>>>(n_reads, read_fraglen ? d_fl16 : nullptr, const_fraglen, (int32_t *)s->d_rd_fl);
     ctx->launches += 3;
     return launch_count(s, n_reads, (const int64_t *)s->d_rd_ptr, (const int32_t *)s->d_rd_tid, (const int32_t *)s->d_rd_fl, ntid);
