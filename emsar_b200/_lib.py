@@ -19,7 +19,7 @@ class IndexDesc(C.Structure):
     _fields_ = [("T", C.c_int32), ("C", C.c_int64), ("class_ptr", C.c_void_p), ("class_tid", C.c_void_p),
                 ("nF", C.c_int32), ("euma", C.c_void_p), ("has_node", C.c_void_p),
                 ("min_fraglength", C.c_int32), ("max_fraglength", C.c_int32), ("readlength", C.c_int32),
-                ("max_t_size", C.c_int32)]
+                ("max_t_size", C.c_int32), ("aux", C.c_void_p)]
 
 
 class IndexInfo(C.Structure):
@@ -58,7 +58,7 @@ class ModelStats(C.Structure):
 # every symbol include/emsar_cuda.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "emsar_cuda_open", "emsar_cuda_close", "emsar_cuda_strerror", "emsar_cuda_last_error", "emsar_cuda_launch_count",
-    "emsar_cuda_synchronize", "emsar_cuda_device_info", "emsar_index_create", "emsar_index_info_get", "emsar_index_destroy",
+    "emsar_cuda_synchronize", "emsar_cuda_device_info", "emsar_index_create", "emsar_index_info_get", "emsar_index_aux_get", "emsar_index_destroy",
     "emsar_sample_begin", "emsar_sample_count", "emsar_sample_count_compact", "emsar_sample_count_device", "emsar_sample_counts_set", "emsar_sample_counts_get",
     "emsar_sample_solve", "emsar_sample_segments_get", "emsar_sample_wf_get", "emsar_sample_end", "emsar_sample_prepare",
     "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_theta_randomize", "emsar_sample_finalize",

@@ -112,7 +112,7 @@ class Index:
         eu = _np(idx.euma, np.int32)
         hn = _np(idx.has_node, np.uint8) if getattr(idx, "has_node", None) is not None else None
         d = L.IndexDesc(self.T, self.C, _ptr(cp), _ptr(ct), self.nF, _ptr(eu), _ptr(hn) if hn is not None else None,
-                        int(idx.min_fraglength), int(idx.max_fraglength), int(idx.readlength), int(idx.max_t_size))
+                        int(idx.min_fraglength), int(idx.max_fraglength), int(idx.readlength), int(idx.max_t_size), None)
         self._h = C.c_void_p()
         L.check(L.lib().emsar_index_create(ctx._h, C.byref(d), C.byref(self._h)), "emsar_index_create")
 

@@ -118,6 +118,9 @@ struct emsar_index {
     std::vector<uint32_t> h_cls_off;
     std::vector<int32_t> h_cls_tid;
     std::vector<int32_t> h_order;
+    std::vector<uint32_t> h_txm_off;       // kept for emsar_index_aux_get (the packed image)
+    std::vector<int32_t> h_txm_cid;
+    std::vector<uint8_t> h_insertable;
     int32_t n_sets_nocut, max_set_tids;
     int64_t device_bytes;
 };

@@ -211,7 +211,22 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
     std::vector<KSeg> kseg;
     std::vector<uint8_t> insertable((size_t)(C - T), 1);
     int32_t max_card = 1;
-    {
+    const emsar_index_aux *aux = d->aux;
+    if (aux) {
+        // packed image: the table was validated when the image was made; only the cardinality segments are rebuilt (one pass over class_ptr)
+        CHECK_ARG(aux->txm_off && aux->order && aux->insertable && (aux->txm_cid || aux->nnz_multi == 0) && aux->nnz_multi == nnz - T,
+                  "emsar_index_create: the packed image's derived arrays do not match the class table");
+        int prev_k = 1;
+        for (int64_t c = T; c < C; c++) {
+            const int k = (int)(d->class_ptr[c + 1] - d->class_ptr[c]);
+            if (k < 2 || k < prev_k || k > d->max_t_size) { emsar_set_err("class %lld out of scan order (packed image)", (long long)c); return EMSAR_ERR_BAD_INDEX; }
+            if (k != prev_k) kseg.push_back(KSeg{k, c, c});
+            kseg.back().cid1 = c + 1;
+            prev_k = k;
+            if (k > max_card) max_card = k;
+        }
+        memcpy(insertable.data(), aux->insertable, (size_t)(C - T));
+    } else {
         int prev_k = 1, prev_t0 = -1;
         int64_t chain_max = -1; // cid holding the running maximum key of the current chain
         for (int64_t c = T; c < C; c++) {
@@ -264,10 +279,19 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
     for (int64_t c = 0; c <= C; c++) ix->h_cls_off[(size_t)c] = (uint32_t)d->class_ptr[c];
     ix->h_cls_tid.assign(d->class_tid, d->class_tid + nnz);
     // ---- transpose of the multi-tid classes (build_TC_from_CT_2 :2201-2227 without the singleton entries) ----
-    std::vector<uint32_t> txm_off((size_t)T + 1, 0);
+    std::vector<uint32_t> &txm_off = ix->h_txm_off;
+    std::vector<int32_t> &txm_cid = ix->h_txm_cid;
+    ix->h_insertable = insertable;
+    if (aux) {
+        txm_off.assign(aux->txm_off, aux->txm_off + T + 1);
+        txm_cid.assign(aux->txm_cid, aux->txm_cid + (nnz - T));
+        ix->h_order.assign(aux->order, aux->order + T);
+        ix->n_sets_nocut = aux->n_sets_nocut; ix->max_set_tids = aux->max_set_tids;
+    } else {
+    txm_off.assign((size_t)T + 1, 0);
     for (int64_t j = T; j < nnz; j++) txm_off[(size_t)d->class_tid[j] + 1]++;
     for (int32_t t = 0; t < T; t++) txm_off[(size_t)t + 1] += txm_off[(size_t)t];
-    std::vector<int32_t> txm_cid((size_t)(nnz - T));
+    txm_cid.resize((size_t)(nnz - T));
     {
         std::vector<uint32_t> cur(txm_off.begin(), txm_off.end() - 1);
         for (int64_t c = T; c < C; c++)
@@ -297,6 +321,7 @@ extern "C" int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *d, ems
         int orc = emsar_locality_order(T, C, d->class_ptr, d->class_tid, mode, ix->h_order.data());
         if (orc != EMSAR_OK) { delete ix; return orc; }
     }
+    }   // !aux
     // ---- upload ----
     int rc;
 #define UP(dst, src, n, type)                                                                         \
@@ -334,6 +359,17 @@ extern "C" int emsar_index_info_get(const emsar_index *ix, emsar_index_info *inf
     info->hash_slots = (int64_t)ix->hash_mask + 1; info->hash_inserted = ix->hash_inserted;
     info->n_sets_nocut = ix->n_sets_nocut; info->max_set_tids = ix->max_set_tids;
     info->device_bytes = ix->device_bytes; info->frag_min = ix->frag_min; info->frag_max = ix->frag_max;
+    return EMSAR_OK;
+}
+
+extern "C" int emsar_index_aux_get(const emsar_index *ix, emsar_index_aux *aux)
+{
+    CHECK_ARG(ix && aux, "emsar_index_aux_get: NULL argument");
+    memset(aux, 0, sizeof(*aux));
+    aux->nnz_multi = ix->nnz_multi;
+    aux->txm_off = ix->h_txm_off.data(); aux->txm_cid = ix->h_txm_cid.data(); aux->order = ix->h_order.data();
+    aux->insertable = ix->h_insertable.data();
+    aux->n_sets_nocut = ix->n_sets_nocut; aux->max_set_tids = ix->max_set_tids;
     return EMSAR_OK;
 }
 

@@ -22,7 +22,10 @@ class _Rsh(C.Structure):
                 ("nF", C.c_int32), ("euma", C.POINTER(C.c_int32)), ("has_node", C.POINTER(C.c_uint8)),
                 ("min_fraglength", C.c_int32), ("max_fraglength", C.c_int32), ("readlength", C.c_int32), ("max_t_size", C.c_int32),
                 ("frag_min", C.c_int32), ("frag_max", C.c_int32), ("names", C.POINTER(C.c_char_p)),
-                ("name_slots", C.POINTER(C.c_uint32)), ("name_mask", C.c_uint32)]
+                ("name_slots", C.POINTER(C.c_uint32)), ("name_mask", C.c_uint32),
+                ("has_aux", C.c_int), ("aux_owned", C.c_int), ("aux_nnz_multi", C.c_int64), ("aux_txm_off", C.POINTER(C.c_uint32)),
+                ("aux_txm_cid", C.POINTER(C.c_int32)), ("aux_order", C.POINTER(C.c_int32)), ("aux_insertable", C.POINTER(C.c_uint8)),
+                ("aux_n_sets_nocut", C.c_int32), ("aux_max_set_tids", C.c_int32)]
 
 
 class _ReaderOpts(C.Structure):
@@ -83,6 +86,32 @@ class Rsh:
         self.readlength, self.max_t_size = int(r.readlength), int(r.max_t_size)
         self.frag_min, self.frag_max = int(r.frag_min), int(r.frag_max)
         self.names = [r.names[t].decode() for t in range(self.T)]
+        self.has_aux = bool(r.has_aux)
+        self._aux_keep = None
+
+    def aux(self):
+        """The derived arrays a complete packed image carries (None for a text index / an image without them)."""
+        r = self._p.contents
+        if not r.has_aux:
+            return None
+        n = int(r.aux_nnz_multi)
+        return dict(nnz_multi=n, txm_off=np.ctypeslib.as_array(r.aux_txm_off, shape=(self.T + 1,)).copy(),
+                    txm_cid=np.ctypeslib.as_array(r.aux_txm_cid, shape=(max(n, 1),))[:n].copy(),
+                    order=np.ctypeslib.as_array(r.aux_order, shape=(self.T,)).copy(),
+                    insertable=np.ctypeslib.as_array(r.aux_insertable, shape=(max(self.C - self.T, 1),))[:self.C - self.T].copy(),
+                    n_sets_nocut=int(r.aux_n_sets_nocut), max_set_tids=int(r.aux_max_set_tids))
+
+    def set_aux(self, txm_off, txm_cid, order, insertable, n_sets_nocut, max_set_tids):
+        """Attach derived arrays (as emsar_index_aux_get hands them out) so that save_packed writes a complete image."""
+        keep = [np.ascontiguousarray(txm_off, dtype=np.uint32), np.ascontiguousarray(txm_cid, dtype=np.int32),
+                np.ascontiguousarray(order, dtype=np.int32), np.ascontiguousarray(insertable, dtype=np.uint8)]
+        self._aux_keep = keep
+        r = self._p.contents
+        r.has_aux, r.aux_owned, r.aux_nnz_multi = 1, 0, len(keep[1])
+        r.aux_txm_off = keep[0].ctypes.data_as(C.POINTER(C.c_uint32)); r.aux_txm_cid = keep[1].ctypes.data_as(C.POINTER(C.c_int32))
+        r.aux_order = keep[2].ctypes.data_as(C.POINTER(C.c_int32)); r.aux_insertable = keep[3].ctypes.data_as(C.POINTER(C.c_uint8))
+        r.aux_n_sets_nocut, r.aux_max_set_tids = int(n_sets_nocut), int(max_set_tids)
+        self.has_aux = True
 
     def tid(self, name: str) -> int:
         return int(lib().emsar_rsh_tid(self._p, name.encode()))

@@ -33,6 +33,15 @@ typedef struct {
     /* tname -> tid (replaces the reference's character trie, stringhash.c) */
     uint32_t *name_slots;
     uint32_t name_mask;
+    /* optional: the structures the device library derives from the class table (emsar_index_aux of include/emsar_cuda.h), carried by a
+     * packed image so that creating the index costs no pass over the members. Owned by this struct when `aux_owned`. */
+    int has_aux, aux_owned;
+    int64_t aux_nnz_multi;
+    uint32_t *aux_txm_off;       /* [T+1] */
+    int32_t *aux_txm_cid;        /* [aux_nnz_multi] */
+    int32_t *aux_order;          /* [T] */
+    uint8_t *aux_insertable;     /* [C-T] */
+    int32_t aux_n_sets_nocut, aux_max_set_tids;
 } emsar_rsh;
 
 int emsar_rsh_load(const char *path, emsar_rsh **out, char *err);

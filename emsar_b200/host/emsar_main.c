@@ -288,8 +288,30 @@ static void *worker(void *p)
     d.T = r->T; d.C = r->C; d.class_ptr = r->class_ptr; d.class_tid = r->class_tid; d.nF = r->nF; d.euma = r->euma; d.has_node = r->has_node;
     d.min_fraglength = r->min_fraglength; d.max_fraglength = r->max_fraglength; d.readlength = r->readlength; d.max_t_size = r->max_t_size;
     emsar_index *ix = NULL;
+    emsar_index_aux ax;
+    if (w->rsh->has_aux && !getenv("EMSAR_RSH_NO_AUX")) {        /* a packed image with the derived arrays: no pass over the members */
+        memset(&ax, 0, sizeof ax);
+        ax.nnz_multi = w->rsh->aux_nnz_multi; ax.txm_off = w->rsh->aux_txm_off; ax.txm_cid = w->rsh->aux_txm_cid; ax.order = w->rsh->aux_order;
+        ax.insertable = w->rsh->aux_insertable; ax.n_sets_nocut = w->rsh->aux_n_sets_nocut; ax.max_set_tids = w->rsh->aux_max_set_tids;
+        d.aux = &ax;
+    }
     rc = emsar_index_create(ctx, &d, &ix);
     if (rc) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());
+    if (w->worker == 0 && d.aux && o->verbose > 0) fprintf(stdout, "index image carries transpose, locality order and reachable classes: nothing derived at load\n");
+    if (w->worker == 0 && getenv("EMSAR_RSH_CACHE") && !r->has_aux && o->rshfile[0] && !(strlen(o->rshfile) > 5 && !strcmp(o->rshfile + strlen(o->rshfile) - 5, ".pack"))) {
+        /* complete the packed image: the arrays the library just derived go into <rshfile>.pack, so that the next run
+         * of this index creates it without a pass over the members */
+        emsar_index_aux got;
+        if (emsar_index_aux_get(ix, &got) == 0) {
+            emsar_rsh tmp = *r;
+            tmp.has_aux = 1; tmp.aux_owned = 0; tmp.aux_nnz_multi = got.nnz_multi;
+            tmp.aux_txm_off = (uint32_t *)got.txm_off; tmp.aux_txm_cid = (int32_t *)got.txm_cid; tmp.aux_order = (int32_t *)got.order;
+            tmp.aux_insertable = (uint8_t *)got.insertable; tmp.aux_n_sets_nocut = got.n_sets_nocut; tmp.aux_max_set_tids = got.max_set_tids;
+            char pk[FILENAMEMAX + 16], e2[EMSAR_HOST_ERRLEN];
+            snprintf(pk, sizeof pk, "%s.pack", o->rshfile);
+            if (emsar_rsh_save_packed(&tmp, pk, o->rshfile, e2) == 0 && o->verbose > 0) fprintf(stdout, "packed index image written: %s\n", pk);
+        }
+    }
     double eumacut = 0;
     if (w->by_class) {
         if (w->worker == 0 && (rc = emsar_comm_unique_id(w->comm_id))) die("%s: %s", emsar_cuda_strerror(rc), emsar_cuda_last_error());

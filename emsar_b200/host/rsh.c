@@ -67,6 +67,7 @@ void emsar_rsh_free(emsar_rsh *r)
     if (!r) return;
     if (r->names) { for (int32_t t = 0; t < r->T; t++) free(r->names[t]); free(r->names); }
     free(r->class_ptr); free(r->class_tid); free(r->euma); free(r->has_node); free(r->name_slots);
+    if (r->aux_owned) { free(r->aux_txm_off); free(r->aux_txm_cid); free(r->aux_order); free(r->aux_insertable); }
     free(r);
 }
 
@@ -280,9 +281,11 @@ int emsar_rsh_write(const emsar_rsh *r, int pe, const char *path, char *err)
  * already applied), so loading it is a handful of large reads. It records size and mtime of the text file it was made
  * from and is ignored when they no longer match. */
 typedef struct {
-    char magic[8];                      /* "EMSARPK1" */
+    char magic[8];                      /* "EMSARPK2" */
     int32_t T, nF, min_fraglength, max_fraglength, readlength, max_t_size, frag_min, frag_max;
     int64_t C, nnz, names_bytes, src_size, src_mtime_ns;
+    int64_t aux_nnz_multi;      /* EMSARPK2: > 0 (or aux_present) = the derived arrays follow the names */
+    int32_t aux_present, aux_n_sets_nocut, aux_max_set_tids, reserved;
 } pack_header;
 
 static void src_stamp(const char *src, int64_t *size, int64_t *mtime_ns)
@@ -300,7 +303,8 @@ int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_
     if (!f) return fail(err, "can't write packed rsh image %s", tmp);
     pack_header h;
     memset(&h, 0, sizeof h);
-    memcpy(h.magic, "EMSARPK1", 8);
+    memcpy(h.magic, "EMSARPK2", 8);
+    if (r->has_aux) { h.aux_present = 1; h.aux_nnz_multi = r->aux_nnz_multi; h.aux_n_sets_nocut = r->aux_n_sets_nocut; h.aux_max_set_tids = r->aux_max_set_tids; }
     h.T = r->T; h.nF = r->nF; h.min_fraglength = r->min_fraglength; h.max_fraglength = r->max_fraglength; h.readlength = r->readlength;
     h.max_t_size = r->max_t_size; h.frag_min = r->frag_min; h.frag_max = r->frag_max;
     h.C = r->C; h.nnz = r->class_ptr[r->C];
@@ -312,6 +316,12 @@ int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_
     ok = ok && fwrite(r->euma, sizeof(int32_t), (size_t)r->C * r->nF, f) == (size_t)r->C * r->nF;
     ok = ok && fwrite(r->has_node, 1, (size_t)r->C, f) == (size_t)r->C;
     for (int32_t t = 0; ok && t < r->T; t++) ok = fwrite(r->names[t], 1, strlen(r->names[t]) + 1, f) == strlen(r->names[t]) + 1;
+    if (ok && r->has_aux) {       /* transpose, locality order, reachable classes: what emsar_index_create would otherwise derive */
+        ok = fwrite(r->aux_txm_off, sizeof(uint32_t), (size_t)r->T + 1, f) == (size_t)r->T + 1;
+        ok = ok && (r->aux_nnz_multi == 0 || fwrite(r->aux_txm_cid, sizeof(int32_t), (size_t)r->aux_nnz_multi, f) == (size_t)r->aux_nnz_multi);
+        ok = ok && fwrite(r->aux_order, sizeof(int32_t), (size_t)r->T, f) == (size_t)r->T;
+        ok = ok && (r->C == r->T || fwrite(r->aux_insertable, 1, (size_t)(r->C - r->T), f) == (size_t)(r->C - r->T));
+    }
     ok = (fclose(f) == 0) && ok;
     if (!ok || rename(tmp, path) != 0) { remove(tmp); return fail(err, "can't write packed rsh image %s", path); }
     return 0;
@@ -323,7 +333,7 @@ int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **ou
     FILE *f = fopen(path, "rb");
     if (!f) return fail(err, "can't open packed rsh image %s", path);
     pack_header h;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "EMSARPK1", 8) != 0 || h.T <= 0 || h.C < h.T || h.nF <= 0 || h.nnz < h.C || h.names_bytes < h.T) {
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "EMSARPK2", 8) != 0 || h.T <= 0 || h.C < h.T || h.nF <= 0 || h.nnz < h.C || h.names_bytes < h.T) {
         fclose(f);
         return fail(err, "%s is not a packed rsh image", path);
     }
@@ -347,6 +357,21 @@ int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **ou
     ok = ok && fread(r->euma, sizeof(int32_t), (size_t)h.C * h.nF, f) == (size_t)h.C * h.nF;
     ok = ok && fread(r->has_node, 1, (size_t)h.C, f) == (size_t)h.C;
     ok = ok && fread(blob, 1, (size_t)h.names_bytes, f) == (size_t)h.names_bytes;
+    if (ok && h.aux_present) {
+        ok = h.aux_nnz_multi == h.nnz - h.T;
+        r->aux_txm_off = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)h.T + 1));
+        r->aux_txm_cid = (int32_t *)malloc(sizeof(int32_t) * (size_t)(h.aux_nnz_multi > 0 ? h.aux_nnz_multi : 1));
+        r->aux_order = (int32_t *)malloc(sizeof(int32_t) * (size_t)h.T);
+        r->aux_insertable = (uint8_t *)malloc((size_t)(h.C - h.T > 0 ? h.C - h.T : 1));
+        r->aux_owned = 1;
+        ok = ok && r->aux_txm_off && r->aux_txm_cid && r->aux_order && r->aux_insertable;
+        ok = ok && fread(r->aux_txm_off, sizeof(uint32_t), (size_t)h.T + 1, f) == (size_t)h.T + 1;
+        ok = ok && (h.aux_nnz_multi == 0 || fread(r->aux_txm_cid, sizeof(int32_t), (size_t)h.aux_nnz_multi, f) == (size_t)h.aux_nnz_multi);
+        ok = ok && fread(r->aux_order, sizeof(int32_t), (size_t)h.T, f) == (size_t)h.T;
+        ok = ok && (h.C == h.T || fread(r->aux_insertable, 1, (size_t)(h.C - h.T), f) == (size_t)(h.C - h.T));
+        ok = ok && r->aux_txm_off[0] == 0 && (int64_t)r->aux_txm_off[h.T] == h.aux_nnz_multi;
+        if (ok) { r->has_aux = 1; r->aux_nnz_multi = h.aux_nnz_multi; r->aux_n_sets_nocut = h.aux_n_sets_nocut; r->aux_max_set_tids = h.aux_max_set_tids; }
+    }
     fclose(f);
     ok = ok && r->class_ptr[0] == 0 && r->class_ptr[h.C] == h.nnz && blob[h.names_bytes - 1] == 0;
     if (ok) {

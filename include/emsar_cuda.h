@@ -80,7 +80,21 @@ typedef struct {
     int32_t max_fraglength;    /* rsh header field 4 -> Max_Fraglength (:1420) */
     int32_t readlength;        /* rsh header field 5, -1 for SE (:1421) */
     int32_t max_t_size;        /* rsh header field 2 -> rshbucket_max_t_size (:1418) */
+    const struct emsar_index_aux *aux; /* optional: the derived structures from a packed image (below); NULL = derive them here */
 } emsar_index_desc;
+
+/* What emsar_index_create derives from the class table - the transpose of the multi-tid classes (build_TC_from_CT_2 :2201-2227), which
+ * classes the chain walk can reach (hash insertion), the set statistics without EUMAcut and the locality order of the transcripts. A packed
+ * index image carries them so that loading an index costs no pass over its members: emsar_index_aux_get hands out
+ * the arrays of a created index (valid until it is destroyed), emsar_index_desc.aux takes them back. They are trusted, not re-validated. */
+typedef struct emsar_index_aux {
+    int64_t nnz_multi;         /* members of the multi-tid classes */
+    const uint32_t *txm_off;   /* [T+1] */
+    const int32_t *txm_cid;    /* [nnz_multi] ascending cid per transcript */
+    const int32_t *order;      /* [T] emsar_locality_order mode 3 */
+    const uint8_t *insertable; /* [C-T] 1 = reachable by the reference's chain walk (:1603-1622) */
+    int32_t n_sets_nocut, max_set_tids;
+} emsar_index_aux;
 
 typedef struct {
     int32_t T;
@@ -103,6 +117,7 @@ int emsar_index_create(emsar_ctx *ctx, const emsar_index_desc *desc, emsar_index
  * 1, or 2 where that leaves fewer member references outside an SM's range; 0: tid order. */
 int emsar_locality_order(int32_t T, int64_t C, const int64_t *class_ptr, const int32_t *class_tid, int32_t mode, int32_t *order);
 int emsar_index_info_get(const emsar_index *index, emsar_index_info *info);
+int emsar_index_aux_get(const emsar_index *index, emsar_index_aux *aux);
 int emsar_index_destroy(emsar_index *index);
 
 /* -------- per-sample ----------------------------------------------------------------------------

@@ -170,3 +170,22 @@ def test_cli_restart_rounds_sd_column(built, tmp_path):
     assert amb.sum() >= 2 and abs(f1[amb].sum() - f4[amb].sum()) <= 1e-3 * max(f1[amb].sum(), 1.0) + 1e-3
     assert sd4[amb].max() > 100 * max(sd4[ident].max(), 1e-9)            # the split between indistinguishable transcripts depends on the start
     assert open(os.path.join(str(tmp_path), "one", "p.0.segments")).read() == open(os.path.join(str(tmp_path), "n4", "p.0.segments")).read()
+
+
+def test_cli_complete_index_image(built, tmp_path):
+    """with EMSAR_RSH_CACHE=1 the first run writes <rsh>.pack including what the device library derived (transpose,
+    locality order, reachable classes, set statistics); the second run creates the index from the image without deriving anything and
+    writes the same files byte for byte."""
+    fx = gu.FIXTURES["config1"]
+    rsh, aln = gu.materialize(fx["rsh"], tmp_path), gu.materialize(fx["aln"], tmp_path)
+    env = dict(os.environ, EMSAR_RSH_CACHE="1")
+    outs = []
+    for tag in ("first", "second"):
+        out = os.path.join(str(tmp_path), tag)
+        r = subprocess.run([EMSAR, "-g", "-P", "-S", "-I", rsh, out, "p", aln], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append((out, r.stdout))
+    assert "packed index image written" in outs[0][1] and os.path.exists(rsh + ".pack")
+    assert "rsh index taken from its packed image" in outs[1][1] and "nothing derived at load" in outs[1][1]
+    for ext in ("fpkm", "segments", "fraglength_effect"):
+        assert open(os.path.join(outs[0][0], f"p.0.{ext}")).read() == open(os.path.join(outs[1][0], f"p.0.{ext}")).read(), ext

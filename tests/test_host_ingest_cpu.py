@@ -97,8 +97,24 @@ def test_packed_rsh_image_round_trip(built, tmp_path, monkeypatch):
     e = host.Rsh(txt, auto=True)
     f = host.Rsh(txt, auto=True)
     assert not e.from_cache and f.from_cache and _same_index(a, f)
+    # a complete image: the derived arrays (transpose, locality order, reachable classes) travel with it
+    T, Cn = a.T, a.C
+    k = np.diff(a.class_ptr)[T:]
+    cid = np.repeat(np.arange(T, Cn, dtype=np.int32), k)
+    tids = a.class_tid[T:]
+    o = np.lexsort((cid, tids))
+    txm_off = np.concatenate([[0], np.cumsum(np.bincount(tids, minlength=T))]).astype(np.uint32)
+    g = host.Rsh(txt)
+    g.set_aux(txm_off, cid[o], np.arange(T)[::-1], np.ones(Cn - T, dtype=np.uint8), 7, 42)
+    g.save_packed(str(tmp_path / "full.pack"), src=txt)
+    h = host.Rsh(str(tmp_path / "full.pack"), packed=True, src=txt)
+    ax = h.aux()
+    assert _same_index(a, h) and ax is not None and b.aux() is None
+    assert np.array_equal(ax["txm_off"], txm_off) and np.array_equal(ax["txm_cid"], cid[o]) and np.array_equal(ax["order"], np.arange(T)[::-1])
+    assert ax["insertable"].all() and (ax["n_sets_nocut"], ax["max_set_tids"], ax["nnz_multi"]) == (7, 42, len(cid))
+    g.close(); h.close()
     # garbage is rejected
-    (tmp_path / "bad.pack").write_bytes(b"EMSARPK1" + b"\0" * 40)
+    (tmp_path / "bad.pack").write_bytes(b"EMSARPK2" + b"\0" * 40)
     with pytest.raises(host.HostError):
         host.Rsh(str(tmp_path / "bad.pack"), packed=True)
     for r in (a, b, c, d, e, f):
