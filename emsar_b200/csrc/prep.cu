@@ -695,6 +695,128 @@ static void compute_sets(const emsar_index *ix, const std::vector<double> &adj, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Device: the same decomposition (propagate_2 :2234-2259 with the EUMAcut loop of emsar_main.c:411-425) as label propagation. Every
+// transcript starts as its own label; a class that survives the cut pulls all its members to the smallest label among them
+// (atomicMin), labels are shortened by pointer jumping, until nothing changes: a transcript's label is then the smallest tid of its
+// set. The reference numbers the sets in the order its scan first meets them, and it meets the singleton class of every transcript
+// (cid == tid) before any multi-tid class: set ids are the ranks of those smallest tids. Integer work only: the result is exact.
+__global__ void k_cc_init(int32_t T, int32_t *__restrict__ label)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) label[t] = t;
+}
+__global__ void k_cc_hook(int64_t n_multi, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const double *__restrict__ adj,
+                          double cut, int32_t *__restrict__ label, int *__restrict__ changed)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_multi) return;
+    if (adj[T + i] < cut) return;                                   // propagate_2 :2242
+    const uint32_t o = cls_off[T + i], e = cls_off[T + i + 1];
+    int m = 0x7fffffff;
+    for (uint32_t j = o + lane; j < e; j += 32) m = min(m, label[cls_tid[j]]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+    bool ch = false;
+    for (uint32_t j = o + lane; j < e; j += 32) {
+        const int t = cls_tid[j];
+        if (label[t] > m) { atomicMin(&label[t], m); ch = true; }
+        const int r = label[m];                                     // keep the trees shallow: the root of the minimum, too
+        if (r < m) atomicMin(&label[t], r);
+    }
+    if (__any_sync(0xffffffffu, ch) && lane == 0) *changed = 1;
+}
+__global__ void k_cc_jump(int32_t T, int32_t *__restrict__ label, int *__restrict__ changed)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int l = label[t];
+    int r = label[l];
+    if (r != l) {
+        while (label[r] != r) r = label[r];
+        label[t] = r;
+        *changed = 1;
+    }
+}
+__global__ void k_cc_sizes(int32_t T, const int32_t *__restrict__ label, int32_t *__restrict__ size, uint32_t *__restrict__ isroot)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > T) return;
+    if (t == T) { isroot[T] = 0; return; }
+    atomicAdd(&size[label[t]], 1);
+    isroot[t] = label[t] == t ? 1u : 0u;
+}
+__global__ void k_cc_max(int32_t T, const int32_t *__restrict__ size, int32_t *__restrict__ mx)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = t < T ? size[t] : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(mx, v);
+}
+__global__ void k_cc_class_sets(int64_t C, int32_t T, const uint32_t *__restrict__ cls_off, const int32_t *__restrict__ cls_tid, const double *__restrict__ adj,
+                                double cut, const int32_t *__restrict__ label, const uint32_t *__restrict__ sid_of_root, int32_t *__restrict__ CS,
+                                uint8_t *__restrict__ in_model)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int cs = -1;
+    if (c < T || adj[c] >= cut) cs = (int)sid_of_root[label[cls_tid[cls_off[c]]]];
+    CS[c] = cs;
+    in_model[c] = cs >= 0 ? 1 : 0;
+}
+
+// sets on the device: fills d_CS [C] and d_in_model [C], raises *eumacut by 2 until no set has more than max_ntid transcripts
+static int device_sets(emsar_sample *s, double *eumacut, int max_ntid, int32_t *d_CS, uint8_t *d_in_model, int32_t *max_sid)
+{
+    emsar_index *ix = s->index; emsar_ctx *ctx = s->ctx; cudaStream_t st = ctx->stream;
+    const int32_t T = ix->T;
+    const int64_t C = ix->C, nm = ix->n_multi;
+    int32_t *d_label = nullptr, *d_size = nullptr, *d_flag = nullptr;
+    uint32_t *d_isroot = nullptr, *d_sid = nullptr;
+    TRY(dev_alloc(&d_label, (size_t)T + 1)); TRY(dev_alloc(&d_size, (size_t)T + 1)); TRY(dev_alloc(&d_flag, 4));
+    TRY(dev_alloc(&d_isroot, (size_t)T + 1)); TRY(dev_alloc(&d_sid, (size_t)T + 1));
+    struct G { int32_t *a, *b, *c; uint32_t *d, *e; ~G() { dev_free(a); dev_free(b); dev_free(c); dev_free(d); dev_free(e); } } g{d_label, d_size, d_flag, d_isroot, d_sid};
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, T + 1);
+    void *d_tmp = nullptr;
+    TRY(ctx_scratch(ctx, scan_bytes + 256, &d_tmp));
+    const unsigned bt = (unsigned)((T + 255) / 256), bc = (unsigned)((nm * 32 + 255) / 256);
+    for (;;) {
+        k_cc_init<<<bt, 256, 0, st>>>(T, d_label);
+        LAUNCHED(ctx);
+        for (int round = 0; round < 4096; round++) {
+            CU(cudaMemsetAsync(d_flag, 0, 4, st));
+            if (nm > 0) k_cc_hook<<<bc, 256, 0, st>>>(nm, T, ix->d_cls_off, ix->d_cls_tid, s->d_adj, *eumacut, d_label, d_flag);
+            k_cc_jump<<<bt, 256, 0, st>>>(T, d_label, d_flag);
+            ctx->launches += 2;
+            int changed = 0;
+            CU(cudaMemcpyAsync(&changed, d_flag, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (!changed) break;
+        }
+        CU(cudaMemsetAsync(d_size, 0, ((size_t)T + 1) * 4, st));
+        CU(cudaMemsetAsync(d_flag, 0, 4, st));
+        k_cc_sizes<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(T, d_label, d_size, d_isroot);
+        k_cc_max<<<bt, 256, 0, st>>>(T, d_size, d_flag);
+        ctx->launches += 2;
+        int mx = 0;
+        CU(cudaMemcpyAsync(&mx, d_flag, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (mx > max_ntid) { *eumacut += 2; continue; }             // EUMACUT_INCREMENT, emsar_main.c:417-423
+        break;
+    }
+    CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_isroot, d_sid, T + 1, st));
+    k_cc_class_sets<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, T, ix->d_cls_off, ix->d_cls_tid, s->d_adj, *eumacut, d_label, d_sid, d_CS, d_in_model);
+    ctx->launches += 2;
+    uint32_t nsets = 0;
+    CU(cudaMemcpyAsync(&nsets, d_sid + T, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *max_sid = (int32_t)nsets - 1;
+    return EMSAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 template <class T> static T *arena_take(char *&cur, size_t n)
 {
     T *p = (T *)cur;
@@ -757,15 +879,28 @@ extern "C" int emsar_sample_prepare(emsar_sample *s, const emsar_solve_opts *opt
         d_in_model = s->d_in_model;
         s->max_sid = -1;
     } else if (s->eumacut > 0 || ix->max_set_tids > o.max_ntid_per_sid) {
-        std::vector<double> adj((size_t)C);
-        CU(cudaMemcpyAsync(adj.data(), s->d_adj, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        compute_sets(ix, adj, &s->eumacut, o.max_ntid_per_sid, &s->h_CS, &s->max_sid);
-        s->have_CS = true;
-        std::vector<uint8_t> im((size_t)C);
-        for (int64_t c = 0; c < C; c++) im[(size_t)c] = s->h_CS[(size_t)c] >= 0;
-        CU(cudaMemcpyAsync(s->d_in_model, im.data(), (size_t)C, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
+        if (getenv("EMSAR_SETS_HOST")) {          // the host union-find (cross-check of the device decomposition)
+            std::vector<double> adj((size_t)C);
+            CU(cudaMemcpyAsync(adj.data(), s->d_adj, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            compute_sets(ix, adj, &s->eumacut, o.max_ntid_per_sid, &s->h_CS, &s->max_sid);
+            s->have_CS = true;
+            std::vector<uint8_t> im((size_t)C);
+            for (int64_t c = 0; c < C; c++) im[(size_t)c] = s->h_CS[(size_t)c] >= 0;
+            CU(cudaMemcpyAsync(s->d_in_model, im.data(), (size_t)C, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        } else {
+            int32_t *d_CS = nullptr;
+            TRY(dev_alloc(&d_CS, (size_t)C));
+            int rc_ = device_sets(s, &s->eumacut, o.max_ntid_per_sid, d_CS, s->d_in_model, &s->max_sid);
+            if (rc_ == EMSAR_OK) {
+                s->h_CS.resize((size_t)C);
+                rc_ = cudaMemcpyAsync(s->h_CS.data(), d_CS, (size_t)C * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess ? EMSAR_OK : EMSAR_ERR_CUDA;
+                s->have_CS = rc_ == EMSAR_OK;
+            }
+            dev_free(d_CS);
+            if (rc_ != EMSAR_OK) return rc_;
+        }
         d_in_model = s->d_in_model;
     } else {
         s->max_sid = ix->n_sets_nocut - 1;
@@ -1300,11 +1435,25 @@ int sample_ensure_sets(emsar_sample *s)
 {
     if (s->have_CS) return EMSAR_OK;
     emsar_index *ix = s->index;
-    std::vector<double> adj((size_t)ix->C);
-    CU(cudaMemcpyAsync(adj.data(), s->d_adj, (size_t)ix->C * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
-    CU(cudaStreamSynchronize(s->ctx->stream));
+    TRY(ctx_use(s->ctx));
     double cut = s->eumacut;
-    compute_sets(ix, adj, &cut, s->opts.max_ntid_per_sid > 0 ? s->opts.max_ntid_per_sid : 5000, &s->h_CS, &s->max_sid);
-    s->have_CS = true;
-    return EMSAR_OK;
+    const int cap = s->opts.max_ntid_per_sid > 0 ? s->opts.max_ntid_per_sid : 5000;
+    if (getenv("EMSAR_SETS_HOST")) {
+        std::vector<double> adj((size_t)ix->C);
+        CU(cudaMemcpyAsync(adj.data(), s->d_adj, (size_t)ix->C * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+        CU(cudaStreamSynchronize(s->ctx->stream));
+        compute_sets(ix, adj, &cut, cap, &s->h_CS, &s->max_sid);
+        s->have_CS = true;
+        return EMSAR_OK;
+    }
+    int32_t *d_CS = nullptr; uint8_t *d_im = nullptr;
+    TRY(dev_alloc(&d_CS, (size_t)ix->C)); TRY(dev_alloc(&d_im, (size_t)ix->C));
+    int rc = device_sets(s, &cut, cap, d_CS, d_im, &s->max_sid);
+    if (rc == EMSAR_OK) {
+        s->h_CS.resize((size_t)ix->C);
+        rc = cudaMemcpyAsync(s->h_CS.data(), d_CS, (size_t)ix->C * 4, cudaMemcpyDeviceToHost, s->ctx->stream) == cudaSuccess && cudaStreamSynchronize(s->ctx->stream) == cudaSuccess ? EMSAR_OK : EMSAR_ERR_CUDA;
+        s->have_CS = rc == EMSAR_OK;
+    }
+    dev_free(d_CS); dev_free(d_im);
+    return rc;
 }
