@@ -683,7 +683,7 @@ def main():
                          "traffic_note": "DRAM bytes per launch (ncu, profiles/traffic.json); algorithmic bytes per launch = bytes_per_iter x "
                                          "em_iters_per_step: the packed model is L2-resident after the first iteration",
                          "algorithmic_bytes_per_launch": int(st["bytes_per_iter"]) * int(args.em_iters),
-                         "peak_source": peak_src, "kernel": f"k_em_persistent<{st['em_variant']}>", "bytes_per_iter": st["bytes_per_iter"],
+                         "peak_source": peak_src, "kernel": "k_em_psum" if st['em_variant'] == 5 else f"k_em_persistent<{st['em_variant']}>", "bytes_per_iter": st["bytes_per_iter"],
                          "us_per_iter": 1e6 * t_em / max(iters_done, 1)},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
