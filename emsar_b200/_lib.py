@@ -63,6 +63,7 @@ SYMBOLS = [
     "emsar_sample_solve", "emsar_sample_segments_get", "emsar_sample_wf_get", "emsar_sample_end", "emsar_sample_prepare",
     "emsar_sample_model_stats", "emsar_sample_em_run", "emsar_sample_theta_get", "emsar_sample_theta_randomize", "emsar_sample_finalize",
     "emsar_host_alloc", "emsar_host_free", "emsar_sample_count_wait", "emsar_comm_unique_id", "emsar_comm_init", "emsar_comm_destroy", "emsar_comm_info", "emsar_sample_counts_allreduce", "emsar_shard_ranges", "emsar_locality_order", "emsar_cuda_timer_start", "emsar_cuda_timer_stop", "emsar_sample_time_adjeuma",
+    "emsar_build_classes_run", "emsar_build_classes_free",
 ]
 
 

@@ -80,12 +80,12 @@ def build_host(force=False):
                   "-o", out] + lib_srcs + ["-lz", "-lm", "-lpthread"])
         outs.append(out)
     bmain = os.path.join(HOST, "emsar_build_main.c")
-    if os.path.exists(bmain):          # index construction runs on the CPU: no CUDA library behind it
+    if os.path.exists(bmain):          # no link-time CUDA dependency: --device loads libemsar_cuda.so at run time
         os.makedirs(os.path.join(PKG, "bin"), exist_ok=True)
         out = os.path.join(PKG, "bin", "emsar-build")
         if force or _newer(out, srcs + hdrs):
             _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out, bmain] + lib_srcs +
-                 ["-lz", "-lm", "-lpthread"])
+                 ["-lz", "-lm", "-lpthread", "-ldl"])
         outs.append(out)
     main = os.path.join(HOST, "emsar_main.c")
     if os.path.exists(main):

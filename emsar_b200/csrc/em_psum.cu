@@ -39,6 +39,16 @@ template <bool RES> __device__ __forceinline__ uint32_t ps_ld32(const unsigned c
     return __ldg((const uint32_t *)g + off4);
 }
 
+// maximum over the warp of a value >= +0 that is not NaN: such doubles order like their bit patterns, two integer warp reductions
+// (high word, then the low words of the lanes that hold the maximal high word) replace ten shuffles. A NaN wins.
+__device__ __forceinline__ double ps_warp_max(double x)
+{
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 __device__ __forceinline__ double ps_q_of(uint32_t r, double s) { return s > 0 ? fast_div((double)r, s) : 0.0; }
 
 __device__ __forceinline__ double ps_gather4(const double *a, uint2 w, double s)
@@ -211,12 +221,16 @@ __device__ __forceinline__ void ps_m_item(const PsParams &p, const PsView &v, co
 
 #define PS_TRACE(slot) do { if (p.trace && it == p.max_iter - 1 && threadIdx.x == 0) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
 
+// SCHED bit 0: the E tiles are dealt to the warps in a fixed boustrophedon order over the cost-sorted list (no ticket, the next descriptor is
+// requested while the current tile is processed) instead of being taken from the CTA's work queue.
+template <int SCHED>
 __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
 {
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     __shared__ double sm_red[EM_WARPS];
     __shared__ double sm_bc;
     __shared__ int sm_ctr[2];
+    __shared__ int sm_flag;          // bit 0: some CTA's convergence measure of the previous iteration is above 1; bit 1: abort
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = (int)blockIdx.x + p.m.block0;
     const int row0 = p.m.blk_row0[b], nrows = p.m.blk_row0[b + 1] - row0;
@@ -292,16 +306,32 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     };
     int it = 0;
     double d = INFINITY;
-    bool stopped = false;
+    // the slots of a thread's first two halo rows stay in registers: one dependent round trip less at the top of every iteration
+    const int hs0 = (int)threadIdx.x < nhr ? __ldg(p.m.halo_rows + hr0 + threadIdx.x) : 0;
+    const int hs1 = (int)threadIdx.x + EM_BLOCK < nhr ? __ldg(p.m.halo_rows + hr0 + threadIdx.x + EM_BLOCK) : 0;
     while (it < p.max_iter) {
         const unsigned tag = p.tag0 + (unsigned)it + 1u;
         PS_TRACE(0);
         // theta of the halo rows, as their owners published it
-        for (int i = threadIdx.x; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
-        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; }
+        if ((int)threadIdx.x < nhr) v.theta[nrows + threadIdx.x] = ll_load(th_slots + 16 * (size_t)hs0, tag, p.abort_flag);
+        if ((int)threadIdx.x + EM_BLOCK < nhr) v.theta[nrows + threadIdx.x + EM_BLOCK] = ll_load(th_slots + 16 * (size_t)hs1, tag, p.abort_flag);
+        for (int i = threadIdx.x + 2 * EM_BLOCK; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
+        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; sm_flag = 0; }
         __syncthreads();
         PS_TRACE(1);
-        if (desc_smem) {
+        if (SCHED & 1) {
+            int pos = warp;
+            int4 t = pos < n_et ? et[n_et - 1 - pos] : make_int4(0, 0, 0, 0);
+            for (int j = 0; pos < n_et; ) {
+                j++;
+                const int pos2 = j * 32 + ((j & 1) ? 31 - warp : warp);
+                // a position beyond the list in an odd stripe belongs to no tile: the warp's list ends there (stripe j + 1 is beyond it as well)
+                const int4 t2 = pos2 < n_et ? et[n_et - 1 - pos2] : make_int4(0, 0, 0, 0);
+                if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
+                else ps_e_tile<false>(v, t, p.m.e_data, gR, lane);
+                pos = pos2; t = t2;
+            }
+        } else if (desc_smem) {
             for (int tk = next_item(&sm_ctr[0], lane); tk < n_et; tk = next_item(&sm_ctr[0], lane)) {
                 const int4 t = et[n_et - 1 - tk];               // tiles are ordered by cardinality: heaviest first
                 if ((t.w >> 30) & 1) ps_e_tile<true>(v, t, nullptr, nullptr, lane);
@@ -320,13 +350,19 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
             }
         }
         PS_TRACE(2);
-        if (it > 0) {
-            d = read_dm(it - 1);
-            if (*((volatile int *)p.abort_flag) != 0 || (p.stop_on_conv && d <= 1.0)) { stopped = true; break; }
-        } else __syncthreads();
+        __syncthreads();
+        // the convergence measure of the previous iteration: every CTA's slot is polled by one thread, by the first warps, before they join the
+        // M-phase queue - the other warps start on the items at once, and nobody waits for the result before the end of the M-phase (theta is
+        // untouched until the U-phase, so that stopping after the M-phase leaves exactly the previous iteration's state)
+        if (it > 0 && (int)threadIdx.x < Bt) {
+            double x = 0;
+            for (int i = threadIdx.x; i < Bt; i += EM_BLOCK) x = fmax(x, ll_load(dm_slots + 16 * (size_t)(((it - 1) & 1) * Bt + i), tag - 1u, p.abort_flag));
+            if (!(x <= 1.0)) atomicOr(&sm_flag, 1);
+        }
+        if (threadIdx.x == 0 && *((volatile int *)p.abort_flag) != 0) atomicOr(&sm_flag, 2);
         if (desc_smem) {
             for (int tk = next_item(&sm_ctr[1], lane); tk < n_mi; tk = next_item(&sm_ctr[1], lane)) {
-                const int4 t = mi[tk];                          // items are ordered longest first
+                const int4 t = mi[tk];                          // items: groups of long rows, then slices, longest first
                 if ((t.w >> 29) & 1) ps_m_item<true>(p, v, t, nullptr, lane, tag);
                 else ps_m_item<false>(p, v, t, p.m.m_data, lane, tag);
             }
@@ -343,6 +379,10 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         }
         __syncthreads();
         PS_TRACE(3);
+        {
+            const int fl = sm_flag;
+            if ((fl & 2) || (p.stop_on_conv && it > 0 && !(fl & 1))) break;      // the same decision in every CTA: they all read the same slots
+        }
         // owner update: own partial sum + the contributions of the other CTAs, in CTA order. The constants of a thread's first two rows are
         // requested first, then every incoming partial sum is fetched by its own thread (one round trip for all of them) and staged
         double dm = 0;
@@ -372,20 +412,18 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         if (i1 < nrows) update(i1, ra1, a1, b1, mk1);
         for (int i = threadIdx.x + 2 * EM_BLOCK; i < nrows; i += EM_BLOCK)
             update(i, __ldg(p.m.row_RsA + row0 + i), __ldg(p.m.inc_off + row0 + i), __ldg(p.m.inc_off + row0 + i + 1), (unsigned)__ldg(p.m.row_mask + row0 + i));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        dm = ps_warp_max(dm);
         if (lane == 0) sm_red[warp] = dm;
         __syncthreads();
-        if ((int)threadIdx.x < p.m.nranks) {                     // one store per rank: every CTA of every rank reads every CTA's measure
-            double bm = 0;
-            for (int w = 0; w < EM_WARPS; w++) bm = fmax(bm, sm_red[w]);
-            ll_store(p.m.win[threadIdx.x] + p.m.dm_off + 16 * (size_t)((it & 1) * Bt + b), bm, tag);
+        if (warp == 0) {                                         // one store per rank: every CTA of every rank reads every CTA's measure
+            const double bm = ps_warp_max(sm_red[lane]);
+            if (lane < p.m.nranks) ll_store(p.m.win[lane] + p.m.dm_off + 16 * (size_t)((it & 1) * Bt + b), bm, tag);
         }
-        __syncthreads();                                         // sm_red is reused by read_dm
-        PS_TRACE(4);
+        PS_TRACE(4);                                             // (sm_red is written again three barriers from here)
         it++;
     }
-    if (it > 0 && !stopped) d = read_dm(it - 1);
+    __syncthreads();
+    if (it > 0) d = read_dm(it - 1);
     if (*((volatile int *)p.abort_flag) != 0) d = INFINITY;
     __syncthreads();
     for (int i = threadIdx.x; i < nrows; i += EM_BLOCK) p.m.theta[row0 + i] = v.theta[i];      // the copy the output kernels read
@@ -398,11 +436,22 @@ __global__ void k_ps_theta_to_slots(int32_t P, const double *__restrict__ theta,
     if (p < P) ll_store(th_slots + 16 * (size_t)p, theta[p], tag);
 }
 
+// EMSAR_PS_SCHED: 0 (default) = E tiles taken from the CTA's work queue, 1 = dealt to the warps in a fixed order (measured slower, profiles/r2o:
+// 23.6 vs 22.0 us at config #2, 194 vs 171 at config #5 - the queue's balance inside a CTA is worth more than the 20 instructions of a ticket)
+static int ps_sched()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EMSAR_PS_SCHED"); v = e ? (atoi(e) & 1) : 0; }
+    return v;
+}
+typedef void (*ps_kernel_t)(PsParams);
+static ps_kernel_t ps_kernel() { return ps_sched() ? k_em_psum<1> : k_em_psum<0>; }
+
 int em_psum_attr(emsar_ctx *ctx)
 {
-    CU(cudaFuncSetAttribute(k_em_psum, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));
+    CU(cudaFuncSetAttribute(ps_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_psum, EM_BLOCK, ctx->em_smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ps_kernel(), EM_BLOCK, ctx->em_smem_bytes));
     if (nb < 1) { emsar_set_err("k_em_psum does not fit on an SM (%d bytes of shared memory)", ctx->em_smem_bytes); return EMSAR_ERR_CUDA; }
     return EMSAR_OK;
 }
@@ -476,9 +525,9 @@ int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_d
     }
     cfg.attrs = attrs;
     cfg.numAttrs = na;
-    CU(cudaFuncSetAttribute(k_em_psum, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));    // per device, and other contexts may have changed it
+    CU(cudaFuncSetAttribute(ps_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->em_smem_bytes));    // per device, and other contexts may have changed it
     CU(cudaEventRecord(ctx->ev0, st));
-    CU(cudaLaunchKernelEx(&cfg, k_em_psum, p));
+    CU(cudaLaunchKernelEx(&cfg, ps_kernel(), p));
     LAUNCHED(ctx);
     CU(cudaEventRecord(ctx->ev1, st));
     if (multi && s->ps.P > 0) {
@@ -501,5 +550,54 @@ int em_psum_launch(emsar_sample *s, int max_iter, int stop_on_conv, int *iters_d
     if (iters_done) *iters_done = it;
     if (final_delta) *final_delta = fd;
     if (ms_out) *ms_out = ms;
+    return EMSAR_OK;
+}
+
+// tuning aid (profiles/trace_psum.py): per CTA, 16 numbers that describe its share of the packed model -
+// {rows, halo rows, classes, incoming partial sums, E tiles, M items, resident 16-byte units, descriptors in smem,
+//  cardinality-2 tiles, cardinality-3/4 tiles, chunk steps of one-lane tiles, chunk steps of multi-lane tiles, resident E tiles,
+//  chunk steps of slices, 32-word blocks of groups, resident M items}
+extern "C" int emsar_debug_psum_blocks(emsar_sample *s, int32_t *out, int *n_blocks)
+{
+    if (!s || !s->prepared || !s->use_psum) return EMSAR_ERR_STATE;
+    TRY(ctx_use(s->ctx));
+    const PsModel &m = s->ps;
+    const int B = m.B, b0 = m.block0;
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    std::vector<int32_t> row0(B + 1), cls0(B + 1), et0(B + 1), mi0(B + 1), hr0(B + 1), res(B + 1), desc(B + 1);
+    CU(cudaMemcpy(row0.data(), m.blk_row0 + b0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cls0.data(), m.blk_cls0 + b0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(et0.data(), m.blk_etile0 + b0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(mi0.data(), m.blk_mitem0 + b0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hr0.data(), m.blk_hr0 + b0, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(res.data(), m.blk_res16 + b0, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(desc.data(), m.blk_desc_smem + b0, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    std::vector<int4> et((size_t)(et0[B] - et0[0]) + 1), mi((size_t)(mi0[B] - mi0[0]) + 1);
+    if (et0[B] > et0[0]) CU(cudaMemcpy(et.data(), m.e_tiles + et0[0], (size_t)(et0[B] - et0[0]) * 16, cudaMemcpyDeviceToHost));
+    if (mi0[B] > mi0[0]) CU(cudaMemcpy(mi.data(), m.m_items + mi0[0], (size_t)(mi0[B] - mi0[0]) * 16, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; b++) {
+        int32_t *o = out + 16 * (size_t)b;
+        int32_t in_lo = 0, in_hi = 0;
+        CU(cudaMemcpy(&in_lo, m.inc_off + row0[b], 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&in_hi, m.inc_off + row0[b + 1], 4, cudaMemcpyDeviceToHost));
+        o[0] = row0[b + 1] - row0[b]; o[1] = hr0[b + 1] - hr0[b]; o[2] = cls0[b + 1] - cls0[b]; o[3] = in_hi - in_lo;
+        o[4] = et0[b + 1] - et0[b]; o[5] = mi0[b + 1] - mi0[b]; o[6] = res[b]; o[7] = desc[b];
+        for (int k = 8; k < 16; k++) o[k] = 0;
+        for (int i = et0[b] - et0[0]; i < et0[b + 1] - et0[0]; i++) {
+            const int4 t = et[(size_t)i];
+            const int steps = t.w & 0xfff, lg = (t.w >> 12) & 0xf, nb = std::max(1, (t.w >> 16) & 0xff);
+            if (lg == 0 && steps <= 4) o[steps == 2 ? 8 : 9]++;
+            else if (lg == 0) o[10] += (steps + 3) >> 2;
+            else o[11] += nb * ((steps + 3) >> 2);
+            if ((t.w >> 30) & 1) o[12]++;
+        }
+        for (int i = mi0[b] - mi0[0]; i < mi0[b + 1] - mi0[0]; i++) {
+            const int4 t = mi[(size_t)i];
+            const int len = t.w & 0x1fffffff;
+            if ((t.w >> 30) & 1) o[14] += (t.x * 4 + 31) / 32; else o[13] += (len + 3) >> 2;
+            if ((t.w >> 29) & 1) o[15]++;
+        }
+    }
+    *n_blocks = B;
     return EMSAR_OK;
 }

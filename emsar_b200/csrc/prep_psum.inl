@@ -116,19 +116,23 @@ __global__ void k_ps_touched(int64_t n, const unsigned long long *__restrict__ k
     tr_key[tidx[i]] = keys[i] >> 16;            // (CTA << 16) | row slot
     tr_start[tidx[i]] = (uint32_t)i;
 }
+// Order of a CTA's touched rows: long rows (groups) first, then the short rows, longest first. With remote_first the short rows whose owner is
+// another CTA come before its own, so that the partial sums other CTAs wait for are sent in the first part of the M-phase.
 __global__ void k_ps_touched_keys(uint32_t n_tr, const unsigned long long *__restrict__ tr_key, const uint32_t *__restrict__ tr_start,
-                                  unsigned long long *__restrict__ key, int32_t *__restrict__ val)
+                                  const int32_t *__restrict__ row0, int remote_first, unsigned long long *__restrict__ key, int32_t *__restrict__ val)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_tr) return;
     const uint32_t deg = tr_start[j + 1] - tr_start[j];
-    key[j] = ((tr_key[j] >> 16) << 32) | (unsigned long long)(0xFFFFFFFFu - deg);      // (CTA, longest first)
+    const int b = (int)(tr_key[j] >> 16), slot = (int)(tr_key[j] & 0xffffu);
+    const uint32_t part = deg > (uint32_t)M_LONG ? 2u : ((remote_first && slot >= row0[b + 1] - row0[b]) ? 1u : 0u);
+    key[j] = ((tr_key[j] >> 16) << 32) | (unsigned long long)(0xFFFFFFFFu - ((part << 28) | (deg & 0x0FFFFFFFu)));
     val[j] = (int32_t)j;
 }
 __global__ void k_ps_sorted_deg(uint32_t n_tr, const unsigned long long *__restrict__ skey, uint32_t *__restrict__ tdeg)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j <= n_tr) tdeg[j] = j < n_tr ? 0xFFFFFFFFu - (uint32_t)skey[j] : 0u;
+    if (j <= n_tr) tdeg[j] = j < n_tr ? ((0xFFFFFFFFu - (uint32_t)skey[j]) & 0x0FFFFFFFu) : 0u;
 }
 
 // M items of every CTA over its touched rows (sorted longest first): groups of its long rows, then slices of 32 rows.
@@ -178,7 +182,8 @@ __global__ void k_ps_items_fill(int B, const int32_t *__restrict__ tr0, const ui
     }
     const int nrows = r1 - r0;
     for (int s0 = nl; s0 < nrows; s0 += 32, g++) {
-        const uint32_t d = tdeg[r0 + s0];
+        uint32_t d = 0;                                 // the slice that straddles the remote / own boundary is not sorted
+        for (int i = s0; i < min(s0 + 32, nrows); i++) d = max(d, tdeg[r0 + i]);
         const uint32_t s16 = (uint32_t)ps_slice_u16((int)d) >> 3;
         items[g] = make_int4((int)s16, min(32, nrows - s0), 0, (int)d);
         size16[g] = s16;
@@ -515,7 +520,10 @@ static int sample_build_psum(emsar_sample *s, const PsPrepIn &in)
         }
     }
     k_ps_touched<<<(unsigned)((nnz_a + 255) / 256), 256, 0, st>>>((int64_t)nnz_a, d_pb, d_flag, d_tidx, n_tr, d_trkey, d_trstart);
-    k_ps_touched_keys<<<(n_tr + 255) / 256, 256, 0, st>>>(n_tr, d_trkey, d_trstart, d_k2, d_v2);
+    // EMSAR_PS_MORDER=1: remote-owner rows first in the M-phase. Measured (profiles/r2p): no gain on one GPU (21.8 us both ways at config #2,
+    // 167.2 vs 165.0 us at config #5: the mixed slice costs padding), so the plain longest-first order is the default
+    static const int remote_first = []() { const char *e = getenv("EMSAR_PS_MORDER"); return e ? atoi(e) : 0; }();
+    k_ps_touched_keys<<<(n_tr + 255) / 256, 256, 0, st>>>(n_tr, d_trkey, d_trstart, m.blk_row0, remote_first, d_k2, d_v2);
     CU(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_k2, d_sk2, d_v2, d_tperm, (int)n_tr, 0, 32 + cta_bits, st));
     k_ps_sorted_deg<<<(n_tr + 1 + 255) / 256, 256, 0, st>>>(n_tr, d_sk2, d_tdeg);
     k_halo_ranges<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(B, n_tr, d_sk2, d_tr0);

@@ -22,10 +22,13 @@
 #define _GNU_SOURCE
 #include <pthread.h>
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "emsar_host.h"
+#include "emsar_cuda.h"       /* emsar_build_desc / emsar_build_classes: the layout of the device builder's interface (no link dependency) */
 
 static int fail(char *err, const char *fmt, ...)
 {
@@ -193,8 +196,8 @@ static void cs_rehash(cstore *c)
     }
     free(c->slots); c->slots = ns; c->mask = nmask;
 }
-/* update_rshbucket(..., 'e', fi): the class of the sorted tid multiset t[0..k) gains one substring at fragment-length index fi */
-static void cs_add(cstore *c, const int32_t *t, int k, int fi)
+/* the EUMA row of the class of the sorted tid multiset t[0..k), created (all zero) when it is new */
+static int32_t *cs_row(cstore *c, const int32_t *t, int k)
 {
     if (k > c->max_k) c->max_k = k;
     uint64_t s = key_hash(t, k) & c->mask;
@@ -202,7 +205,7 @@ static void cs_add(cstore *c, const int32_t *t, int k, int fi)
         uint64_t v = c->slots[s];
         if (!v) break;
         const bclass *b = &c->cls[v - 1];
-        if (b->k == k && memcmp(c->tids + b->tid_off, t, sizeof(int32_t) * (size_t)k) == 0) { c->euma[b->euma_row * c->nF + fi]++; return; }
+        if (b->k == k && memcmp(c->tids + b->tid_off, t, sizeof(int32_t) * (size_t)k) == 0) return c->euma + b->euma_row * c->nF;
         s = (s + 1) & c->mask;
     }
     if (c->ncls == c->capcls) { c->capcls = c->capcls ? c->capcls * 2 : 4096; c->cls = (bclass *)realloc(c->cls, sizeof(bclass) * (size_t)c->capcls); }
@@ -212,11 +215,14 @@ static void cs_add(cstore *c, const int32_t *t, int k, int fi)
     b->k = k; b->tid_off = c->ntids; b->euma_row = c->nrows;
     memcpy(c->tids + c->ntids, t, sizeof(int32_t) * (size_t)k);
     memset(c->euma + c->nrows * c->nF, 0, sizeof(int32_t) * (size_t)c->nF);
-    c->euma[c->nrows * c->nF + fi] = 1;
+    const int64_t row = c->nrows;
     c->ntids += k; c->nrows++;
     c->slots[s] = (uint64_t)(++c->ncls);
     if ((uint64_t)c->ncls * 2 > c->mask) cs_rehash(c);
+    return c->euma + row * c->nF;
 }
+/* update_rshbucket(..., 'e', fi): the class gains one substring at fragment-length index fi */
+static void cs_add(cstore *c, const int32_t *t, int k, int fi) { cs_row(c, t, k)[fi]++; }
 static void cs_add_single(cstore *c, int32_t tid, int fi) { c->s_node[tid] = 1; c->s_euma[(size_t)tid * c->nF + fi]++; }
 
 /* fold the store of a worker thread into dst (counts add up; the final order does not depend on who found a class first) */
@@ -230,22 +236,8 @@ static void cs_merge(cstore *dst, const cstore *src)
     for (int64_t j = 0; j < src->ncls; j++) {
         const bclass *b = &src->cls[j];
         const int32_t *row = src->euma + b->euma_row * src->nF;
-        int first = 1;
-        for (int i = 0; i < src->nF; i++) {
-            if (!row[i]) continue;
-            cs_add(dst, src->tids + b->tid_off, b->k, i);              /* creates the class on its first count */
-            if (row[i] > 1) {
-                /* the class exists now: find it once more and add the rest of the count */
-                uint64_t s = key_hash(src->tids + b->tid_off, b->k) & dst->mask;
-                for (;;) {
-                    const bclass *d = &dst->cls[dst->slots[s] - 1];
-                    if (d->k == b->k && memcmp(dst->tids + d->tid_off, src->tids + b->tid_off, sizeof(int32_t) * (size_t)b->k) == 0) { dst->euma[d->euma_row * dst->nF + i] += row[i] - 1; break; }
-                    s = (s + 1) & dst->mask;
-                }
-            }
-            first = 0;
-        }
-        (void)first;
+        int32_t *dst_row = cs_row(dst, src->tids + b->tid_off, b->k);
+        for (int i = 0; i < src->nF; i++) dst_row[i] += row[i];
     }
 }
 
@@ -476,6 +468,32 @@ static void build_pe(const txome *x, const emsar_build_opts *o, cstore *c, int f
     free(H); free(ok); free(m1);
 }
 
+/* ---- construction on the device (include/emsar_cuda.h: emsar_build_classes_run) ---------------------------------------------- */
+static int build_device(const txome *x, const emsar_build_opts *o, cstore *c, int fmin, int fmax, char *err)
+{
+    const int L0 = o->pe ? o->readlength : o->readlen_min, L1 = o->pe ? o->readlength : o->readlen_max;
+    for (int L = L0; L <= L1; L++) {
+        emsar_build_desc d;
+        memset(&d, 0, sizeof d);
+        d.seq = x->S; d.border = x->border; d.end = x->end; d.T = x->T; d.start = x->start;
+        d.pe = o->pe; d.stranded = o->stranded; d.readlen = L; d.max_repeat = o->max_repeat;
+        if (o->pe) { d.d_min = fmin - L; d.d_max = fmax - L; }
+        emsar_build_classes r;
+        memset(&r, 0, sizeof r);
+        if (o->device_run(o->device_ctx, &d, &r)) return fail(err, "index construction on the device: %s", o->device_error ? o->device_error() : "failed");
+        const int fi0 = o->pe ? 0 : L - fmin;               /* PE: fragment length index = distance index (d_min = fmin - L) */
+        for (int32_t t = 0; t < r.T; t++)
+            for (int j = 0; j < r.n_d; j++) {
+                const int32_t n = r.single_count[(size_t)t * r.n_d + j];
+                if (n) { c->s_node[t] = 1; c->s_euma[(size_t)t * c->nF + fi0 + j] += n; }
+            }
+        for (int64_t u = 0; u < r.n_class; u++)
+            cs_row(c, r.class_tid + r.class_off[u], (int)(r.class_off[u + 1] - r.class_off[u]))[fi0 + r.class_d[u]] += r.class_count[u];
+        if (o->device_free) o->device_free(&r);
+    }
+    return 0;
+}
+
 /* ---- class store -> emsar_rsh in the reference's scan / print order ------------------------------------------------------ */
 static const cstore *g_cs;
 static int cls_cmp(const void *a, const void *b)
@@ -504,12 +522,20 @@ int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh
         fmin = o->readlen_min; fmax = o->readlen_max;
     }
     nF = fmax - fmin + 1;
+    /* EMSAR_BUILD_TIMING=1: seconds per stage on stderr (profiles/build_bench.py) */
+    const int timing = getenv("EMSAR_BUILD_TIMING") && atoi(getenv("EMSAR_BUILD_TIMING"));
+    struct timespec ts0, ts1, ts2, ts3;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     txome x;
     if (txome_read(fasta_path, o->header == 'R' ? 'R' : 'E', &x, err)) return 1;
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
     cstore c;
     cs_init(&c, x.T, nF);
-    if (o->pe) build_pe(&x, o, &c, fmin, fmax);
+    if (o->device_run) {
+        if (build_device(&x, o, &c, fmin, fmax, err)) { cs_free(&c); txome_free(&x); return 1; }
+    } else if (o->pe) build_pe(&x, o, &c, fmin, fmax);
     else build_se(&x, o, &c);
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
     /* flatten: singletons in tid order, then by (cardinality, tids) - the order print_rsh walks the buckets and their sorted chains */
     int64_t *ord = (int64_t *)malloc(sizeof(int64_t) * (size_t)(c.ncls ? c.ncls : 1));
     for (int64_t i = 0; i < c.ncls; i++) ord[i] = i;
@@ -543,5 +569,11 @@ int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh
     cs_free(&c);
     txome_free(&x);
     *out = r;
+    clock_gettime(CLOCK_MONOTONIC, &ts3);
+    if (timing) {
+        #define SECS(a, b) ((double)((b).tv_sec - (a).tv_sec) + 1e-9 * (double)((b).tv_nsec - (a).tv_nsec))
+        fprintf(stderr, "build timing: fasta %.3f s, classes (%s) %.3f s, order %.3f s\n", SECS(ts0, ts1), o->device_run ? "device" : "host", SECS(ts1, ts2), SECS(ts2, ts3));
+        #undef SECS
+    }
     return 0;
 }

@@ -53,6 +53,8 @@ int emsar_rsh_save_packed(const emsar_rsh *r, const char *path, const char *src_
 int emsar_rsh_load_packed(const char *path, const char *src_path, emsar_rsh **out, char *err);   /* 2 = stale w.r.t. src_path */
 int emsar_rsh_load_auto(const char *path, emsar_rsh **out, int *from_cache, char *err);          /* <path>.pack if fresh, else text */
 
+struct emsar_build_desc;
+struct emsar_build_classes;
 /* ---- index construction from a fasta (what emsar-build / emsar -x do; emsar_b200/host/build_index.c) ---- */
 typedef struct {
     int pe;                        /* -P */
@@ -63,6 +65,13 @@ typedef struct {
     int max_repeat;                /* -k MAX_REPEAT: substrings occurring this often or more are dropped (default 100) */
     char header;                   /* 'E' Ensembl header (name up to the first blank, default), 'R' RefSeq (4th '|' field) */
     int threads;                   /* worker threads of the paired-end construction (-p); results do not depend on it */
+    /* optional: the classes are constructed on the device (libemsar_cuda: emsar_build_classes_run / _free / emsar_cuda_last_error with an
+     * open context in device_ctx; include/emsar_cuda.h) instead of by the host code in build_index.c. Fasta reader, class store and the
+     * print order stay here; the file is the same byte for byte. NULL device_run = host construction. */
+    int (*device_run)(void *device_ctx, const struct emsar_build_desc *d, struct emsar_build_classes *out);
+    void (*device_free)(struct emsar_build_classes *out);
+    const char *(*device_error)(void);
+    void *device_ctx;
 } emsar_build_opts;
 int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh **out, char *err);
 /* read length(s) of an alignment file, as emsar -x learns them (emsar_main.c:306-316): PE -> the first aligned record,

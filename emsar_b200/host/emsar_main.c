@@ -3,15 +3,17 @@
  * libemsar_cuda (include/emsar_cuda.h) where the reference calls update_ReadCounts / scan_rshbucket / run_MLE_threads.
  *
  * Differences that are visible and deliberate:
- *   - the estimator is one deterministic EM run, not NUM_ROUND random restarts: `sd.of.FPKM` prints 0.000000, -n is
- *     accepted and ignored; -e / -r / -i map to eps_abs / eps_rel / max EM iterations when given;
+ *   - the estimator is a deterministic EM run from theta = 1; with -n R (R > 1) R - 1 further runs start from seeded random points
+ *     and the files carry the mean and sd.of.FPKM over the R runs like the reference's rounds (without -n: one run, sd 0.000000);
+ *     -e / -r / -i map to eps_abs / eps_rel / max EM iterations when given;
  *   - -x builds the index on the host first (emsar_b200/host/build_index.c: same classes and counts as the reference's
  *     suffix-array construction, the read length(s) are learnt from the first alignment file like emsar_main.c:306-316);
  *     -T (print suffix array) is rejected: there is no suffix array;  -m/-W/-w (positional bias, undocumented and
  *     half-implemented in the reference) are rejected;
  *   - -k above 1024 is rejected (device sort limit, EMSAR_MAX_READ_TIDS);
- *   - EMSAR_DEVICES=0,1,.. spreads the files of a -M list over several GPUs (one host thread per GPU, no
- *     communication); EUMAcut then persists per GPU instead of per run.
+ *   - EMSAR_DEVICES=0,1,.. spreads the files of a -M list over several GPUs (one host thread per GPU taking files from a shared
+ *     queue, largest first, no communication). EUMAcut carries over from file to file on one GPU as in the reference; on several
+ *     GPUs every file starts from the initial cut, so that the output does not depend on which GPU took which file.
  *   - EMSAR_DEVICES=0,1,.. with EMSAR_SHARD=classes puts EVERY sample on all the GPUs: the sample's active classes are
  *     range-sharded, theta is all-reduced over NVLink every iteration (BASELINE.json configs[2]); GPU 0 reads and counts,
  *     the other GPUs join the collectives, the first GPU writes the files.
@@ -442,7 +444,23 @@ int main(int argc, char *argv[])
             else fprintf(stdout, "read length range : %d - %d\n", rl0, rl1);
         }
         stamp(&o, "building the rsh index from the fasta file...");
+        /* the classes are constructed on the first device (emsar_build_classes_run); EMSAR_BUILD_HOST=1 keeps the construction
+         * on the host (emsar_b200/host/build_index.c) - the index is the same file byte for byte */
+        emsar_ctx *bctx = NULL;
+        const char *bh = getenv("EMSAR_BUILD_HOST");
+        if (!(bh && atoi(bh))) {
+            int dev0 = 0;
+            const char *denv = getenv("EMSAR_DEVICES");
+            if (denv && *denv) dev0 = atoi(denv);
+            int brc = emsar_cuda_open(dev0, &bctx);
+            if (brc) die("%s: %s", emsar_cuda_strerror(brc), emsar_cuda_last_error());
+            bo.device_run = (int (*)(void *, const struct emsar_build_desc *, struct emsar_build_classes *))emsar_build_classes_run;
+            bo.device_free = emsar_build_classes_free;
+            bo.device_error = emsar_cuda_last_error;
+            bo.device_ctx = bctx;
+        }
         if (emsar_rsh_build(o.fasta, &bo, &rsh, err)) { printf("%s\n", err); exit(1); }
+        if (bctx) emsar_cuda_close(bctx);
     } else if (emsar_rsh_load_auto(o.rshfile, &rsh, &from_cache, err)) { printf("%s\n", err); exit(1); }
     if (from_cache && o.verbose > 0) fprintf(stdout, "rsh index taken from its packed image\n");
     fprintf(stderr, "done reading rsh. rshsize=%lld\n", (long long)(rsh->C - rsh->T));

@@ -259,6 +259,38 @@ int emsar_cuda_timer_stop(emsar_ctx *ctx, double *elapsed_ms);
 int emsar_sample_time_adjeuma(emsar_sample *s, int32_t reps, double *ms_per_launch);
 int emsar_sample_finalize(emsar_sample *s, emsar_solve_out *out);
 
+/* ---- index construction on the device ---------------------------------------------------------------------------
+ * Replaces the reference's suffix-array construction for one read length: initialize_suffixarray_* / sort (emsar_functions.c:949-1230),
+ * construct_rshbucket_2 (:1758-1816), construct_rshbucket_PE_3 (:1902-1974), process_mate1_cluster_by_mate_3 (:2784-2934). The caller owns
+ * the fasta reader and the class store (emsar_b200/host/build_index.c): it passes the concatenated transcriptome exactly as read_raw_fasta
+ * (:31-196) lays it out and folds the returned counts into its store (update_rshbucket[_single] 'e', :1514-1596). */
+typedef struct emsar_build_desc {
+    const char *seq;          /* S[0 .. end]: transcripts (upper case, other letters = 'N') joined by '@', '$' at `border`, the reverse
+                                 complement of S[0 .. border), '$' at `end` = 2 * border + 1 */
+    int64_t border, end;
+    int32_t T;
+    const int64_t *start;     /* [T + 1] first position of every transcript in the forward half; start[T] = border + 1 */
+    int32_t pe;               /* paired-end: fragments (mate 1, mate 2 at distance d on the same strand string) instead of single reads */
+    int32_t stranded;         /* 0: an occurrence stands for the smaller of itself and its reverse complement / flipped fragment */
+    int32_t readlen;          /* read length of this pass */
+    int32_t d_min, d_max;     /* pe: mate distance range = fragment length - read length (>= 0); ignored otherwise */
+    int32_t max_repeat;       /* MAX_REPEAT (-k): a sequence shared by this many occurrences or more is dropped */
+} emsar_build_desc;
+typedef struct emsar_build_classes {     /* arrays owned by the library until emsar_build_classes_free */
+    int32_t T, n_d;           /* n_d = d_max - d_min + 1 (1 for single-end) */
+    const int32_t *single_count;   /* [T * n_d] sequences seen in exactly one place: transcript t, distance index d - d_min */
+    int64_t n_class;               /* distinct (tid multiset, distance) pairs shared by 2 .. max_repeat - 1 occurrences */
+    const int64_t *class_off;      /* [n_class + 1] into class_tid */
+    const int32_t *class_tid;      /* ascending tids, a transcript repeats when the sequence occurs in it more than once */
+    const int32_t *class_d;        /* [n_class] distance index */
+    const int32_t *class_count;    /* [n_class] number of distinct sequences with exactly this tid multiset at this distance */
+    int64_t occurrences, runs;     /* diagnostics: occurrences keyed, distinct sequences among them */
+    int32_t partitions;
+    void *owner;
+} emsar_build_classes;
+int emsar_build_classes_run(emsar_ctx *ctx, const emsar_build_desc *desc, emsar_build_classes *out);
+void emsar_build_classes_free(emsar_build_classes *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,3 +29,15 @@ print("start spread", (t[:, 0].max() - t0) / 1e3, "iteration (first start -> las
 for lab, a in (("E", E), ("M", M), ("U", U), ("halo", H)):
     o = np.argsort(-a)
     print("slowest", lab, [(int(i), round(a[i] / 1e3, 2)) for i in o[:5]], "fastest", [(int(i), round(a[i] / 1e3, 2)) for i in o[-3:]])
+
+# per-CTA table for cost-model work: features of the CTA's share of the packed model (emsar_debug_psum_blocks) next to its phase times
+feat = np.zeros(nb.value * 16, dtype=np.int32); nb2 = C.c_int(0)
+fn = getattr(_lib.lib(), "emsar_debug_psum_blocks", None)
+if fn is not None and st["em_variant"] == 5 and fn(s._h, feat.ctypes.data_as(C.c_void_p), C.byref(nb2)) == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = f"gpurun_out/psum_blocks_{name}{os.environ.get('TRACE_TAG', '')}.csv"
+    with open(path, "w") as f:
+        f.write("cta,rows,halo,classes,incoming,etiles,mitems,res16,desc,k2_tiles,k34_tiles,lane_steps,multi_steps,res_etiles,slice_steps,group_blocks,res_mitems,halo_ns,E_ns,M_ns,U_ns\n")
+        for i in range(nb2.value):
+            f.write(",".join([str(i)] + [str(int(x)) for x in feat[16 * i:16 * i + 16]] + [str(int(H[i])), str(int(E[i])), str(int(M[i])), str(int(U[i]))]) + "\n")
+    print("per-CTA table:", path)

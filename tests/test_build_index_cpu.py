@@ -135,8 +135,10 @@ def test_emsar_dash_x_builds_the_same_index(built, tmp_path, pe):
     _write_sam(str(tmp_path / "in.sam"), tx, L, pe, np.random.default_rng(3))
     out = str(tmp_path / "out")
     flags = ["-q", "-R", "-S"] + (["-P", "-f", "40", "-F", "70"] if pe else [])
-    r = subprocess.run([emsar] + flags + ["-x", fa, out, "p", str(tmp_path / "in.sam")], capture_output=True, text=True)
     import torch
+    # with a GPU `emsar -x` constructs the classes on the device (tests/test_build_index_gpu.py); EMSAR_BUILD_HOST=1 keeps them on the host
+    env = dict(os.environ) if torch.cuda.is_available() else dict(os.environ, EMSAR_BUILD_HOST="1")
+    r = subprocess.run([emsar] + flags + ["-x", fa, out, "p", str(tmp_path / "in.sam")], capture_output=True, text=True, env=env)
     if not torch.cuda.is_available():
         assert r.returncode != 0 and "no CPU" in (r.stdout + r.stderr)
     else:
@@ -164,7 +166,9 @@ def test_emsar_dash_x_se_read_length_range_from_bowtie(built, tmp_path):
                 continue
             f.write(f"r{r}\t+\tTX{t:03d}\t{int(rng.integers(0, len(tx[t]) - 30))}\t{'A' * L}\t{'I' * L}\t0\t\n")
     out = str(tmp_path / "out")
-    subprocess.run([emsar, "-q", "-R", "-x", fa, out, "p", str(tmp_path / "in.bowtie")], capture_output=True, text=True)
+    import torch
+    env = dict(os.environ) if torch.cuda.is_available() else dict(os.environ, EMSAR_BUILD_HOST="1")
+    subprocess.run([emsar, "-q", "-R", "-x", fa, out, "p", str(tmp_path / "in.bowtie")], capture_output=True, text=True, env=env)
     mine = open(os.path.join(out, "p.rsh"), "rb").read()
     assert mine.startswith(b"#") and b",24,27,-1\n" in mine.split(b"\n")[0] + b"\n"
     bdir = str(tmp_path / "b")
