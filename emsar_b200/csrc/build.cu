@@ -389,6 +389,7 @@ extern "C" int emsar_build_classes_run(emsar_ctx *ctx, const emsar_build_desc *b
     int32_t *d_single = nullptr; int *d_flags = nullptr; unsigned long long *d_count = nullptr, *d_pc = nullptr;
     TRY(B.take(&d_S, (size_t)n + 1)); TRY(B.take(&d_start, (size_t)T + 1)); TRY(B.take(&H1, (size_t)n)); TRY(B.take(&H2, (size_t)n)); TRY(B.take(&ok, (size_t)n));
     TRY(B.take(&d_single, (size_t)T * nD)); TRY(B.take(&d_flags, 4)); TRY(B.take(&d_count, 1));
+    CU(cudaEventRecord(ctx->ev0, st));
     CU(cudaMemcpyAsync(d_S, bd->seq, (size_t)n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_start, bd->start, ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_single, 0, (size_t)T * nD * 4, st));
@@ -448,7 +449,10 @@ extern "C" int emsar_build_classes_run(emsar_ctx *ctx, const emsar_build_desc *b
     ho.single.resize((size_t)T * nD);
     CU(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ho.single.data(), d_single, (size_t)T * nD * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev1, st));
     CU(cudaStreamSynchronize(st));
+    float dev_ms = 0;
+    CU(cudaEventElapsedTime(&dev_ms, ctx->ev0, ctx->ev1));
     if (flags[1] || flags[2]) {
         emsar_set_err("index construction: two different %s share a 128-bit hash (EMSAR_BUILD_HOST=1 selects the host builder)", flags[1] ? "substrings" : "classes");
         return EMSAR_ERR_STATE;
@@ -460,7 +464,7 @@ extern "C" int emsar_build_classes_run(emsar_ctx *ctx, const emsar_build_desc *b
     out->class_tid = ho.class_tid.data();
     out->class_d = ho.class_d.data();
     out->class_count = ho.class_count.data();
-    out->occurrences = occ; out->runs = runs; out->partitions = nparts;
+    out->occurrences = occ; out->runs = runs; out->partitions = nparts; out->device_ms = dev_ms;
     out->owner = own;
     guard.o = nullptr;
     return EMSAR_OK;

@@ -469,8 +469,12 @@ static void build_pe(const txome *x, const emsar_build_opts *o, cstore *c, int f
 }
 
 /* ---- construction on the device (include/emsar_cuda.h: emsar_build_classes_run) ---------------------------------------------- */
+static double g_device_ms;      /* diagnostics of the last device construction (EMSAR_BUILD_TIMING) */
+static long long g_device_occ, g_device_runs;
+static int g_device_parts;
 static int build_device(const txome *x, const emsar_build_opts *o, cstore *c, int fmin, int fmax, char *err)
 {
+    g_device_ms = 0; g_device_occ = 0; g_device_runs = 0; g_device_parts = 0;
     const int L0 = o->pe ? o->readlength : o->readlen_min, L1 = o->pe ? o->readlength : o->readlen_max;
     for (int L = L0; L <= L1; L++) {
         emsar_build_desc d;
@@ -489,6 +493,7 @@ static int build_device(const txome *x, const emsar_build_opts *o, cstore *c, in
             }
         for (int64_t u = 0; u < r.n_class; u++)
             cs_row(c, r.class_tid + r.class_off[u], (int)(r.class_off[u + 1] - r.class_off[u]))[fi0 + r.class_d[u]] += r.class_count[u];
+        g_device_ms += r.device_ms; g_device_occ += r.occurrences; g_device_runs += r.runs; g_device_parts += r.partitions;
         if (o->device_free) o->device_free(&r);
     }
     return 0;
@@ -573,6 +578,7 @@ int emsar_rsh_build(const char *fasta_path, const emsar_build_opts *o, emsar_rsh
     if (timing) {
         #define SECS(a, b) ((double)((b).tv_sec - (a).tv_sec) + 1e-9 * (double)((b).tv_nsec - (a).tv_nsec))
         fprintf(stderr, "build timing: fasta %.3f s, classes (%s) %.3f s, order %.3f s\n", SECS(ts0, ts1), o->device_run ? "device" : "host", SECS(ts1, ts2), SECS(ts2, ts3));
+        if (o->device_run) fprintf(stderr, "build timing: device stream %.1f ms for %lld occurrences, %lld distinct sequences, %d partition(s)\n", g_device_ms, g_device_occ, g_device_runs, g_device_parts);
         #undef SECS
     }
     return 0;

@@ -286,6 +286,7 @@ typedef struct emsar_build_classes {     /* arrays owned by the library until em
     const int32_t *class_count;    /* [n_class] number of distinct sequences with exactly this tid multiset at this distance */
     int64_t occurrences, runs;     /* diagnostics: occurrences keyed, distinct sequences among them */
     int32_t partitions;
+    double device_ms;              /* CUDA-event time of the call on the context's stream (copies, kernels, sorts) */
     void *owner;
 } emsar_build_classes;
 int emsar_build_classes_run(emsar_ctx *ctx, const emsar_build_desc *desc, emsar_build_classes *out);
