@@ -471,6 +471,110 @@ def class_sharded_leg(ctx, name, idx, reads, rank, world, torch, dist):
     return out
 
 
+def note(msg):
+    """Progress on stderr (rank and seconds since start): a leg that stalls is visible in the driver's log."""
+    print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+SELFTEST = "small"             # T = 20K, 200K classes, 3M reads: the small case that goes first
+
+
+def sharded_child(args, rank, world, local):
+    """`--leg class_sharded` (one process per GPU, started by the ranks of the main run): its own process group and contexts, so that a stall
+    of the cross-GPU EM kernel at this GPU count can be cut off by the parent without losing the headline line."""
+    fake = os.environ.get("EMSAR_BENCH_FAKE_LEG")          # tests/test_bench_cpu.py: the process plumbing without a GPU
+    if fake:
+        if fake == "hang":
+            time.sleep(3600)
+        if rank == 0:
+            json.dump({"workload": args.sharded_workloads, "n_gpus": world, "fake": True}, open(args.leg_out, "w"))
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from emsar_b200.api import Context
+    ctx = Context(local)
+    ctx.comm_init_torch()
+    name = args.sharded_workloads
+    note(f"sharded leg {name}: workload")
+    sidx, sreads = bcast_workload(name, 1000, rank, torch, dist)
+    note(f"sharded leg {name}: solve")
+    o = class_sharded_leg(ctx, name, sidx, sreads, rank, world, torch, dist)
+    note(f"sharded leg {name}: done")
+    if rank == 0:
+        with open(args.leg_out, "w") as f:
+            json.dump(o, f)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def run_sharded_children(names, rank, world, local, budget_s):
+    """Every rank starts one child per workload (same RANK / WORLD_SIZE, the master port shifted) and waits for it at most budget_s[name]
+    seconds; a child that is still running then is killed (by its pid). Rank 0 collects the children's results."""
+    import subprocess
+    import tempfile
+    out = []
+    port = int(os.environ.get("MASTER_PORT", "29500"))
+    for k, name in enumerate(names):
+        leg_out = os.path.join(tempfile.gettempdir(), f"emsar_bench_leg_{port}_{k}.json")
+        if rank == 0 and os.path.exists(leg_out):
+            os.remove(leg_out)
+        env = dict(os.environ, MASTER_PORT=str(port + 17 + k), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local))
+        cmd = [sys.executable, os.path.abspath(__file__), "--leg", "class_sharded", "--gpus", str(world), "--sharded-workloads", name, "--leg-out", leg_out]
+        note(f"class_sharded {name}: child started (limit {budget_s[name]} s)")
+        pr = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL)
+        _WATCH["children"].append(pr)
+        try:
+            rc = pr.wait(timeout=budget_s[name])
+            err = None if rc == 0 else f"child exited with {rc}"
+        except subprocess.TimeoutExpired:
+            pr.kill()
+            pr.wait()
+            err = f"no result within {budget_s[name]} s at {world} GPUs (child stopped)"
+        note(f"class_sharded {name}: {'ok' if err is None else err}")
+        o = None
+        if rank == 0:
+            if err is None and os.path.exists(leg_out):
+                o = json.load(open(leg_out))
+                os.remove(leg_out)
+            else:
+                o = {"workload": name, "n_gpus": world, "error": err or "no result file"}
+        out.append(o)
+        if o is not None and "error" in o and name == SELFTEST:
+            break                       # the small case did not come back: the full-size ones are not attempted
+        if rank != 0 and err is not None and name == SELFTEST:
+            break
+    return out
+
+
+_WATCH = {"line": None, "done": False, "children": []}
+
+
+def start_watchdog(rank, limit_s):
+    """A run that has not printed its line after limit_s seconds prints what it has (the headline without the legs that did not come back)
+    and ends the process: a stalled leg must not turn into a run without a result."""
+    def run():
+        time.sleep(limit_s)
+        if _WATCH["done"]:
+            return
+        note(f"watchdog: no result line after {limit_s} s")
+        for pr in _WATCH["children"]:
+            if pr.poll() is None:
+                pr.kill()
+        if rank == 0:
+            line = _WATCH["line"]
+            if line is not None:
+                line = dict(line, incomplete=f"stopped by the bench watchdog after {limit_s} s: the legs that are missing did not come back")
+                print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0 if _WATCH["line"] is not None or rank != 0 else 1)
+    threading.Thread(target=run, daemon=True).start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -486,6 +590,8 @@ def main():
     ap.add_argument("--others", default=",".join(OTHER_WORKLOADS), help="comma-separated workloads of the other_workloads object (N = 1)")
     ap.add_argument("--m64-per-gpu", type=int, default=8, help="samples per GPU of the -M batch leg (8 x 8 GPUs = BASELINE configs[3])")
     ap.add_argument("--sharded-workloads", default="config2_human_se,config5_full", help="N > 1: workloads of the class_sharded legs")
+    ap.add_argument("--leg", default="", help="internal: run one leg as a child of the ranks of the main run (class_sharded)")
+    ap.add_argument("--leg-out", default="", help="internal: where rank 0 of a child leg writes its result")
     ap.add_argument("--no-ref-binary", action="store_true",
                     help="skip timing the unmodified reference binary (oracle/_ref/emsar -p N) on the scaled twin (about 20 s)")
     args = ap.parse_args()
@@ -496,6 +602,9 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
+    if args.leg == "class_sharded":
+        sharded_child(args, rank, world, local)
+        return
 
     import torch
     import torch.distributed as dist
@@ -504,7 +613,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from emsar_b200.api import Context, Index
 
+    note(f"start: {args.workload}, {world} GPU(s)")
+    start_watchdog(rank, int(os.environ.get("EMSAR_BENCH_LIMIT_S", "1500")))
     idx, reads, gen_s = make_workload(args.workload, seed=1000 + rank)
+    note("workload generated")
     ctx = Context(local)
     ix = Index(ctx, idx)
     # pinned host copies of this rank's read lists (the e2e leg copies them every step)
@@ -540,6 +652,7 @@ def main():
         it, fd, ms = smp.em_run(max_iter=args.em_iters, stop_on_conv=False, reset_theta=True)
         return it, ms
 
+    note("sample resident, warm-up")
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local)
@@ -558,6 +671,8 @@ def main():
     launches = ctx.launches() - l0
     wall = t1 - t0
     t_em = em_ms / 1e3           # device time of the EM kernel alone (CUDA events on the library's stream) -> roofline
+
+    note("device-timed steps done")
 
     # ---- e2e leg: host buffers through the C ABI ----
     def step_e2e():
@@ -585,6 +700,7 @@ def main():
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
+    note("e2e steps done")
     # ---- one sample to convergence (samples/min context) ----
     conv = None
     if not args.no_converge:
@@ -615,20 +731,8 @@ def main():
     else:
         iters_tot, e_iters_tot, launches_tot = iters_done, e_iters, launches
 
-    # ---- the other legs (outside every timed region above) ----
-    extras = {}
-    if not args.no_extras:
-        try:
-            extras["m64"] = m64_leg(ctx, ix, idx, args.workload, rank, world, torch, dist, args.m64_per_gpu)
-        except Exception as e:
-            extras["m64"] = {"error": repr(e)}
-        if rank == 0:
-            try:
-                extras["kernels"] = [count_roofline(ctx, ix.sample, reads, torch)]
-            except Exception as e:
-                extras["kernels"] = [{"kernel": "k_count", "error": repr(e)}]
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         cores = os.cpu_count() or 1
         R, F, N = smp.counts()
@@ -639,34 +743,8 @@ def main():
         sec = oracle.em_time(idx, R, ps, n_it, cores)
         cpu = {"value": n_it / sec, "unit": "iterations/s", "cores": cores, "kind": "port",
                "sample": f"{n_it} EM iterations of the same packed sample ({sec:.1f} s), pthread team of {cores}"}
+    line = None
     n_reads_sample = len(reads.read_fraglen)
-    smp.close()
-    ix.close()
-    del h_len, h_tid, h_fl
-    if not args.no_extras and world > 1:
-        ctx.comm_init_torch()
-        extras["class_sharded"] = []
-        for name in [w for w in args.sharded_workloads.split(",") if w]:
-            try:
-                sidx, sreads = bcast_workload(name, 1000, rank, torch, dist)
-                o = class_sharded_leg(ctx, name, sidx, sreads, rank, world, torch, dist)
-                del sidx, sreads
-            except Exception as e:
-                o = {"workload": name, "error": repr(e)}
-            if rank == 0:
-                extras["class_sharded"].append(o)
-    if not args.no_extras and world == 1:
-        extras["other_workloads"] = []
-        for name in [w for w in args.others.split(",") if w]:
-            try:
-                extras["other_workloads"].append(other_workload(ctx, name, torch, flush, args.em_iters))
-            except Exception as e:
-                extras["other_workloads"].append({"workload": name, "error": repr(e)})
-        try:
-            extras["file_to_file"] = file_to_file_twin(os.cpu_count() or 1, local) if not args.no_ref_binary else None
-        except Exception as e:
-            extras["file_to_file"] = {"error": repr(e)}
-
     if rank == 0:
         peak, peak_src = peaks()
         achieved = st["bytes_per_iter"] * iters_done / t_em / 1e9 if t_em > 0 else 0.0
@@ -690,7 +768,49 @@ def main():
             "to_convergence": conv,
             "model": st, "gen_seconds": gen_s,
         }
+        _WATCH["line"] = line                    # from here on the watchdog can still print the headline if a later leg stalls
+
+    # ---- the other legs (outside every timed region above) ----
+    extras = {}
+    note("to-convergence sample done")
+    if not args.no_extras:
+        try:
+            extras["m64"] = m64_leg(ctx, ix, idx, args.workload, rank, world, torch, dist, args.m64_per_gpu)
+        except Exception as e:
+            extras["m64"] = {"error": repr(e)}
+        note("m64 leg done")
+        if rank == 0:
+            try:
+                extras["kernels"] = [count_roofline(ctx, ix.sample, reads, torch)]
+            except Exception as e:
+                extras["kernels"] = [{"kernel": "k_count", "error": repr(e)}]
+    smp.close()
+    ix.close()
+    del h_len, h_tid, h_fl
+    if not args.no_extras and world > 1:
+        # ONE sample over the N GPUs: in child processes (their own process group), a small case first; see run_sharded_children
+        names = [SELFTEST] + [w for w in args.sharded_workloads.split(",") if w]
+        budget = {SELFTEST: 150, "config2_human_se": 240, "config5_full": 360}
+        torch.cuda.empty_cache()
+        res = run_sharded_children(names, rank, world, local, {n: budget.get(n, 300) for n in names})
+        dist.barrier()
+        if rank == 0:
+            extras["class_sharded"] = [o for o in res if o is not None]
+    if not args.no_extras and world == 1:
+        extras["other_workloads"] = []
+        for name in [w for w in args.others.split(",") if w]:
+            try:
+                extras["other_workloads"].append(other_workload(ctx, name, torch, flush, args.em_iters))
+            except Exception as e:
+                extras["other_workloads"].append({"workload": name, "error": repr(e)})
+        try:
+            extras["file_to_file"] = file_to_file_twin(os.cpu_count() or 1, local) if not args.no_ref_binary else None
+        except Exception as e:
+            extras["file_to_file"] = {"error": repr(e)}
+
+    if rank == 0:
         line.update(extras)
+        _WATCH["done"] = True
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     __shared__ double sm_red[EM_WARPS];
     __shared__ double sm_bc;
-    __shared__ int sm_ctr[3];
+    __shared__ int sm_ctr[2];
     __shared__ int sm_flag;          // bit 0: some CTA's convergence measure of the previous iteration is above 1; bit 1: abort
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = (int)blockIdx.x + p.m.block0;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         if ((int)threadIdx.x < nhr) v.theta[nrows + threadIdx.x] = ll_load(th_slots + 16 * (size_t)hs0, tag, p.abort_flag);
         if ((int)threadIdx.x + EM_BLOCK < nhr) v.theta[nrows + threadIdx.x + EM_BLOCK] = ll_load(th_slots + 16 * (size_t)hs1, tag, p.abort_flag);
         for (int i = threadIdx.x + 2 * EM_BLOCK; i < nhr; i += EM_BLOCK) v.theta[nrows + i] = ll_load(th_slots + 16 * (size_t)__ldg(p.m.halo_rows + hr0 + i), tag, p.abort_flag);
-        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; sm_ctr[2] = 0; sm_flag = 0; }
+        if (threadIdx.x == 0) { sm_ctr[0] = 0; sm_ctr[1] = 0; sm_flag = 0; }
         __syncthreads();
         PS_TRACE(1);
         if (SCHED & 1) {
@@ -377,13 +377,14 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
                 tk = tk2; t = t2;
             }
         }
-        // a warp that finds the item queue empty turns to the partial sums the CTA receives: blocks of 32 slots, each polled by one lane and
-        // staged in shared memory (they come from other CTAs' M-phases, nothing of this CTA's is needed for them); the constants of a thread's
-        // first two rows are requested before the barrier as well, so that the U-phase starts with everything in place
-        for (int c = next_item(&sm_ctr[2], lane); c * 32 < nin; c = next_item(&sm_ctr[2], lane)) {
-            const int e = c * 32 + lane;
-            if (e < nin) s_in[e] = ll_load(part_slots + 16 * (size_t)(in0 + e), tag, p.abort_flag);
+        __syncthreads();
+        PS_TRACE(3);
+        {
+            const int fl = sm_flag;
+            if ((fl & 2) || (p.stop_on_conv && it > 0 && !(fl & 1))) break;      // the same decision in every CTA: they all read the same slots
         }
+        // owner update: own partial sum + the contributions of the other CTAs, in CTA order. The constants of a thread's first two rows are
+        // requested first, then every incoming partial sum is fetched by its own thread (one round trip for all of them) and staged
         double dm = 0;
         const int i0 = threadIdx.x, i1 = threadIdx.x + EM_BLOCK;
         double2 ra0 = make_double2(0.0, 1.0), ra1 = ra0;
@@ -391,13 +392,8 @@ __global__ void __launch_bounds__(EM_BLOCK, 1) k_em_psum(PsParams p)
         unsigned mk0 = 0, mk1 = 0;
         if (i0 < nrows) { ra0 = __ldg(p.m.row_RsA + row0 + i0); a0 = __ldg(p.m.inc_off + row0 + i0); b0 = __ldg(p.m.inc_off + row0 + i0 + 1); mk0 = (unsigned)__ldg(p.m.row_mask + row0 + i0); }
         if (i1 < nrows) { ra1 = __ldg(p.m.row_RsA + row0 + i1); a1 = __ldg(p.m.inc_off + row0 + i1); b1 = __ldg(p.m.inc_off + row0 + i1 + 1); mk1 = (unsigned)__ldg(p.m.row_mask + row0 + i1); }
+        for (int e = threadIdx.x; e < nin; e += EM_BLOCK) s_in[e] = ll_load(part_slots + 16 * (size_t)(in0 + e), tag, p.abort_flag);
         __syncthreads();
-        PS_TRACE(3);
-        {
-            const int fl = sm_flag;
-            if ((fl & 2) || (p.stop_on_conv && it > 0 && !(fl & 1))) break;      // the same decision in every CTA: they all read the same slots
-        }
-        // owner update: own partial sum + the contributions of the other CTAs, in CTA order
         auto update = [&](int i, double2 ra, int e0, int e1, unsigned mk) {
             double Q = v.Q[i];
             for (int e = e0; e < e1; e++) Q += s_in[e - in0];
