@@ -614,7 +614,7 @@ def main():
     from emsar_b200.api import Context, Index
 
     note(f"start: {args.workload}, {world} GPU(s)")
-    start_watchdog(rank, int(os.environ.get("EMSAR_BENCH_LIMIT_S", "1500")))
+    start_watchdog(rank, int(os.environ.get("EMSAR_BENCH_LIMIT_S", "1200")))
     idx, reads, gen_s = make_workload(args.workload, seed=1000 + rank)
     note("workload generated")
     ctx = Context(local)
