@@ -357,38 +357,51 @@ def m64_leg(ctx, ix, idx, workload, rank, world, torch, dist, per_gpu):
         load[r] += sizes[j]
         if r == rank:
             mine.append(int(j))
-    bufs = []
-    for j in mine:
-        rd = make_reads(workload, idx, seed=1000 + j, n_reads=int(sizes[j]))
-        bufs.append((j, torch.from_numpy(np.diff(rd.read_ptr).astype(np.uint16)).pin_memory(), torch.from_numpy(rd.read_tid).pin_memory(),
-                     None if idx.nF == 1 else torch.from_numpy(rd.read_fraglen.astype(np.uint16)).pin_memory(), int(rd.read_fraglen[0])))
-        del rd
+    # whatever happens on one rank, every rank reaches the collectives below (a rank that skipped them would leave the others waiting)
+    bufs, err = [], None
+    try:
+        for j in mine:
+            rd = make_reads(workload, idx, seed=1000 + j, n_reads=int(sizes[j]))
+            bufs.append((j, torch.from_numpy(np.diff(rd.read_ptr).astype(np.uint16)).pin_memory(), torch.from_numpy(rd.read_tid).pin_memory(),
+                         None if idx.nF == 1 else torch.from_numpy(rd.read_fraglen.astype(np.uint16)).pin_memory(), int(rd.read_fraglen[0])))
+            del rd
+    except Exception as e:
+        err = repr(e)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    iters, h2d, chk = 0, 0, 0.0
-    for j, p, t, f, f0 in bufs:
-        s = ix.sample()
-        s.count_compact(p, t, f, f0)                     # the compact wire form: uint16 lengths, tids, uint16 / no fragment lengths
-        r = s.solve()
-        s.close()
-        iters += int(r["n_iter"])
-        h2d += p.numel() * 2 + t.numel() * 4 + (0 if f is None else f.numel() * 2)
-        chk += float(r["tpm"].sum())
-        assert r["final_delta"] <= 1.0
-    ctx.synchronize()
+    iters, h2d, chk, done, not_conv = 0, 0, 0.0, 0, 0
+    try:
+        for j, p, t, f, f0 in bufs:
+            s = ix.sample()
+            s.count_compact(p, t, f, f0)                     # the compact wire form: uint16 lengths, tids, uint16 / no fragment lengths
+            r = s.solve()
+            s.close()
+            iters += int(r["n_iter"])
+            h2d += p.numel() * 2 + t.numel() * 4 + (0 if f is None else f.numel() * 2)
+            chk += float(r["tpm"].sum())
+            done += 1
+            not_conv += 0 if r["final_delta"] <= 1.0 else 1
+        ctx.synchronize()
+    except Exception as e:
+        err = err or repr(e)
     mine_s = time.perf_counter() - t0
+    if err is not None:
+        note(f"m64 leg failed on this rank: {err}")
     tt = torch.tensor([mine_s], dtype=torch.float64, device="cuda")
-    ss = torch.tensor([float(iters), float(h2d), float(len(bufs))], dtype=torch.float64, device="cuda")
+    ss = torch.tensor([float(iters), float(h2d), float(done), float(not_conv), 0.0 if err is None else 1.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ss)
     sec = float(tt.item())
-    iters_all, h2d_all, n_all = ss.tolist()
+    iters_all, h2d_all, n_all, nc_all, n_err = ss.tolist()
+    if n_err > 0:
+        return {"workload": workload, "samples": int(n_all), "error": err or "a rank failed (its stderr has the exception)"}
     return {"workload": f"{workload}: {n_samples} samples (seeds 1000..{999 + n_samples}) sharing one index, 20-40M reads each", "samples": int(n_all), "samples_per_gpu": per_gpu,
             "assignment": "largest first to the least loaded GPU (LPT)", "seconds": sec, "samples_per_min": 60.0 * n_all / sec, "em_iterations": int(iters_all),
-            "h2d_bytes": int(h2d_all), "what": "pinned host read lists -> counts -> model -> EM to convergence -> FPKM/TPM on the host; max over ranks"}
+            "h2d_bytes": int(h2d_all), "not_converged": int(nc_all),
+            "what": "pinned host read lists -> counts -> model -> EM to convergence -> FPKM/TPM on the host; max over ranks"}
 
 
 def bcast_workload(name, seed, rank, torch, dist):
@@ -777,6 +790,7 @@ def main():
         try:
             extras["m64"] = m64_leg(ctx, ix, idx, args.workload, rank, world, torch, dist, args.m64_per_gpu)
         except Exception as e:
+            note(f"m64 leg: {e!r}")
             extras["m64"] = {"error": repr(e)}
         note("m64 leg done")
         if rank == 0:
