@@ -8,7 +8,8 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "emsar_b200", "csrc", "_obj")
-KERNELS = [("em_psum.o", "k_em_psum"), ("prep.o", "k_adjeuma_stream"), ("count.o", "k_count"), ("em.o", "k_em_persistentILi3E")]
+KERNELS = [("em_psum.o", "k_em_psumILi0E"), ("prep.o", "k_adjeuma_stream"), ("count.o", "k_count"), ("em.o", "k_em_persistentILi3E"),
+           ("build.o", "k_window_hash"), ("build.o", "k_occ_peILb0E"), ("build.o", "k_run_heads")]
 
 for obj, pat in KERNELS:
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(OBJ, obj)], capture_output=True, text=True).stdout
@@ -18,14 +19,14 @@ for obj, pat in KERNELS:
         if m:
             cur = m.group(1)
             body[cur] = []
-        elif cur and re.search(r"/\*[0-9a-f]{4}\*/", line):
+        elif cur and re.search(r"/\*[0-9a-f]{4,6}\*/", line):
             body[cur].append(line)
     for fn, lines in body.items():
         if pat not in fn:
             continue
         ops = collections.Counter()
         for l in lines:
-            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", l)
+            m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", l)
             if m:
                 ops[m.group(1)] += 1
         fam = collections.Counter()
