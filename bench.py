@@ -524,9 +524,10 @@ def sharded_child(args, rank, world, local):
     dist.destroy_process_group()
 
 
-def run_sharded_children(names, rank, world, local, budget_s):
+def run_sharded_children(names, rank, world, local, budget_s, agree=None):
     """Every rank starts one child per workload (same RANK / WORLD_SIZE, the master port shifted) and waits for it at most budget_s[name]
-    seconds; a child that is still running then is killed (by its pid). Rank 0 collects the children's results."""
+    seconds; a child that is still running then is killed (by its pid). Rank 0 collects the children's results. `agree(failed)` returns
+    whether the child failed on ANY rank (an all-reduce over the parents), so that all ranks take the same decision about going on."""
     import subprocess
     import tempfile
     out = []
@@ -548,6 +549,8 @@ def run_sharded_children(names, rank, world, local, budget_s):
             pr.wait()
             err = f"no result within {budget_s[name]} s at {world} GPUs (child stopped)"
         note(f"class_sharded {name}: {'ok' if err is None else err}")
+        if agree is not None and agree(err is not None) and err is None:
+            err = "the child of another rank did not come back"
         o = None
         if rank == 0:
             if err is None and os.path.exists(leg_out):
@@ -805,8 +808,15 @@ def main():
         # ONE sample over the N GPUs: in child processes (their own process group), a small case first; see run_sharded_children
         names = [SELFTEST] + [w for w in args.sharded_workloads.split(",") if w]
         budget = {SELFTEST: 150, "config2_human_se": 240, "config5_full": 360}
+        if os.environ.get("EMSAR_BENCH_CHILD_LIMIT_S"):                       # tests: one short limit for every child
+            budget = {n: int(os.environ["EMSAR_BENCH_CHILD_LIMIT_S"]) for n in names}
         torch.cuda.empty_cache()
-        res = run_sharded_children(names, rank, world, local, {n: budget.get(n, 300) for n in names})
+        def agree(failed):
+            fl = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+            return bool(fl.item() > 0)
+
+        res = run_sharded_children(names, rank, world, local, {n: budget.get(n, 300) for n in names}, agree)
         dist.barrier()
         if rank == 0:
             extras["class_sharded"] = [o for o in res if o is not None]

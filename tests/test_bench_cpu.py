@@ -147,8 +147,9 @@ def _mock_everything():
     return bench
 
 
-def _main_rank(rank, world, port, path):
-    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT=str(port), MASTER_ADDR="127.0.0.1", EMSAR_BENCH_FAKE_LEG="ok")
+def _main_rank(rank, world, port, path, mode="ok"):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT=str(port), MASTER_ADDR="127.0.0.1", EMSAR_BENCH_FAKE_LEG=mode,
+                      EMSAR_BENCH_CHILD_LIMIT_S="5")
     bench = _mock_everything()
     sys.argv = ["bench.py", "--gpus", str(world), "--workload", "tiny", "--steps", "2", "--warmup", "1", "--em-iters", "5", "--m64-per-gpu", "1"]
     if rank == 0:
@@ -174,3 +175,19 @@ def test_two_rank_control_flow_over_gloo(tmp_path):
     assert line["m64"]["samples"] == 2 and "error" not in line["m64"]
     assert [o["workload"] for o in line["class_sharded"]] == ["small", "config2_human_se", "config5_full"]
     assert "incomplete" not in line
+
+
+def test_two_rank_run_survives_a_child_that_never_returns(tmp_path):
+    ctx = mp.get_context("spawn")
+    path = str(tmp_path / "rank0.out")
+    ps = [ctx.Process(target=_main_rank, args=(r, 2, 29901, path, "hang")) for r in range(2)]
+    t0 = time.perf_counter()
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert time.perf_counter() - t0 < 120
+    line = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][0])
+    assert line["n_gpus"] == 2 and line["value"] > 0 and "error" not in line["m64"]
+    assert len(line["class_sharded"]) == 1 and "no result within 5 s" in line["class_sharded"][0]["error"]
