@@ -233,6 +233,51 @@ def file_to_file_twin(cores, device):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def index_build_leg(cores, device, transcripts=20000):
+    """the rsh index of a generated transcriptome (gene families over a shared exon pool, 1.7K bases per transcript) built three
+    ways - classes constructed on the device (`emsar-build --device`), by the host builder, and by the unmodified reference `emsar-build`
+    (oracle/_ref, on a quarter of the transcripts: it is the slow one) - with the files compared byte for byte (SHA-256)."""
+    import hashlib
+    import shutil
+    import tempfile
+    from profiles import build_bench as bb
+    mine = os.path.join(ROOT, "emsar_b200", "bin", "emsar-build")
+    ref = os.path.join(ROOT, "oracle", "_ref", "emsar-build")
+    d = tempfile.mkdtemp(prefix="emsar_build_")
+
+    def run(tool, extra, fa, tag, limit):
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([tool, "-q"] + extra + [fa, "50", os.path.join(d, tag), "x"], capture_output=True, text=True, timeout=limit,
+                               env=dict(os.environ, EMSAR_BUILD_TIMING="1"))
+        except subprocess.TimeoutExpired:
+            return {"error": f"over {limit} s"}
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        data = open(os.path.join(d, tag, "x.rsh"), "rb").read()
+        return {"seconds": dt, "sha256": hashlib.sha256(data).hexdigest()[:16], "classes": data.count(b"\n"),
+                "stages": [l.split(": ", 1)[1] for l in r.stderr.splitlines() if l.startswith("build timing")]}
+
+    try:
+        fa, fa4 = os.path.join(d, "t.fa"), os.path.join(d, "t4.fa")
+        bases = bb.make_fasta(fa, transcripts)
+        bases4 = bb.make_fasta(fa4, max(transcripts // 4, 1))
+        out = {"workload": f"single-end unstranded, read length 50, {transcripts} transcripts / {bases} bases (reference: {max(transcripts // 4, 1)} / {bases4})"}
+        run(mine, ["--device", str(device)], fa4, "warm", 300)                     # CUDA start-up, page cache
+        out["device"] = run(mine, ["--device", str(device)], fa, "dev", 600)
+        out["host"] = run(mine, ["-p", str(cores)], fa, "host", 600)
+        out["device_quarter"] = run(mine, ["--device", str(device)], fa4, "dev4", 300)
+        out["reference_quarter"] = run(ref, [], fa4, "ref4", 120) if os.path.exists(ref) else None
+        out["identical_device_host"] = out["device"].get("sha256") is not None and out["device"].get("sha256") == out["host"].get("sha256")
+        if out["reference_quarter"] is not None:
+            out["identical_device_reference"] = out["device_quarter"].get("sha256") is not None and \
+                out["device_quarter"].get("sha256") == out["reference_quarter"].get("sha256")
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path: no EM exists in parklab/emsar, so the
     metric 'EM iterations/s' is timed on the oracle port (same update as the CUDA kernel) with all host threads;
@@ -831,6 +876,12 @@ def main():
             extras["file_to_file"] = file_to_file_twin(os.cpu_count() or 1, local) if not args.no_ref_binary else None
         except Exception as e:
             extras["file_to_file"] = {"error": repr(e)}
+        note("file-to-file twin done")
+        try:
+            extras["index_build"] = index_build_leg(os.cpu_count() or 1, local)
+        except Exception as e:
+            extras["index_build"] = {"error": repr(e)}
+        note("index construction leg done")
 
     if rank == 0:
         line.update(extras)

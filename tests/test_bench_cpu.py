@@ -107,6 +107,8 @@ def test_single_gpu_control_flow_prints_one_complete_line(monkeypatch, capsys):
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
     monkeypatch.setattr(bench, "file_to_file_twin", lambda cores, dev: {"fake": True})
+    real_leg = bench.index_build_leg
+    monkeypatch.setattr(bench, "index_build_leg", lambda cores, dev: real_leg(cores, dev, transcripts=400))
     monkeypatch.setattr(bench, "OTHER_WORKLOADS", ["tiny"])
     monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "tiny", "--steps", "2", "--warmup", "1", "--em-iters", "5", "--m64-per-gpu", "1", "--others", "tiny"])
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
@@ -119,10 +121,12 @@ def test_single_gpu_control_flow_prints_one_complete_line(monkeypatch, capsys):
     assert len(out) == 1
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
-                "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "to_convergence", "m64", "kernels", "other_workloads", "file_to_file"):
+                "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "to_convergence", "m64", "kernels", "other_workloads", "file_to_file", "index_build"):
         assert key in line, key
     assert line["n_gpus"] == 1 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert "error" not in line["m64"] and "error" not in line["kernels"][0] and "error" not in line["other_workloads"][0], line
+    ib = line["index_build"]                 # no GPU here: the device arms fail loudly, the host builder and the reference agree with each other
+    assert "no CUDA device" in ib["device"]["error"] and ib["host"]["classes"] > 100 and "sha256" in ib["reference_quarter"]
     assert "incomplete" not in line
 
 
