@@ -19,8 +19,14 @@ Further objects of the JSON line (all measured in the same run, none of them ins
                    the 100M-read north-star sample, config2 under random transcript names): it/s, roofline fraction, kernel variant
   m64              BASELINE configs[3]: a -M batch of 8 samples per GPU (64 on 8 GPUs) sharing one index, largest-first assignment,
                    host buffers -> results: samples/min
-  class_sharded    N > 1 only: ONE sample sharded over the N GPUs (BASELINE configs[2]) with its parity against the single-GPU solve
+  class_sharded    N > 1 only: ONE sample sharded over the N GPUs (BASELINE configs[2]) with its parity against the single-GPU solve. Each
+                   workload runs in child processes (one per GPU, their own process group) under a time limit, a small case first: a
+                   stall of the cross-GPU kernel at some GPU count shows up as {"error": ...} here instead of a run without a line
   file_to_file     N = 1 only: this repo's `emsar` command and the unmodified reference binary on the same .rsh + bowtie text files
+  index_build      N = 1 only: the rsh index of a generated transcriptome constructed on the device, by the host builder and by the
+                   reference's emsar-build, files compared
+Progress goes to stderr per rank ("[bench r<rank> +<seconds>s] ..."). A run that has not printed its line after EMSAR_BENCH_LIMIT_S
+(default 1200) seconds prints the headline it has, marked "incomplete", and ends.
 """
 from __future__ import annotations
 
