@@ -588,6 +588,8 @@ def run_sharded_children(names, rank, world, local, budget_s, agree=None):
         if rank == 0 and os.path.exists(leg_out):
             os.remove(leg_out)
         env = dict(os.environ, MASTER_PORT=str(port + 17 + k), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local))
+        if rank == 0:
+            env["OMP_NUM_THREADS"] = str(min(16, os.cpu_count() or 1))       # rank 0 generates the workload; torchrun had set 1
         cmd = [sys.executable, os.path.abspath(__file__), "--leg", "class_sharded", "--gpus", str(world), "--sharded-workloads", name, "--leg-out", leg_out]
         note(f"class_sharded {name}: child started (limit {budget_s[name]} s)")
         pr = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL)
